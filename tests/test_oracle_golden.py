@@ -79,8 +79,9 @@ def test_two_adam_steps_match_reference(sail_golden):
 
 
 def test_beam_decode_matches_reference(sail_golden):
-    name, arr, meta, params, _ = sail_golden
-    p = _f64(params)
+    name, arr, meta, _, _ = sail_golden
+    # make_golden.py runs the beam search AFTER its two Adam steps: use those weights
+    p = {k[len("adam_param::"):]: v.astype(np.float64) for k, v in arr.items() if k.startswith("adam_param::")}
     cfg = meta["cfg"]
 
     def dec_fn(z, prefix):
