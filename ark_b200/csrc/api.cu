@@ -1,0 +1,58 @@
+// Library-level state of libarkb200: thread-local error text, launch counter, TMA descriptor encoder lookup.
+#include "common.cuh"
+#include "tmap.cuh"
+#include <mutex>
+
+namespace ark {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(ARK_E_NODRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstride[1] = {ld * 2};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ARK_E_SHAPE, "cuTensorMapEncodeTiled failed (CUresult %d) dims=(%llu,%llu) ld=%llu box=(%u,%u)", (int)r,
+                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+  return 0;
+}
+
+}  // namespace ark
+
+extern "C" int ark_abi_version(void) { return ARK_ABI_VERSION; }
+extern "C" const char* ark_last_error(void) { return ark::g_err; }
+extern "C" int64_t ark_launch_count(void) { return ark::g_launches; }
+extern "C" void ark_launch_count_reset(void) { ark::g_launches = 0; }

@@ -1,0 +1,283 @@
+// Elementwise / reduction helpers of the ELBO step: activation backward, bias gradients (column sums),
+// residual add, casts, inter-layer dropout, and K10 dense Adam over the flat parameter buffer
+// (torch.optim.Adam defaults, kgvae/experiments/ablation_study.py:571).  All HBM-bound, 128-bit accesses.
+#include "common.cuh"
+
+namespace ark {
+
+template <int MODE>  // 0: gelu'(aux)   1: 1 - aux^2 (tanh, aux = output)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dact, const float* __restrict__ aux,
+                                                      int64_t n, float* __restrict__ dpre,
+                                                      uint16_t* __restrict__ dpre_bf16) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float a[4], g[4], o[4];
+  if (i + 4 <= n) {
+    const float4 av = *reinterpret_cast<const float4*>(aux + i), gv = *reinterpret_cast<const float4*>(dact + i);
+    a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+    g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+  } else {
+    for (int k = 0; k < 4; ++k) {
+      a[k] = (i + k < n) ? aux[i + k] : 0.f;
+      g[k] = (i + k < n) ? dact[i + k] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = g[k] * (MODE == 0 ? gelu_erf_grad(a[k]) : (1.f - a[k] * a[k]));
+  if (i + 4 <= n) {
+    if (dpre) *reinterpret_cast<float4*>(dpre + i) = make_float4(o[0], o[1], o[2], o[3]);
+    if (dpre_bf16) {
+      uint2 p;
+      p.x = pack_bf16x2(o[0], o[1]);
+      p.y = pack_bf16x2(o[2], o[3]);
+      *reinterpret_cast<uint2*>(dpre_bf16 + i) = p;
+    }
+  } else {
+    for (int k = 0; k < 4 && i + k < n; ++k) {
+      if (dpre) dpre[i + k] = o[k];
+      if (dpre_bf16) dpre_bf16[i + k] = f32_to_bf16_bits(o[k]);
+    }
+  }
+}
+
+// column sums: block = 32 x 8 threads, each thread owns one column (stride-1 across lanes, coalesced) and
+// walks rows ty, ty+8*gridDim.y, ...; 8 partials reduced through smem, one atomicAdd per column per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int64_t M, int N, int64_t ld,
+                                                     float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (col < N) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < M; r += (int64_t)gridDim.y * 8) {
+      if constexpr (sizeof(T) == 2)
+        acc += bf16_bits_to_f32(X[r * ld + col]);
+      else
+        acc += X[r * ld + col];
+    }
+  }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][tx];
+    atomicAdd(out + col, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                  float* __restrict__ y, uint16_t* __restrict__ yb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = a[i] + (b ? b[i] : 0.f);
+  if (y) y[i] = v;
+  if (yb) yb[i] = f32_to_bf16_bits(v);
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = seed
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restrict__ x, int64_t n, float p,
+                                                          uint64_t seed, uint64_t offset, float* __restrict__ y,
+                                                          uint16_t* __restrict__ yb, uint8_t* __restrict__ mask) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = q * 4;
+  if (i >= n) return;
+  const uint64_t c = offset + (uint64_t)q;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  const float scale = 1.f / (1.f - p);
+  for (int k = 0; k < 4 && i + k < n; ++k) {
+    const float u = (float)(rr[k] >> 8) * (1.f / 16777216.f);  // [0,1)
+    const bool keep = u >= p;
+    const float v = keep ? x[i + k] * scale : 0.f;
+    if (mask) mask[i + k] = keep ? 1 : 0;
+    if (y) y[i + k] = v;
+    if (yb) yb[i + k] = f32_to_bf16_bits(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                                          int64_t n, float scale, float* __restrict__ dx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dx[i] = mask[i] ? dy[i] * scale : 0.f;
+}
+
+// Adam: 16 B p + 16 B g + 16 B m + 16 B v read, 16+16+16 written (+8 B bf16 shadow) per 4 parameters.
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        uint16_t* __restrict__ shadow, int64_t n, float step_size,
+                                                        float beta1, float beta2, float eps, float inv_sqrt_bc2,
+                                                        float grad_scale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      float4 pv = *reinterpret_cast<float4*>(p + i);
+      const float4 gv = *reinterpret_cast<const float4*>(g + i);
+      float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+      float pp[4] = {pv.x, pv.y, pv.z, pv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+      float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vv4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = gg[k] * grad_scale;
+        mm[k] = beta1 * mm[k] + (1.f - beta1) * gk;
+        vv4[k] = beta2 * vv4[k] + (1.f - beta2) * gk * gk;
+        pp[k] -= step_size * mm[k] / (sqrtf(vv4[k]) * inv_sqrt_bc2 + eps);
+      }
+      *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(v + i) = make_float4(vv4[0], vv4[1], vv4[2], vv4[3]);
+      if (shadow) {
+        uint2 s;
+        s.x = pack_bf16x2(pp[0], pp[1]);
+        s.y = pack_bf16x2(pp[2], pp[3]);
+        *reinterpret_cast<uint2*>(shadow + i) = s;
+      }
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        const float gk = g[j] * grad_scale;
+        const float mj = beta1 * m[j] + (1.f - beta1) * gk;
+        const float vj = beta2 * v[j] + (1.f - beta2) * gk * gk;
+        const float pj = p[j] - step_size * mj / (sqrtf(vj) * inv_sqrt_bc2 + eps);
+        m[j] = mj; v[j] = vj; p[j] = pj;
+        if (shadow) shadow[j] = f32_to_bf16_bits(pj);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, int64_t n, uint16_t* __restrict__ y) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      uint2 s;
+      s.x = pack_bf16x2(v.x, v.y);
+      s.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(y + i) = s;
+    } else {
+      for (int64_t j = i; j < n; ++j) y[j] = f32_to_bf16_bits(x[j]);
+    }
+  }
+}
+
+}  // namespace ark
+
+using namespace ark;
+
+static inline unsigned blocks_for(int64_t n, int per_block, int64_t cap) {
+  int64_t b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (cap > 0 && b > cap) b = cap;
+  return (unsigned)b;
+}
+
+extern "C" int ark_gelu_bwd(const float* dact, const float* pre, int64_t n, float* dpre, uint16_t* dpre_bf16,
+                            void* stream) {
+  ARK_REQUIRE(dact && pre && (dpre || dpre_bf16), ARK_E_BADARG, "gelu_bwd: null pointer");
+  ARK_REQUIRE(aligned16(dact) && aligned16(pre) && (!dpre || aligned16(dpre)) && (!dpre_bf16 || aligned16(dpre_bf16)),
+              ARK_E_ALIGN, "gelu_bwd: 16-byte alignment");
+  if (n <= 0) return 0;
+  act_bwd_kernel<0><<<blocks_for(n, 1024, 0), 256, 0, (cudaStream_t)stream>>>(dact, pre, n, dpre, dpre_bf16);
+  return launched("gelu_bwd");
+}
+
+extern "C" int ark_tanh_bwd(const float* dh, const float* h, int64_t n, float* dpre, uint16_t* dpre_bf16,
+                            void* stream) {
+  ARK_REQUIRE(dh && h && (dpre || dpre_bf16), ARK_E_BADARG, "tanh_bwd: null pointer");
+  ARK_REQUIRE(aligned16(dh) && aligned16(h) && (!dpre || aligned16(dpre)) && (!dpre_bf16 || aligned16(dpre_bf16)),
+              ARK_E_ALIGN, "tanh_bwd: 16-byte alignment");
+  if (n <= 0) return 0;
+  act_bwd_kernel<1><<<blocks_for(n, 1024, 0), 256, 0, (cudaStream_t)stream>>>(dh, h, n, dpre, dpre_bf16);
+  return launched("tanh_bwd");
+}
+
+extern "C" int ark_colsum(const void* X, int dtype, int64_t M, int64_t N, int64_t ld, float* out, int accumulate,
+                          void* stream) {
+  ARK_REQUIRE(X && out, ARK_E_BADARG, "colsum: null pointer");
+  ARK_REQUIRE(M >= 0 && N > 0 && ld >= N, ARK_E_BADARG, "colsum: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s);
+    if (e != cudaSuccess) return fail((int)e, "colsum: memset: %s", cudaGetErrorString(e));
+  }
+  if (M == 0) return 0;
+  int64_t gy = (M + 63) / 64;
+  const int64_t gx = (N + 31) / 32;
+  const int64_t want = 4 * kNumSMs;  // enough CTAs to cover the machine, few enough atomics
+  if (gx * gy > want) gy = (want + gx - 1) / gx;
+  if (gy < 1) gy = 1;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  if (dtype == ARK_BF16)
+    colsum_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)X, M, (int)N, ld, out);
+  else if (dtype == ARK_F32)
+    colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)X, M, (int)N, ld, out);
+  else
+    return fail(ARK_E_BADARG, "colsum: unknown dtype %d", dtype);
+  return launched("colsum");
+}
+
+extern "C" int ark_add_f32(const float* a, const float* b, int64_t n, float* y, uint16_t* y_bf16, void* stream) {
+  ARK_REQUIRE(a && (y || y_bf16), ARK_E_BADARG, "add_f32: null pointer");
+  if (n <= 0) return 0;
+  add_kernel<<<blocks_for(n, 256, 0), 256, 0, (cudaStream_t)stream>>>(a, b, n, y, y_bf16);
+  return launched("add_f32");
+}
+
+extern "C" int ark_cast_f32_to_bf16(const float* x, int64_t n, uint16_t* y, void* stream) {
+  ARK_REQUIRE(x && y, ARK_E_BADARG, "cast: null pointer");
+  ARK_REQUIRE(aligned16(x) && aligned16(y), ARK_E_ALIGN, "cast: 16-byte alignment");
+  if (n <= 0) return 0;
+  cast_bf16_kernel<<<blocks_for(n, 1024, 8 * kNumSMs), 256, 0, (cudaStream_t)stream>>>(x, n, y);
+  return launched("cast_f32_to_bf16");
+}
+
+extern "C" int ark_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, float* y,
+                               uint16_t* y_bf16, uint8_t* mask, void* stream) {
+  ARK_REQUIRE(x && (y || y_bf16), ARK_E_BADARG, "dropout_fwd: null pointer");
+  ARK_REQUIRE(p >= 0.f && p < 1.f, ARK_E_BADARG, "dropout_fwd: p must be in [0,1)");
+  if (n <= 0) return 0;
+  dropout_fwd_kernel<<<blocks_for((n + 3) / 4, 256, 0), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y,
+                                                                                       y_bf16, mask);
+  return launched("dropout_fwd");
+}
+
+extern "C" int ark_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, void* stream) {
+  ARK_REQUIRE(dy && mask && dx, ARK_E_BADARG, "dropout_bwd: null pointer");
+  ARK_REQUIRE(p >= 0.f && p < 1.f, ARK_E_BADARG, "dropout_bwd: p must be in [0,1)");
+  if (n <= 0) return 0;
+  dropout_bwd_kernel<<<blocks_for(n, 256, 0), 256, 0, (cudaStream_t)stream>>>(dy, mask, n, 1.f / (1.f - p), dx);
+  return launched("dropout_bwd");
+}
+
+extern "C" int ark_adam_flat(float* p, const float* g, float* m, float* v, uint16_t* shadow, int64_t n, float lr,
+                             float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream) {
+  ARK_REQUIRE(p && g && m && v, ARK_E_BADARG, "adam_flat: null pointer");
+  ARK_REQUIRE(step >= 1, ARK_E_BADARG, "adam_flat: step is 1-based");
+  ARK_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || aligned16(shadow)),
+              ARK_E_ALIGN, "adam_flat: 16-byte alignment");
+  if (n <= 0) return 0;
+  // torch.optim.Adam: step_size = lr / bc1; denom = sqrt(v)/sqrt(bc2) + eps   (computed in double on the host)
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  adam_flat_kernel<<<blocks_for(n, 1024, 16 * kNumSMs), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, shadow, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
+  return launched("adam_flat");
+}

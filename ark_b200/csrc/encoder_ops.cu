@@ -1,0 +1,201 @@
+// K1/K2: entity/relation embedding gather fused with masked mean-pooling, and its scatter-add
+// backward.  K4: reparameterisation + analytic KL, forward and backward.
+// Replaces kgvae/model/models.py:47-58 (gather/concat/mask/mean), :62-63 (clamp, reparam) and
+// :199-200 (kl_mean) of the reference.  All HBM-bound: 128-bit loads, one pass, nothing staged.
+#include "common.cuh"
+
+namespace ark {
+
+// grid (B, 3): CTA (b, slot) pools column block `slot` (head | relation | tail) of graph perm[b].
+// Each thread owns float4 columns c, c+blockDim, ...; triples are read through L1 (broadcast).
+template <int UNROLL>
+__global__ void __launch_bounds__(256) gather_pool_fwd_kernel(
+    const int64_t* __restrict__ triples, const int32_t* __restrict__ perm, const float* __restrict__ E,
+    const float* __restrict__ R, int T, int d, long long pad_rid, float* __restrict__ g,
+    uint16_t* __restrict__ g_bf16, float* __restrict__ inv_cnt) {
+  const int b = blockIdx.x, slot = blockIdx.y;
+  const int src = perm ? perm[b] : b;
+  const int64_t* tri = triples + (int64_t)src * T * 3;
+  const float* table = (slot == 1) ? R : E;
+  const int d4 = d >> 2;
+
+  // number of valid triples (uniform over the CTA)
+  int cnt = 0;
+  if (pad_rid >= 0) {
+    for (int t = 0; t < T; ++t) cnt += (tri[t * 3 + 1] != pad_rid);
+  } else {
+    cnt = T;
+  }
+  const float inv = 1.f / (float)(cnt > 0 ? cnt : 1);
+  if (slot == 0 && threadIdx.x == 0) inv_cnt[b] = inv;
+
+  for (int c = threadIdx.x; c < d4; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int t = 0;
+    for (; t + UNROLL <= T; t += UNROLL) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t rel = tri[(t + u) * 3 + 1];
+        const bool ok = (pad_rid < 0) || (rel != pad_rid);
+        const int64_t idx = tri[(t + u) * 3 + slot];
+        v[u] = ok ? __ldg(reinterpret_cast<const float4*>(table + idx * d) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+    }
+    for (; t < T; ++t) {
+      const int64_t rel = tri[t * 3 + 1];
+      if (pad_rid >= 0 && rel == pad_rid) continue;
+      const int64_t idx = tri[t * 3 + slot];
+      const float4 v = __ldg(reinterpret_cast<const float4*>(table + idx * d) + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    const int64_t o = (int64_t)b * 3 * d + (int64_t)slot * d + c * 4;
+    if (g) *reinterpret_cast<float4*>(g + o) = acc;
+    if (g_bf16) {
+      uint2 p;
+      p.x = pack_bf16x2(acc.x, acc.y);
+      p.y = pack_bf16x2(acc.z, acc.w);
+      *reinterpret_cast<uint2*>(g_bf16 + o) = p;
+    }
+  }
+}
+
+// grid (B, 3): every valid triple of graph perm[b] receives the SAME slice dg[b, slot]/cnt_b, so the
+// value is loaded once into registers and pushed with one 16-byte L2 reduction per (triple, float4).
+__global__ void __launch_bounds__(256) gather_pool_bwd_kernel(
+    const float* __restrict__ dg, const int64_t* __restrict__ triples, const int32_t* __restrict__ perm,
+    const float* __restrict__ inv_cnt, int T, int d, long long pad_rid, long long pad_eid,
+    float* __restrict__ dE, float* __restrict__ dR) {
+  const int b = blockIdx.x, slot = blockIdx.y;
+  const int src = perm ? perm[b] : b;
+  const int64_t* tri = triples + (int64_t)src * T * 3;
+  float* table = (slot == 1) ? dR : dE;
+  const int d4 = d >> 2;
+  const float inv = inv_cnt[b];
+  for (int c = threadIdx.x; c < d4; c += blockDim.x) {
+    float4 v = *reinterpret_cast<const float4*>(dg + (int64_t)b * 3 * d + (int64_t)slot * d + c * 4);
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    for (int t = 0; t < T; ++t) {
+      const int64_t rel = tri[t * 3 + 1];
+      if (pad_rid >= 0 && rel == pad_rid) continue;
+      const int64_t idx = tri[t * 3 + slot];
+      if (slot != 1 && idx == pad_eid) continue;  // padding_idx row never accumulates
+      red_add_v4(table + idx * d + c * 4, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(
+    const float* __restrict__ heads, int ld_heads, const float* __restrict__ eps, const int32_t* __restrict__ perm,
+    int B, int dz, int clamp_logv, float kl_scale, float* __restrict__ z, uint16_t* __restrict__ z_bf16,
+    int ld_zb, float* __restrict__ kl_acc) {
+  __shared__ float red[33];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (i < B * dz) {
+    const int b = i / dz, j = i - b * dz;
+    const float mu = heads[(int64_t)b * ld_heads + j];
+    float lv = heads[(int64_t)b * ld_heads + dz + j];
+    if (clamp_logv) lv = fminf(fmaxf(lv, -10.f), 10.f);
+    const float e = eps[(int64_t)(perm ? perm[b] : b) * dz + j];
+    const float zz = fmaf(e, expf(0.5f * lv), mu);
+    z[i] = zz;
+    if (z_bf16) z_bf16[(int64_t)b * ld_zb + j] = f32_to_bf16_bits(zz);
+    term = -0.5f * (1.f + lv - mu * mu - expf(lv));
+  }
+  const float s = block_sum(term, red);
+  if (threadIdx.x == 0 && kl_acc) atomicAdd(kl_acc, s * kl_scale);
+}
+
+__global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(
+    const float* __restrict__ heads, int ld_heads, const float* __restrict__ eps, const int32_t* __restrict__ perm,
+    const float* __restrict__ dz_in, int B, int dz, int clamp_logv, float bk, float* __restrict__ dheads,
+    uint16_t* __restrict__ dheads_bf16, int ld_dh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dz) return;
+  const int b = i / dz, j = i - b * dz;
+  const float mu = heads[(int64_t)b * ld_heads + j];
+  const float raw = heads[(int64_t)b * ld_heads + dz + j];
+  float lv = raw;
+  bool pass = true;
+  if (clamp_logv) {
+    lv = fminf(fmaxf(raw, -10.f), 10.f);
+    pass = (raw >= -10.f) && (raw <= 10.f);  // torch.clamp passes the gradient on the closed interval
+  }
+  const float e = eps[(int64_t)(perm ? perm[b] : b) * dz + j];
+  const float dzv = dz_in[i];
+  const float dmu = fmaf(bk, mu, dzv);
+  float dlv = 0.5f * dzv * e * expf(0.5f * lv) + 0.5f * bk * (expf(lv) - 1.f);
+  if (!pass) dlv = 0.f;
+  const int64_t o = (int64_t)b * ld_dh;
+  if (dheads) {
+    dheads[o + j] = dmu;
+    dheads[o + dz + j] = dlv;
+  }
+  if (dheads_bf16) {
+    dheads_bf16[o + j] = f32_to_bf16_bits(dmu);
+    dheads_bf16[o + dz + j] = f32_to_bf16_bits(dlv);
+  }
+}
+
+}  // namespace ark
+
+using namespace ark;
+
+extern "C" int ark_gather_pool_fwd(const int64_t* triples, const int32_t* perm, const float* E, const float* R,
+                                   int64_t B, int64_t T, int64_t d, int64_t pad_rid, float* g, uint16_t* g_bf16,
+                                   float* inv_cnt, void* stream) {
+  ARK_REQUIRE(triples && E && R && inv_cnt && (g || g_bf16), ARK_E_BADARG, "gather_pool_fwd: null pointer");
+  ARK_REQUIRE(B > 0 && T > 0 && d > 0, ARK_E_BADARG, "gather_pool_fwd: B,T,d must be positive");
+  ARK_REQUIRE(d % 4 == 0, ARK_E_SHAPE, "gather_pool_fwd: d=%lld must be a multiple of 4", (long long)d);
+  ARK_REQUIRE(aligned16(E) && aligned16(R) && (!g || aligned16(g)) && (!g_bf16 || aligned16(g_bf16)), ARK_E_ALIGN,
+              "gather_pool_fwd: tables/outputs must be 16-byte aligned");
+  const int threads = (int)((d / 4 + 31) / 32 * 32 < 256 ? (d / 4 + 31) / 32 * 32 : 256);
+  dim3 grid((unsigned)B, 3);
+  gather_pool_fwd_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>(triples, perm, E, R, (int)T, (int)d,
+                                                                      (long long)pad_rid, g, g_bf16, inv_cnt);
+  return launched("gather_pool_fwd");
+}
+
+extern "C" int ark_gather_pool_bwd(const float* dg, const int64_t* triples, const int32_t* perm,
+                                   const float* inv_cnt, int64_t B, int64_t T, int64_t d, int64_t pad_rid,
+                                   int64_t pad_eid, float* dE, float* dR, void* stream) {
+  ARK_REQUIRE(dg && triples && inv_cnt && dE && dR, ARK_E_BADARG, "gather_pool_bwd: null pointer");
+  ARK_REQUIRE(B > 0 && T > 0 && d > 0, ARK_E_BADARG, "gather_pool_bwd: B,T,d must be positive");
+  ARK_REQUIRE(d % 4 == 0, ARK_E_SHAPE, "gather_pool_bwd: d must be a multiple of 4");
+  ARK_REQUIRE(aligned16(dg) && aligned16(dE) && aligned16(dR), ARK_E_ALIGN, "gather_pool_bwd: 16-byte alignment");
+  const int threads = (int)((d / 4 + 31) / 32 * 32 < 256 ? (d / 4 + 31) / 32 * 32 : 256);
+  dim3 grid((unsigned)B, 3);
+  gather_pool_bwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(dg, triples, perm, inv_cnt, (int)T, (int)d,
+                                                                    (long long)pad_rid, (long long)pad_eid, dE, dR);
+  return launched("gather_pool_bwd");
+}
+
+extern "C" int ark_reparam_kl_fwd(const float* heads, int64_t ld_heads, const float* eps, const int32_t* perm,
+                                  int64_t B, int64_t dz, int clamp_logv, float kl_scale, float* z,
+                                  uint16_t* z_bf16, int64_t ld_zb, float* kl_acc, void* stream) {
+  ARK_REQUIRE(heads && eps && z, ARK_E_BADARG, "reparam_kl_fwd: null pointer");
+  ARK_REQUIRE(B > 0 && dz > 0 && ld_heads >= 2 * dz && (!z_bf16 || ld_zb >= dz), ARK_E_BADARG,
+              "reparam_kl_fwd: bad sizes");
+  const int n = (int)(B * dz);
+  reparam_kl_fwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      heads, (int)ld_heads, eps, perm, (int)B, (int)dz, clamp_logv, kl_scale, z, z_bf16, (int)ld_zb, kl_acc);
+  return launched("reparam_kl_fwd");
+}
+
+extern "C" int ark_reparam_kl_bwd(const float* heads, int64_t ld_heads, const float* eps, const int32_t* perm,
+                                  const float* dz_in, int64_t B, int64_t dz, int clamp_logv, float beta_kl_scale,
+                                  float* dheads, uint16_t* dheads_bf16, int64_t ld_dh, void* stream) {
+  ARK_REQUIRE(heads && eps && dz_in && (dheads || dheads_bf16), ARK_E_BADARG, "reparam_kl_bwd: null pointer");
+  ARK_REQUIRE(B > 0 && dz > 0 && ld_heads >= 2 * dz && ld_dh >= 2 * dz, ARK_E_BADARG, "reparam_kl_bwd: bad sizes");
+  const int n = (int)(B * dz);
+  reparam_kl_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      heads, (int)ld_heads, eps, perm, dz_in, (int)B, (int)dz, clamp_logv, beta_kl_scale, dheads, dheads_bf16,
+      (int)ld_dh);
+  return launched("reparam_kl_bwd");
+}

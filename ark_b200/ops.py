@@ -1,0 +1,211 @@
+"""Thin torch-tensor wrappers over the C ABI (include/arkb200.h).
+
+Each function checks dtype/device/contiguity, extracts raw device pointers and the CURRENT stream, and
+enqueues one library call.  torch is used only for memory and streams.  No fallbacks: a non-CUDA tensor
+is an error.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _C
+from ._C import BF16, EPI_GELU, EPI_NONE, EPI_TANH, F32, MAJOR_K, MAJOR_MN  # noqa: F401
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _C.ArkError("ark_b200 kernels need CUDA tensors (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _C.ArkError(f"expected {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _host_i32(a):
+    """HOST int32 array (numpy) -> pointer; the C side reads it synchronously during the call."""
+    import numpy as np
+    if not (isinstance(a, np.ndarray) and a.dtype == np.int32 and a.flags.c_contiguous):
+        raise _C.ArkError("host metadata must be a contiguous numpy int32 array")
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _contig(*ts):
+    for t in ts:
+        if t is not None and not t.is_contiguous():
+            raise _C.ArkError("tensor must be contiguous")
+
+
+def gather_pool_fwd(triples, perm, E, R, pad_rid, g=None, g_bf16=None, inv_cnt=None):
+    B, T, _ = triples.shape
+    d = E.shape[1]
+    _contig(triples, perm, E, R, g, g_bf16, inv_cnt)
+    _C.lib().call("ark_gather_pool_fwd", _ptr(triples, torch.int64), _ptr(perm, torch.int32), _ptr(E, torch.float32),
+                  _ptr(R, torch.float32), B, T, d, -1 if pad_rid is None else int(pad_rid), _ptr(g, torch.float32),
+                  _ptr(g_bf16, torch.bfloat16), _ptr(inv_cnt, torch.float32), _stream())
+
+
+def gather_pool_bwd(dg, triples, perm, inv_cnt, pad_rid, pad_eid, dE, dR):
+    B, T, _ = triples.shape
+    d = dE.shape[1]
+    _contig(dg, triples, perm, inv_cnt, dE, dR)
+    _C.lib().call("ark_gather_pool_bwd", _ptr(dg, torch.float32), _ptr(triples, torch.int64), _ptr(perm, torch.int32),
+                  _ptr(inv_cnt, torch.float32), B, T, d, -1 if pad_rid is None else int(pad_rid),
+                  -1 if pad_eid is None else int(pad_eid), _ptr(dE, torch.float32), _ptr(dR, torch.float32), _stream())
+
+
+def pack_tokens(seq, perm, bt, off, L, tok_in, tgt):
+    B, seq_len = seq.shape
+    _contig(seq, perm, bt, off, tok_in, tgt)
+    _C.lib().call("ark_pack_tokens", _ptr(seq, torch.int64), _ptr(perm, torch.int32), _ptr(bt, torch.int32),
+                  _ptr(off, torch.int32), B, seq_len, L, _ptr(tok_in, torch.int32), _ptr(tgt, torch.int32), _stream())
+
+
+def tok_gather_fwd(W, tok, X_f32=None, X_bf16=None):
+    V, d = W.shape
+    _contig(W, tok, X_f32, X_bf16)
+    _C.lib().call("ark_tok_gather_fwd", _ptr(W), _DT[W.dtype], _ptr(tok, torch.int32), tok.numel(), d, V,
+                  _ptr(X_f32, torch.float32), _ptr(X_bf16, torch.bfloat16), _stream())
+
+
+def tok_scatter_add(dX, tok, dW):
+    V, d = dW.shape
+    _contig(dX, tok, dW)
+    _C.lib().call("ark_tok_scatter_add", _ptr(dX, torch.float32), _ptr(tok, torch.int32), tok.numel(), d, V,
+                  _ptr(dW, torch.float32), _stream())
+
+
+def reparam_kl_fwd(heads, eps, perm, dz, clamp, kl_scale, z, z_bf16, kl_acc):
+    B = heads.shape[0]
+    _contig(eps, perm, z, z_bf16)
+    _C.lib().call("ark_reparam_kl_fwd", _ptr(heads, torch.float32), heads.stride(0), _ptr(eps, torch.float32),
+                  _ptr(perm, torch.int32), B, dz, int(clamp), float(kl_scale), _ptr(z, torch.float32),
+                  _ptr(z_bf16, torch.bfloat16), 0 if z_bf16 is None else z_bf16.stride(0),
+                  _ptr(kl_acc, torch.float32), _stream())
+
+
+def reparam_kl_bwd(heads, eps, perm, dz_in, dz, clamp, beta_kl_scale, dheads, dheads_bf16):
+    B = heads.shape[0]
+    _contig(eps, perm, dz_in)
+    ld = dheads.stride(0) if dheads is not None else dheads_bf16.stride(0)
+    if dheads is not None and dheads_bf16 is not None and dheads.stride(0) != dheads_bf16.stride(0):
+        raise _C.ArkError("dheads and dheads_bf16 must share a row stride")
+    _C.lib().call("ark_reparam_kl_bwd", _ptr(heads, torch.float32), heads.stride(0), _ptr(eps, torch.float32),
+                  _ptr(perm, torch.int32), _ptr(dz_in, torch.float32), B, dz, int(clamp), float(beta_kl_scale),
+                  _ptr(dheads, torch.float32), _ptr(dheads_bf16, torch.bfloat16), ld, _stream())
+
+
+def softmax_ce(logits, V, tgt, grad_scale, write_grad, loss_acc=None, lse=None):
+    N, ldv = logits.shape[0], logits.stride(0)
+    _contig(tgt, lse)
+    _C.lib().call("ark_softmax_ce", _ptr(logits), _DT[logits.dtype], N, V, ldv, _ptr(tgt, torch.int32),
+                  float(grad_scale), int(write_grad), _ptr(loss_acc, torch.float32), _ptr(lse, torch.float32), _stream())
+
+
+def _ld(t):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _C.ArkError("GEMM operands must be 2-D with unit inner stride")
+    return t.stride(0)
+
+
+def gemm(A, a_major, B, b_major, C, M, N, K, bias=None, epilogue=EPI_NONE, accumulate=False, aux=None,
+         backend="tc"):
+    """C[M,N] = epi(A.B^T + bias).  A is [M,K] (MAJOR_K) or [K,M] (MAJOR_MN); B is [N,K] or [K,N].
+
+    backend "tc" = tcgen05/TMA kernel (bf16 operands, 16-byte aligned, ld % 8 == 0); "simt" = fp32-FMA
+    kernel (any dtype pair / alignment).  The choice is the caller's; nothing is substituted silently.
+    """
+    if A.dtype != B.dtype:
+        raise _C.ArkError("GEMM operands must share a dtype")
+    if aux is not None and (aux.stride(0) != C.stride(0)):
+        raise _C.ArkError("aux must share C's row stride")
+    lda, ldb, ldc = _ld(A), _ld(B), _ld(C)
+    if backend == "tc":
+        _C.lib().call("ark_gemm_bf16_tc", _ptr(A, torch.bfloat16), a_major, lda, _ptr(B, torch.bfloat16), b_major, ldb,
+                      _ptr(C), _DT[C.dtype], ldc, M, N, K, _ptr(bias, torch.float32), epilogue, int(accumulate),
+                      _ptr(aux, torch.float32), _stream())
+    elif backend == "simt":
+        _C.lib().call("ark_gemm_simt", _ptr(A), a_major, lda, _ptr(B), b_major, ldb, _DT[A.dtype], _ptr(C),
+                      _DT[C.dtype], ldc, M, N, K, _ptr(bias, torch.float32), epilogue, int(accumulate),
+                      _ptr(aux, torch.float32), _stream())
+    else:
+        raise _C.ArkError(f"unknown GEMM backend {backend!r}")
+
+
+def tc_eligible(A, B) -> bool:
+    """True when both operands satisfy the TMA constraints of the tensor-core GEMM."""
+    return (A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.stride(0) % 8 == 0 and B.stride(0) % 8 == 0
+            and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0)
+
+
+def gru_layer_fwd(hp_bf16, hp_f32, Whh, gi, b_hh, bt_host, off_host, L, d, y, y_bf16, gates, gh_ws, use_tc):
+    r, z, n, ghn = gates if gates is not None else (None, None, None, None)
+    _C.lib().call("ark_gru_layer_fwd", _ptr(hp_bf16, torch.bfloat16), _ptr(hp_f32, torch.float32), _ptr(Whh),
+                  _DT[Whh.dtype], _ptr(gi, torch.float32), _ptr(b_hh, torch.float32), _host_i32(bt_host), _host_i32(off_host), L, d,
+                  _ptr(y, torch.float32), _ptr(y_bf16, torch.bfloat16), _ptr(r), _ptr(z), _ptr(n), _ptr(ghn),
+                  _ptr(gh_ws, torch.float32), int(use_tc), _stream())
+
+
+def gru_layer_bwd(dy, gates, hp_f32, Whh, bt_host, off_host, L, d, dgi, dgh, dh_a, dh_b, use_tc):
+    """Returns the tensor (dh_a or dh_b) that holds d(loss)/d(h0) [bt[0], d]."""
+    r, z, n, ghn = gates
+    out = ctypes.c_void_p()
+    _C.lib().call("ark_gru_layer_bwd", _ptr(dy, torch.float32), _ptr(r), _ptr(z), _ptr(n), _ptr(ghn),
+                  _ptr(hp_f32, torch.float32), _ptr(Whh), _DT[Whh.dtype], _host_i32(bt_host), _host_i32(off_host), L, d, _ptr(dgi), _ptr(dgh),
+                  _ptr(dh_a, torch.float32), _ptr(dh_b, torch.float32), ctypes.byref(out), int(use_tc), _stream())
+    return dh_a if out.value == dh_a.data_ptr() else dh_b
+
+
+def gelu_bwd(dact, pre, dpre=None, dpre_bf16=None):
+    _contig(dact, pre, dpre, dpre_bf16)
+    _C.lib().call("ark_gelu_bwd", _ptr(dact, torch.float32), _ptr(pre, torch.float32), dact.numel(),
+                  _ptr(dpre, torch.float32), _ptr(dpre_bf16, torch.bfloat16), _stream())
+
+
+def tanh_bwd(dh, h, dpre=None, dpre_bf16=None):
+    _contig(dh, h, dpre, dpre_bf16)
+    _C.lib().call("ark_tanh_bwd", _ptr(dh, torch.float32), _ptr(h, torch.float32), dh.numel(),
+                  _ptr(dpre, torch.float32), _ptr(dpre_bf16, torch.bfloat16), _stream())
+
+
+def colsum(X, M, N, out, accumulate=False):
+    _C.lib().call("ark_colsum", _ptr(X), _DT[X.dtype], M, N, X.stride(0), _ptr(out, torch.float32), int(accumulate),
+                  _stream())
+
+
+def add_(a, b, y=None, y_bf16=None):
+    _contig(a, b, y, y_bf16)
+    _C.lib().call("ark_add_f32", _ptr(a, torch.float32), _ptr(b, torch.float32), a.numel(), _ptr(y, torch.float32),
+                  _ptr(y_bf16, torch.bfloat16), _stream())
+
+
+def cast_bf16(x, y):
+    _contig(x, y)
+    _C.lib().call("ark_cast_f32_to_bf16", _ptr(x, torch.float32), x.numel(), _ptr(y, torch.bfloat16), _stream())
+
+
+def dropout_fwd(x, p, seed, offset, y=None, y_bf16=None, mask=None):
+    _contig(x, y, y_bf16, mask)
+    _C.lib().call("ark_dropout_fwd", _ptr(x, torch.float32), x.numel(), float(p), int(seed), int(offset),
+                  _ptr(y, torch.float32), _ptr(y_bf16, torch.bfloat16), _ptr(mask, torch.uint8), _stream())
+
+
+def dropout_bwd(dy, mask, p, dx):
+    _contig(dy, mask, dx)
+    _C.lib().call("ark_dropout_bwd", _ptr(dy, torch.float32), _ptr(mask, torch.uint8), dy.numel(), float(p),
+                  _ptr(dx, torch.float32), _stream())
+
+
+def adam_flat(p, g, m, v, shadow, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _contig(p, g, m, v, shadow)
+    _C.lib().call("ark_adam_flat", _ptr(p, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32),
+                  _ptr(v, torch.float32), _ptr(shadow, torch.bfloat16), p.numel(), float(lr), float(beta1),
+                  float(beta2), float(eps), int(step), float(grad_scale), _stream())

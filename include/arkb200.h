@@ -1,0 +1,181 @@
+/*
+ * arkb200.h — C ABI of libarkb200.so: hand-written sm_100a kernels for the KG-VAE (SAIL) ELBO
+ * training step of thiviyanT/ARK.
+ *
+ * The reference has no FFI of its own (it is pure Python on PyTorch); each entry
+ * point below replaces the PyTorch op sequence cited next to it (paths relative to the reference
+ * checkout).  The reference-side binding a maintainer would add is the ctypes stub shown in
+ * INTEGRATION.md (this repository's copy of it is ark_b200/_C.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates, frees
+ *     or retains one.  No torch types cross this boundary.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*), is re-entrant
+ *     and keeps no state (autograd's backward thread may call concurrently with the main thread).
+ *   - return value: 0 on success, a positive cudaError_t if the CUDA runtime reported one, a
+ *     negative ARK_E_* code for an argument/shape/alignment violation detected BEFORE launching.
+ *     ark_last_error() returns a thread-local description.
+ *   - "rows" of token-level tensors are PACKED non-PAD decoder positions, time-major over graphs
+ *     sorted by decreasing length: row = off[t] + b  (ark_b200/layout.py; SURVEY.md finding 7).
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t), f32 = IEEE float, indices int32 unless noted.
+ */
+#ifndef ARKB200_H_
+#define ARKB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARK_ABI_VERSION 1
+
+enum {
+  ARK_E_BADARG = -1,    /* null pointer / negative size */
+  ARK_E_ALIGN = -2,     /* pointer or leading dimension violates the stated alignment */
+  ARK_E_SHAPE = -3,     /* shape outside what the kernel supports */
+  ARK_E_NODRIVER = -4,  /* cuTensorMapEncodeTiled could not be resolved from the driver */
+};
+
+/* element types for GEMM operands / results */
+enum { ARK_F32 = 0, ARK_BF16 = 1 };
+/* operand storage: K-major = the contraction index is contiguous (nn.Linear weight [N,K], activations
+ * [M,K]); MN-major = the M (or N) index is contiguous, i.e. the operand is stored as [K, M|N]. */
+enum { ARK_MAJOR_K = 0, ARK_MAJOR_MN = 1 };
+/* GEMM epilogues (applied to acc + bias) */
+enum { ARK_EPI_NONE = 0, ARK_EPI_GELU = 1, ARK_EPI_TANH = 2 };
+
+int ark_abi_version(void);
+const char* ark_last_error(void);
+/* number of kernel launches this thread has enqueued since the last reset (bench.py: gpu_launches) */
+int64_t ark_launch_count(void);
+void ark_launch_count_reset(void);
+
+/* ---- K1/K2: encoder gather + masked mean-pool (models.py:47-58) and its scatter-add backward ----
+ * triples int64 [B,T,3] (the reference's LongTensor, read as is); perm int32 [B] or NULL maps output
+ * row b -> input graph perm[b]; E f32 [nE,d], R f32 [nR,d]; pad_rid < 0 means "no padding" (plain mean
+ * over T, models.py:58).  Writes g (f32 [B,3d], may be NULL), g_bf16 (may be NULL) and inv_cnt f32 [B]
+ * (= 1/max(#valid,1)).  d % 4 == 0. */
+int ark_gather_pool_fwd(const int64_t* triples, const int32_t* perm, const float* E, const float* R,
+                        int64_t B, int64_t T, int64_t d, int64_t pad_rid,
+                        float* g, uint16_t* g_bf16, float* inv_cnt, void* stream);
+/* dE[nE,d] / dR[nR,d] += dg[b, slot*d:(slot+1)*d] * inv_cnt[b] for every valid triple; caller zeroes
+ * dE/dR first.  Rows pad_eid / pad_rid are never touched (nn.Embedding padding_idx semantics). */
+int ark_gather_pool_bwd(const float* dg, const int64_t* triples, const int32_t* perm, const float* inv_cnt,
+                        int64_t B, int64_t T, int64_t d, int64_t pad_rid, int64_t pad_eid,
+                        float* dE, float* dR, void* stream);
+
+/* ---- a1: packed token ids (utils.py:102-108 layout; PAD-skip) ----
+ * seq int64 [B, seq_len]; for t in [0,L), b in [0,bt[t]): row = off[t]+b,
+ * tok_in[row] = seq[perm[b], t], tgt[row] = seq[perm[b], t+1]. */
+int ark_pack_tokens(const int64_t* seq, const int32_t* perm, const int32_t* bt, const int32_t* off,
+                    int64_t B, int64_t seq_len, int64_t L, int32_t* tok_in, int32_t* tgt, void* stream);
+
+/* ---- K5: token-embedding gather (models.py:138) and scatter-add backward ----
+ * W is f32 or bf16 [V,d] (w_dtype); X f32 and/or bf16 [N,d] (either may be NULL). d % 8 == 0. */
+int ark_tok_gather_fwd(const void* W, int w_dtype, const int32_t* tok, int64_t N, int64_t d, int64_t V,
+                       float* X_f32, uint16_t* X_bf16, void* stream);
+/* dW[tok[i], :] += dX[i, :]  (red.global.add.v4.f32); dW is NOT zeroed here (tied weight: it already
+ * holds dLogits^T Y, models.py:130-132). */
+int ark_tok_scatter_add(const float* dX, const int32_t* tok, int64_t N, int64_t d, int64_t V,
+                        float* dW, void* stream);
+
+/* ---- K4: reparameterisation + analytic KL (models.py:62-63, 199-200) ----
+ * heads f32 [B, 2*dz] = [mu | logv_raw] (row stride ld_heads); eps f32 [B,dz] indexed through perm
+ * (eps row perm[b] belongs to output row b) or directly if perm == NULL.
+ * z f32 [B,dz]; z_bf16 [B, ld_zb] zero-padded to ld_zb columns (may be NULL); kl_acc += kl_scale *
+ * sum(-0.5*(1+logv-mu^2-e^logv))  with kl_scale = 1/(B_global*dz); clamp_logv != 0 applies
+ * clamp(-10,10) (SAIL's MLP encoder; t-SAIL's has none, models.py:93). */
+int ark_reparam_kl_fwd(const float* heads, int64_t ld_heads, const float* eps, const int32_t* perm,
+                       int64_t B, int64_t dz, int clamp_logv, float kl_scale,
+                       float* z, uint16_t* z_bf16, int64_t ld_zb, float* kl_acc, void* stream);
+/* dheads [B,2dz] = [dz + bk*mu | clampmask*(0.5*dz*eps*sigma + 0.5*bk*(e^logv-1))], bk = beta*kl_scale */
+int ark_reparam_kl_bwd(const float* heads, int64_t ld_heads, const float* eps, const int32_t* perm,
+                       const float* dz_in, int64_t B, int64_t dz, int clamp_logv, float beta_kl_scale,
+                       float* dheads, uint16_t* dheads_bf16, int64_t ld_dh, void* stream);
+
+/* ---- K7: fused softmax cross-entropy forward+backward (ablation_study.py:64-69) ----
+ * logits [N, ldv] (bf16 or f32 per `dtype`), V valid columns; tgt int32 [N] (never PAD: rows are
+ * packed).  loss_acc += grad_scale * sum_i (lse_i - logits_i[tgt_i]); when write_grad != 0 the row is
+ * overwritten IN PLACE by grad_scale*(softmax - onehot) (columns [V,ldv) zeroed); lse f32 [N] may be
+ * NULL.  The probability matrix never exists in HBM. */
+int ark_softmax_ce(void* logits, int dtype, int64_t N, int64_t V, int64_t ldv, const int32_t* tgt,
+                   float grad_scale, int write_grad, float* loss_acc, float* lse, void* stream);
+
+/* ---- K3: GEMM  C[M,N] = epi(A[M,K] . B[N,K]^T + bias[N])  (nn.Linear, models.py:36,43-44,120,128) ----
+ * tcgen05/TMA tensor-core path: A,B bf16; a_major/b_major as above; lda/ldb/ldc in elements; all
+ * leading dimensions * element size and base pointers must be multiples of 16 bytes.
+ * c_dtype f32|bf16.  accumulate != 0: C += result (f32 C only).  aux (may be NULL, f32 [M,ldc]):
+ * receives the PRE-activation when epilogue != NONE (needed by the backward pass). */
+int ark_gemm_bf16_tc(const uint16_t* A, int a_major, int64_t lda, const uint16_t* B, int b_major, int64_t ldb,
+                     void* C, int c_dtype, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                     const float* bias, int epilogue, int accumulate, float* aux, void* stream);
+/* SIMT path with the same contract for any alignment / tiny shapes and for the fp32 inference path:
+ * ab_dtype f32|bf16 (both operands), fp32 FMA accumulation. */
+int ark_gemm_simt(const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb, int ab_dtype,
+                  void* C, int c_dtype, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                  const float* bias, int epilogue, int accumulate, float* aux, void* stream);
+
+/* ---- K6: GRU (nn.GRU gate order r,z,n; models.py:121-127,141) ----
+ * Pointwise cell, one time step, rows [0,Bt): given gi = W_ih x + b_ih (f32 [Bt,3d], row stride 3d) and
+ * gh = W_hh h_prev (NO bias; f32 [Bt,3d]) computes r,z,n, h = (1-z)n + z h_prev and stores
+ * h (f32), h_bf16 (optional), and the gates for backward: r,z,n,ghn(=gh_n+b_hn) each f32 [Bt,d].
+ * h_next_prev(_bf16): optional second destination, the packed "h_prev" rows of step t+1 (first
+ * Bt_next rows only). */
+int ark_gru_cell_fwd(const float* gi, const float* gh, const float* b_hh, const float* h_prev,
+                     int64_t Bt, int64_t d, float* h, uint16_t* h_bf16,
+                     float* hp_next, uint16_t* hp_next_bf16, int64_t Bt_next,
+                     float* r, float* z, float* n, float* ghn, void* stream);
+/* Backward of one step: dh_total = dy + dh_carry (dh_carry rows >= Bt_carry are treated as 0; may be
+ * NULL).  Writes dgi,dgh f32 [Bt,3d] (+ optional bf16 copies) and dh_prev_direct = dh_total*z. */
+int ark_gru_cell_bwd(const float* dy, const float* dh_carry, int64_t Bt_carry,
+                     const float* r, const float* z, const float* n, const float* ghn, const float* h_prev,
+                     int64_t Bt, int64_t d, float* dgi, float* dgh, uint16_t* dgi_bf16, uint16_t* dgh_bf16,
+                     float* dh_direct, void* stream);
+
+/* One GRU layer through time over the packed batch (the time loop is native, not Python).
+ * bt_host / off_host are HOST int32 arrays of length L (rows of step t: [off[t], off[t]+bt[t]), bt
+ * non-increasing).  hp (bf16, may be NULL on the fp32 path) / hp_f32: [N,d] packed "h_prev" rows; the
+ * caller fills block 0 with h0, the layer fills blocks 1..L-1.  gi f32 [N,3d] = W_ih x + b_ih.
+ * Whh: [3d,d] in w_dtype (ARK_BF16 training path, ARK_F32 inference path).  Outputs y (f32 [N,d]),
+ * y_bf16 (optional) and the saved gates r,z,n,ghn (all NULL for inference).  gh_ws f32 [bt[0],3d] scratch.
+ * use_tc != 0 runs the recurrent projection on tcgen05 (bf16 only), else on the SIMT GEMM. */
+int ark_gru_layer_fwd(void* hp, float* hp_f32, const void* Whh, int w_dtype, const float* gi, const float* b_hh,
+                      const int32_t* bt_host, const int32_t* off_host, int64_t L, int64_t d,
+                      float* y, uint16_t* y_bf16, float* r, float* z, float* n, float* ghn,
+                      float* gh_ws, int use_tc, void* stream);
+/* Backward through time.  dy f32 [N,d] (gradient w.r.t. the layer's outputs); writes dgi/dgh [N,3d]
+ * (bf16 when w_dtype == ARK_BF16, else f32); dh_a/dh_b: two f32 [bt[0],d] scratch buffers; *dh0_out
+ * (HOST pointer to a device pointer) receives whichever of them holds d(loss)/d(h0) at the end. */
+int ark_gru_layer_bwd(const float* dy, const float* r, const float* z, const float* n, const float* ghn,
+                      const float* hp_f32, const void* Whh, int w_dtype, const int32_t* bt_host,
+                      const int32_t* off_host, int64_t L, int64_t d, void* dgi, void* dgh,
+                      float* dh_a, float* dh_b, float** dh0_out, int use_tc, void* stream);
+
+/* ---- elementwise helpers ----
+ * dpre = dact * gelu'(pre) (erf form, models.py:37) -> f32 and/or bf16 */
+int ark_gelu_bwd(const float* dact, const float* pre, int64_t n, float* dpre, uint16_t* dpre_bf16, void* stream);
+/* dpre = dh * (1 - h^2) */
+int ark_tanh_bwd(const float* dh, const float* h, int64_t n, float* dpre, uint16_t* dpre_bf16, void* stream);
+/* out[N] (+)= column sums of X[M, ld] (f32 or bf16) — bias gradients */
+int ark_colsum(const void* X, int dtype, int64_t M, int64_t N, int64_t ld, float* out, int accumulate, void* stream);
+/* y = a + b (f32), optional bf16 copy; y may alias a */
+int ark_add_f32(const float* a, const float* b, int64_t n, float* y, uint16_t* y_bf16, void* stream);
+int ark_cast_f32_to_bf16(const float* x, int64_t n, uint16_t* y, void* stream);
+/* inter-layer dropout (nn.GRU dropout=dec_dropout, train mode): y = x * keep/(1-p), Philox4x32-10 keyed
+ * by (seed, offset+element); mask uint8 [n] saved for backward. */
+int ark_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset,
+                    float* y, uint16_t* y_bf16, uint8_t* mask, void* stream);
+int ark_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, void* stream);
+
+/* ---- K10: dense Adam over a flat parameter buffer (torch.optim.Adam defaults, ablation_study.py:571) ----
+ * p,g,m,v f32 [n]; shadow bf16 [n] may be NULL; step = 1-based count of this update; grad_scale
+ * multiplies g first (1 for summed DP gradients). */
+int ark_adam_flat(float* p, const float* g, float* m, float* v, uint16_t* shadow, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARKB200_H_ */
