@@ -1,0 +1,286 @@
+"""The fused ELBO training step of the KG-VAE (SAIL): hand-scheduled forward + backward + Adam.
+
+This is the B200-native replacement of the body of the reference's training loop
+(kgvae/experiments/ablation_study.py:59-76):
+
+    logits, mu, logv = model(triples, seq[:, :-1]); ce = F.cross_entropy(..., ignore_index=PAD)
+    kl = model.kl_mean(mu, logv); loss = ce + b*kl; loss.backward(); optimizer.step()
+
+Instead of an autograd graph over ~60 ATen ops, the step is a fixed schedule of C-ABI kernel calls
+(include/arkb200.h) over packed, PAD-free token rows (ark_b200/layout.py).  The [B, L, V] logits tensor is
+produced once in bf16, turned into its own gradient in place by the fused softmax-CE kernel and consumed by
+the two backward GEMMs — the probability matrix never exists.  torch provides memory, streams and NCCL only.
+
+Numerics: GEMM operands bf16 (weights from the flat bf16 shadow, activations written in bf16 by the
+producing kernel), fp32 accumulation, fp32 master weights / recurrent state / gates / mu / logv / KL / loss.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .flat import FlatParams, sail_param_order
+from .layout import PackedLayout, pack_layout
+
+K, MN = ops.MAJOR_K, ops.MAJOR_MN
+
+
+def _up8(n):
+    return (n + 7) // 8 * 8
+
+
+class SailEngine:
+    """Owns the flat parameter storage of one SAIL module and runs its ELBO step on one GPU.
+
+    ``gemm_backend``: "tc" (tcgen05/TMA, default, the product path) or "simt" (fp32-FMA kernel with the same
+    bf16 operands — a debugging cross-check, never chosen automatically for TMA-eligible shapes).
+    """
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gemm_backend="tc", dist_group=None,
+                 bucket_mb=32.0, seed=0):
+        cfg = model.config
+        if cfg["model_type"] != "SAIL":
+            raise NotImplementedError("SailEngine accelerates model_type 'SAIL' (MLP encoder + GRU decoder)")
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("SailEngine needs the model on a CUDA device: there is no CPU path")
+        self.model, self.cfg, self.device = model, cfg, dev
+        self.d, self.dz, self.V = cfg["d_model"], cfg["d_latent"], cfg["vocab_size"]
+        self.nl = model.dec.gru.num_layers
+        self.n_mlp = len([m for m in model.enc.mlp if isinstance(m, torch.nn.Linear)])
+        self.pad_rid, self.pad_eid = cfg.get("pad_rid"), cfg.get("pad_eid")
+        self.tied = model.dec.out.weight is model.dec.tok_emb.weight
+        self.p_drop = float(cfg.get("dec_dropout", 0.1)) if self.nl > 1 else 0.0
+        if self.d % 8:
+            raise ValueError("d_model must be a multiple of 8")
+        self.flat = FlatParams(sail_param_order(model), dev)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.step_count = 0
+        self.backend = gemm_backend
+        self.seed, self.philox_offset = int(seed), 0
+        self.ldv = _up8(self.V)
+        self.group = dist_group
+        self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self._pending = []
+        self.stats = torch.zeros(4, device=dev)  # [ce, kl, steps, unused] accumulated on device
+        self.refresh_shadow()
+        if hasattr(model, "_attach_engine"):
+            model._attach_engine(self)
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def refresh_shadow(self):
+        """bf16 operand copies <- fp32 masters (after init / load_state_dict; Adam keeps them in sync)."""
+        ops.cast_bf16(self.flat.param, self.flat.shadow)
+
+    def _w(self, name):       # bf16 shadow view
+        return self.flat.s(name)
+
+    def _gemm(self, A, am, B, bm, C, M, N, Kd, **kw):
+        backend = "tc" if (self.backend == "tc" and ops.tc_eligible(A, B)) else "simt"
+        ops.gemm(A, am, B, bm, C, M, N, Kd, backend=backend, **kw)
+
+    # ------------------------------------------------------------------ forward + backward
+    def forward_backward(self, triples, seq, lay: PackedLayout, eps, beta, n_tok_global=None, batch_global=None,
+                         train=True, stats_out=None):
+        """One ELBO forward+backward over a device-resident batch.  Gradients land in ``self.flat.grad``
+        (overwritten, never accumulated).  Returns a device tensor [ce, kl] (already globally normalised when
+        the *_global normalisers are given; the caller sums them over ranks)."""
+        f, dev, d, dz, V, ldv, nl = self.flat, self.device, self.d, self.dz, self.V, self.ldv, self.nl
+        B = triples.shape[0]
+        N, L = lay.n_tok, lay.L
+        d3 = 3 * d
+        bf, f32 = torch.bfloat16, torch.float32
+        n_tok_g = float(N if n_tok_global is None else n_tok_global)
+        b_g = int(B if batch_global is None else batch_global)
+        out = torch.zeros(2, device=dev) if stats_out is None else stats_out
+        use_tc = 1 if self.backend == "tc" else 0
+        new = lambda *s, dtype=f32: torch.empty(*s, device=dev, dtype=dtype)  # noqa: E731
+
+        # ---------------- encoder forward (models.py:46-64)
+        g_b, inv_cnt = new(B, d3, dtype=bf), new(B)
+        ops.gather_pool_fwd(triples, lay.perm_dev, f.p("enc.e_emb.weight"), f.p("enc.r_emb.weight"), self.pad_rid,
+                            None, g_b, inv_cnt)
+        acts, pres = [g_b], []
+        for k in range(self.n_mlp):
+            a_next, pre = new(B, d3, dtype=bf), new(B, d3)
+            self._gemm(acts[-1], K, self._w(f"enc.mlp.{2 * k}.weight"), K, a_next, B, d3, d3,
+                       bias=f.p(f"enc.mlp.{2 * k}.bias"), epilogue=ops.EPI_GELU, aux=pre)
+            acts.append(a_next)
+            pres.append(pre)
+        w_heads = f.fused(f.shadow, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
+        b_heads = f.fused(f.param, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
+        heads = new(B, 2 * dz)
+        self._gemm(acts[-1], K, w_heads, K, heads, B, 2 * dz, d3, bias=b_heads)
+        z, z_b = new(B, dz), new(B, dz, dtype=bf)
+        ops.reparam_kl_fwd(heads, eps, lay.perm_dev, dz, True, 1.0 / (b_g * dz), z, z_b, out[1:2])
+        h0 = new(B, d)
+        self._gemm(z_b, K, self._w("dec.z_proj.weight"), K, h0, B, d, dz, bias=f.p("dec.z_proj.bias"),
+                   epilogue=ops.EPI_TANH)
+
+        # ---------------- decoder forward (models.py:136-142) over packed rows
+        tok, tgt = new(N, dtype=torch.int32), new(N, dtype=torch.int32)
+        ops.pack_tokens(seq, lay.perm_dev, lay.bt_dev, lay.off_dev, L, tok, tgt)
+        x_b = new(N, d, dtype=bf)
+        ops.tok_gather_fwd(self._w("dec.tok_emb.weight"), tok, None, x_b)
+        b0 = int(lay.bt[0])
+        saved = []
+        u_b = x_b
+        gh_ws = new(b0, d3)
+        for k in range(nl):
+            gi = new(N, d3)
+            self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, bias=f.p(f"dec.gru.bias_ih_l{k}"))
+            hp_f, hp_b = new(N, d), new(N, d, dtype=bf)
+            hp_f[:b0].copy_(h0[:b0])
+            ops.cast_bf16(hp_f[:b0], hp_b[:b0])
+            y, y_b = new(N, d), new(N, d, dtype=bf)
+            gates = tuple(new(N, d) for _ in range(4))
+            ops.gru_layer_fwd(hp_b, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
+                              lay.bt, lay.off, L, d, y, y_b, gates, gh_ws, use_tc)
+            mask = None
+            if train and self.p_drop > 0 and k < nl - 1:
+                mask = new(N, d, dtype=torch.uint8)
+                ops.dropout_fwd(y, self.p_drop, self.seed, self.philox_offset, None, y_b, mask)
+                self.philox_offset += (N * d + 3) // 4
+            saved.append((u_b, hp_f, hp_b, gates, mask))
+            u_b = y_b
+            del gi, y
+        logits = new(N, ldv, dtype=bf)
+        w_out = self._w("dec.tok_emb.weight") if self.tied else self._w("dec.out.weight")
+        self._gemm(u_b, K, w_out, K, logits, N, V, d, bias=f.p("dec.out.bias"))
+        # CE forward+backward in place (ablation_study.py:64-69): logits -> (softmax-onehot)/N_tok
+        ops.softmax_ce(logits, V, tgt, 1.0 / n_tok_g, True, out[0:1], None)
+        if not train:
+            return out
+
+        # ---------------- decoder backward
+        g_wout = f.g("dec.tok_emb.weight") if self.tied else f.g("dec.out.weight")
+        self._gemm(logits, MN, u_b, MN, g_wout, V, d, N)                      # dW = dLogits^T . Y
+        ops.colsum(logits, N, V, f.g("dec.out.bias"))
+        dy = new(N, d)
+        self._gemm(logits, K, w_out, MN, dy, N, d, V)                         # dY = dLogits . W
+        del logits
+        self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
+        dh0 = None
+        dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
+        dh_a, dh_b = new(b0, d), new(b0, d)
+        for k in range(nl - 1, -1, -1):
+            u_in, hp_f, hp_b, gates, mask = saved[k]
+            if mask is not None:
+                ops.dropout_bwd(dy, mask, self.p_drop, dy)
+            dh_k = ops.gru_layer_bwd(dy, gates, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), lay.bt, lay.off, L, d,
+                                     dgi, dgh, dh_a, dh_b, use_tc)
+            if dh0 is None:
+                dh0 = dh_k.clone()
+            else:
+                ops.add_(dh0, dh_k, dh0, None)
+            self._gemm(dgi, MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N)
+            self._gemm(dgh, MN, hp_b, MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N)
+            ops.colsum(dgi, N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
+            ops.colsum(dgh, N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
+            self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3)   # grad w.r.t. layer input
+            self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+        if not self.tied:
+            f.g("dec.tok_emb.weight").zero_()
+        ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
+        self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+
+        # ---------------- h0 = tanh(W_z z + b_z), reparameterisation, KL
+        dpre, dpre_b = new(B, d), new(B, d, dtype=bf)
+        ops.tanh_bwd(dh0, h0, dpre, dpre_b)
+        self._gemm(dpre_b, MN, z_b, MN, f.g("dec.z_proj.weight"), d, dz, B)
+        ops.colsum(dpre, B, d, f.g("dec.z_proj.bias"))
+        dz_in = new(B, dz)
+        self._gemm(dpre_b, K, self._w("dec.z_proj.weight"), MN, dz_in, B, dz, d)
+        ld_dh = _up8(2 * dz)
+        dheads = torch.zeros(B, ld_dh, device=dev)
+        dheads_b = torch.zeros(B, ld_dh, device=dev, dtype=bf)
+        ops.reparam_kl_bwd(heads, eps, lay.perm_dev, dz_in, dz, True, beta / (b_g * dz), dheads, dheads_b)
+        g_wh = f.fused(f.grad, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
+        g_bh = f.fused(f.grad, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
+        self._gemm(dheads_b[:, :2 * dz], MN, acts[-1], MN, g_wh, 2 * dz, d3, B)
+        ops.colsum(dheads, B, 2 * dz, g_bh)
+        da = new(B, d3)
+        self._gemm(dheads_b[:, :2 * dz], K, w_heads, MN, da, B, d3, 2 * dz)
+        self._grad_ready("dec.z_proj.weight", "enc.logv.bias")
+
+        # ---------------- encoder MLP + pooled gather backward
+        for k in range(self.n_mlp - 1, -1, -1):
+            dp_b = new(B, d3, dtype=bf)
+            ops.gelu_bwd(da, pres[k], None, dp_b)
+            self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B)
+            ops.colsum(dp_b, B, d3, f.g(f"enc.mlp.{2 * k}.bias"))
+            da = new(B, d3)
+            self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3)
+            self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
+        gE, gR = f.g("enc.e_emb.weight"), f.g("enc.r_emb.weight")
+        gR.zero_()
+        gE.zero_()
+        ops.gather_pool_bwd(da, triples, lay.perm_dev, inv_cnt, self.pad_rid, self.pad_eid, gE, gR)
+        self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight")
+        return out
+
+    # ------------------------------------------------------------------ data-parallel gradient exchange
+    def _grad_ready(self, first, last):
+        """Gradient slots first..last (contiguous in the flat layout) are final: under data parallelism,
+        sum them over ranks on the side stream while backward continues (bucketed NCCL all-reduce)."""
+        if self.world == 1:
+            return
+        s, e = self.flat.span(first, last)
+        if self._pending and self._pending[-1][1] >= s - 64:
+            self._pending[-1] = (self._pending[-1][0], e)
+        else:
+            self._pending.append((s, e))
+        if self._pending[-1][1] - self._pending[-1][0] >= self.bucket_elems:
+            self._flush_bucket()
+
+    def _flush_bucket(self):
+        if not self._pending:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            for (s, e) in self._pending:
+                torch.distributed.all_reduce(self.flat.grad[s:e], group=self.group)
+        self._pending = []
+
+    def _sync_grads(self):
+        if self.world == 1:
+            return
+        self._flush_bucket()
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self, lr=None):
+        """Dense Adam over the whole flat buffer (torch.optim.Adam defaults, ablation_study.py:571)."""
+        self._sync_grads()
+        self.step_count += 1
+        f = self.flat
+        ops.adam_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.lr if lr is None else lr,
+                      self.betas[0], self.betas[1], self.eps, self.step_count)
+
+    def train_step(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
+        """zero_grad + forward + backward (+ all-reduce) + Adam: ablation_study.py:43,59-76."""
+        out = self.forward_backward(triples, seq, lay, eps, beta, n_tok_global, batch_global, train=True)
+        self.adam_step(lr)
+        self.stats[0:2] += out
+        self.stats[2] += 1
+        return out
+
+    def read_stats(self, beta, reset=True):
+        """(avg_loss, avg_ce, avg_kl) since the last reset — ONE device->host read instead of the reference's
+        three .item() calls per step (ablation_study.py:78-80)."""
+        st = self.stats.clone()
+        if self.world > 1:
+            # ce/kl were normalised by the GLOBAL counts, so the global value is the sum over ranks
+            torch.distributed.all_reduce(st[0:2], group=self.group)
+        ce, kl, n = st[:3].tolist()
+        if reset:
+            self.stats.zero_()
+        n = max(n, 1.0)
+        return (ce + beta * kl) / n, ce / n, kl / n

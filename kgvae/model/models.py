@@ -1,0 +1,277 @@
+"""Drop-in ``kgvae.model.models`` for the KG-VAE hot path, backed by ark_b200's sm_100a kernels.
+
+Same public surface as the reference module (/root/reference/kgvae/model/models.py): ``SAIL(config)`` with
+``.enc(triples) -> (z, mu, logv)``, ``.dec(z, tgt) -> logits``, ``.forward(triples, seq_in)``, ``.kl_mean``,
+``.decode_latent`` / ``.beam_generate`` / ``.generate_test_graphs`` / ``.posterior_bits`` /
+``.bits_per_sequence`` / ``.count_unique_graphs``, identical ``state_dict`` keys and shapes
+(models.py:26-27,36,43-44,119-132), identical initialisation (torch's nn.Embedding / nn.Linear / nn.GRU are
+used as PARAMETER CONTAINERS only — none of their forward methods runs).
+
+What changed underneath:
+  * ``enc`` / ``dec`` / ``forward`` execute on the GPU through the fp32 kernels of libarkb200 (inference:
+    generation, validation, beam search — integer outputs must match the reference, so no bf16 here);
+  * training goes through ``SAIL.elbo_step`` (new) = ark_b200.elbo.SailEngine: bf16 tcgen05 GEMMs, fused
+    softmax-CE, PAD-free packed rows, fused Adam.  ``forward`` never builds an autograd graph.
+There is no CPU implementation: modules must live on a CUDA device before they are called.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ark_b200 import ops
+from ark_b200.elbo import SailEngine
+from ark_b200.layout import PackedLayout, pack_layout
+from kgvae.model.utils import canonical_graph_string
+
+K, MN = ops.MAJOR_K, ops.MAJOR_MN
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: this build of kgvae runs on CUDA only (ark_b200 has no CPU path); "
+                           "move the model and inputs to a B200 with .to('cuda')")
+
+
+def _linear_f32(x, lin, epilogue=ops.EPI_NONE):
+    """y = epi(x W^T + b) in fp32 on the SIMT kernel (reference: nn.Linear, models.py:36,43-44,120,128)."""
+    M, Kd = x.shape
+    N = lin.weight.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    ops.gemm(x, K, lin.weight.detach(), K, y, M, N, Kd, bias=None if lin.bias is None else lin.bias.detach(),
+             epilogue=epilogue, backend="simt")
+    return y
+
+
+class AutoRegEncoderMLP(nn.Module):
+    """Embedding gather + masked mean-pool + GELU MLP + (mu, logv) heads + reparameterisation
+    (reference: models.py:13-64)."""
+
+    def __init__(self, num_entities, num_relations, d_model, latent_dim, pad_eid=None, pad_rid=None, hidden=None,
+                 dropout=0.0, n_layers=2):
+        super().__init__()
+        if dropout:
+            raise NotImplementedError("the reference never enables encoder dropout for SAIL (models.py:151-159)")
+        self.pad_rid, self.pad_eid = pad_rid, pad_eid
+        self.e_emb = nn.Embedding(num_entities, d_model, padding_idx=pad_eid)
+        self.r_emb = nn.Embedding(num_relations, d_model, padding_idx=pad_rid)
+        d_in = 3 * d_model
+        hidden = hidden or max(d_in, 2 * d_model)
+        mods, width = [], d_in
+        for _ in range(n_layers):
+            mods += [nn.Linear(width, hidden), nn.GELU()]   # indices 0,2,4 hold the weights (state_dict names)
+            width = hidden
+        self.mlp = nn.Sequential(*mods)
+        self.mu = nn.Linear(hidden, latent_dim)
+        self.logv = nn.Linear(hidden, latent_dim)
+
+    @torch.no_grad()
+    def encode_stats(self, triples):
+        _need_cuda(triples, "enc")
+        B = triples.shape[0]
+        d3 = 3 * self.e_emb.weight.shape[1]
+        g = torch.empty(B, d3, device=triples.device)
+        inv = torch.empty(B, device=triples.device)
+        ops.gather_pool_fwd(triples.contiguous(), None, self.e_emb.weight.detach(), self.r_emb.weight.detach(),
+                            self.pad_rid, g, None, inv)
+        for m in self.mlp:
+            if isinstance(m, nn.Linear):
+                g = _linear_f32(g, m, ops.EPI_GELU)
+        return _linear_f32(g, self.mu), _linear_f32(g, self.logv).clamp_(-10, 10)
+
+    @torch.no_grad()
+    def forward(self, triples):
+        mu, logv = self.encode_stats(triples)
+        z = mu + torch.randn_like(mu) * torch.exp(0.5 * logv)   # same RNG call as the reference (models.py:63)
+        return z, mu, logv
+
+
+class AutoRegDecoderGRU(nn.Module):
+    """Token embedding + h0 = tanh(z_proj z) + n-layer GRU + tied vocabulary projection
+    (reference: models.py:116-142)."""
+
+    def __init__(self, d_model, num_layers, seq_len, vocab_size, latent_dim, dropout=0.1, tie_weights=True):
+        super().__init__()
+        self.tok_emb = nn.Embedding(vocab_size, d_model)
+        self.z_proj = nn.Linear(latent_dim, d_model)
+        self.gru = nn.GRU(input_size=d_model, hidden_size=d_model, num_layers=num_layers, batch_first=True,
+                          dropout=dropout if num_layers > 1 else 0.0)
+        self.out = nn.Linear(d_model, vocab_size)
+        if tie_weights and self.out.weight.shape == self.tok_emb.weight.shape:
+            self.out.weight = self.tok_emb.weight
+
+    @torch.no_grad()
+    def forward(self, z, tgt):
+        """logits [B, L', V] for any prefix length L' (fp32, eval semantics: no inter-layer dropout)."""
+        _need_cuda(tgt, "dec")
+        if self.training and self.gru.dropout > 0:
+            raise RuntimeError("dec() is the fp32 inference path; train with SAIL.elbo_step (dropout lives there)")
+        B, Lp = tgt.shape
+        dev = tgt.device
+        d = self.tok_emb.weight.shape[1]
+        N = B * Lp
+        bt = np.full(Lp, B, dtype=np.int32)
+        off = (np.arange(Lp + 1, dtype=np.int32) * B).astype(np.int32)
+        tok = tgt.t().contiguous().view(-1).to(torch.int32)           # time-major rows (t, b)
+        x = torch.empty(N, d, device=dev)
+        ops.tok_gather_fwd(self.tok_emb.weight.detach(), tok, x, None)
+        h0 = _linear_f32(z.to(torch.float32).contiguous(), self.z_proj, ops.EPI_TANH)
+        gh_ws = torch.empty(B, 3 * d, device=dev)
+        u = x
+        for k in range(self.gru.num_layers):
+            w_ih, w_hh = getattr(self.gru, f"weight_ih_l{k}").detach(), getattr(self.gru, f"weight_hh_l{k}").detach()
+            b_ih, b_hh = getattr(self.gru, f"bias_ih_l{k}").detach(), getattr(self.gru, f"bias_hh_l{k}").detach()
+            gi = torch.empty(N, 3 * d, device=dev)
+            ops.gemm(u, K, w_ih, K, gi, N, 3 * d, d, bias=b_ih, backend="simt")
+            hp = torch.empty(N, d, device=dev)
+            hp[:B].copy_(h0)
+            y = torch.empty(N, d, device=dev)
+            ops.gru_layer_fwd(None, hp, w_hh, gi, b_hh, bt, off, Lp, d, y, None, None, gh_ws, 0)
+            u = y
+        logits = _linear_f32(u, self.out)
+        return logits.view(Lp, B, -1).transpose(0, 1).contiguous()
+
+
+class SAIL(nn.Module):
+    """The KG-VAE.  Reference: models.py:144-320."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        mt = config["model_type"]
+        if mt == "SAIL":
+            self.enc = AutoRegEncoderMLP(
+                num_entities=config["n_entities"], num_relations=config["n_relations"], d_model=config["d_model"],
+                latent_dim=config["d_latent"], pad_eid=config.get("pad_eid"), pad_rid=config.get("pad_rid"),
+                n_layers=config["n_layers"])
+            self.dec = AutoRegDecoderGRU(
+                d_model=config["d_model"], num_layers=config["n_layers"], seq_len=config["seq_len"],
+                vocab_size=config["vocab_size"], latent_dim=config["d_latent"],
+                dropout=config.get("dec_dropout", 0.1), tie_weights=config.get("tie_weights", True))
+        elif mt == "t-SAIL":
+            raise NotImplementedError(
+                "model_type 't-SAIL' (Transformer encoder/decoder, reference models.py:66-114) is not built yet: "
+                "SURVEY.md §8 priority 2.  Use model_type 'SAIL'.")
+        else:
+            raise NotImplementedError(f"Unknown model_type: {mt}")
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._weights_changed())
+
+    # ---- engine plumbing -------------------------------------------------------------------------
+    def _attach_engine(self, engine):
+        object.__setattr__(self, "_engine", engine)
+
+    def _weights_changed(self):
+        if self._engine is not None:
+            self._engine.refresh_shadow()
+
+    def engine(self, **kw) -> SailEngine:
+        """The fused training engine bound to this module (created on first use; the module must be on CUDA)."""
+        if self._engine is None:
+            SailEngine(self, **kw)          # attaches itself
+        return self._engine
+
+    def elbo_step(self, triples, seq, beta, eps=None, layout: PackedLayout = None, lr=None,
+                  n_tok_global=None, batch_global=None):
+        """NEW fused entry: one optimisation step of ``CE + beta*KL`` (ablation_study.py:43,59-76) that never
+        materialises [B,L,V] probabilities.  ``triples``/``seq`` are the reference's LongTensors; ``eps`` defaults
+        to ``torch.randn(B, d_latent)`` from torch's global CUDA generator, the draw the reference makes at
+        models.py:63.  Returns a device tensor [ce, kl] (no host sync)."""
+        eng = self.engine()
+        if layout is None:
+            seq_host = seq if not seq.is_cuda else seq.cpu()
+            layout = pack_layout(seq_host).to(eng.device)
+        triples = triples.to(eng.device, non_blocking=True)
+        seq = seq.to(eng.device, non_blocking=True)
+        if eps is None:
+            eps = torch.randn(triples.shape[0], self.config["d_latent"], device=eng.device)
+        return eng.train_step(triples.contiguous(), seq.contiguous(), layout, eps.contiguous(), float(beta), lr,
+                              n_tok_global, batch_global)
+
+    # ---- reference interface -----------------------------------------------------------------------
+    def kl_mean(self, mu, logv):
+        return -0.5 * torch.mean(1 + logv - mu.pow(2) - logv.exp())
+
+    def forward(self, triples, seq_in):
+        z, mu, logv = self.enc(triples)
+        return self.dec(z, seq_in), mu, logv
+
+    def bits_per_sequence(self, seq, z, pad_id=0):
+        """AR bits of one sequence under teacher forcing (reference: models.py:202-213).  The GRU decoder is
+        causal, so one pass over the full prefix gives every per-position distribution the reference obtains
+        from its O(L^2) loop of growing prefixes."""
+        seq = seq.unsqueeze(0).to(z.device)
+        n = int((seq[0, 1:] != pad_id).long().cumprod(0).sum().item())   # stop at the first PAD target
+        if n == 0:
+            return 0.0
+        logp = F.log_softmax(self.dec(z, seq[:, :n]), dim=-1)[0]
+        tgt = seq[0, 1:n + 1]
+        return float(-(logp[torch.arange(n, device=z.device), tgt]).sum().item() / math.log(2))
+
+    @torch.no_grad()
+    def posterior_bits(self, dataset, device, pad_id=0, sample_frac=0.1, desc="posterior bits"):
+        """Reference: models.py:218-260."""
+        ln2 = math.log(2)
+        n = max(1, int(sample_frac * len(dataset)))
+        records = []
+        for i in range(n):
+            triples, seq = dataset[i]
+            triples = triples.unsqueeze(0).to(device)
+            z, mu, logv = self.enc(triples)
+            ar = self.bits_per_sequence(seq.to(device), z, pad_id)
+            kl = float((-0.5 * torch.sum(1 + logv - mu.pow(2) - logv.exp(), dim=1) / ln2).item())
+            records.append({"ar_bits": ar, "kl_bits": kl, "total_bits": ar + kl})
+        tot = np.array([r["total_bits"] for r in records])
+        return {"avg_total_bits": float(tot.mean()), "avg_ar_bits": float(np.mean([r["ar_bits"] for r in records])),
+                "avg_kl_bits": float(np.mean([r["kl_bits"] for r in records])), "min_total_bits": float(tot.min()),
+                "max_total_bits": float(tot.max()), "records": records}
+
+    @torch.no_grad()
+    def decode_latent(self, z, seq_len, special_tokens, seq_to_triples, ent_base, rel_base, beam=4):
+        self.eval()
+        z = z.to(next(self.parameters()).device, dtype=torch.float32)
+        return self.beam_generate(seq_len, special_tokens, seq_to_triples, z, ent_base, rel_base, beam=beam)
+
+    @torch.no_grad()
+    def count_unique_graphs(self, latent_dim, decode_latent_fn, num_samples=1000, beam=1):
+        self.eval()
+        z = torch.randn((num_samples, latent_dim), device=next(self.parameters()).device)
+        uniq = {canonical_graph_string(g) for g in decode_latent_fn(z, beam=beam)}
+        print(f"\n[Graph Diversity from {num_samples} Random Latents]")
+        print(f"  Unique graphs generated: {len(uniq)}")
+        print(f"  Diversity ratio: {len(uniq) / num_samples:.3f}")
+        return uniq
+
+    @torch.no_grad()
+    def beam_generate(self, seq_len, special_tokens, seq_to_triples, z, ent_base, rel_base, beam=4):
+        """Batch-shared beam search ranked by the batch-MEAN log-probability — the reference's exact
+        procedure (models.py:283-300), including re-decoding the whole prefix at every step."""
+        dev, B = z.device, z.size(0)
+        eos = special_tokens["EOS"]
+        beams = [(torch.full((B, 1), special_tokens["BOS"], dtype=torch.long, device=dev), torch.zeros(B, device=dev))]
+        for _ in range(seq_len - 1):
+            grown = []
+            for prefix, score in beams:
+                logp = F.log_softmax(self.dec(z, prefix)[:, -1], dim=-1)
+                best, idx = logp.topk(beam, dim=-1)
+                grown += [(torch.cat([prefix, idx[:, j:j + 1]], 1), score + best[:, j]) for j in range(beam)]
+            beams = sorted(grown, key=lambda c: c[1].mean().item(), reverse=True)[:beam]
+            if all(bool((p[:, -1] == eos).all()) for p, _ in beams):
+                break
+        return [seq_to_triples(row, special_tokens, ent_base, rel_base) for row in beams[0][0].cpu()]
+
+    @torch.no_grad()
+    def generate_test_graphs(self, test_loader, seq_len, special_tokens, seq_to_triples, ent_base, rel_base,
+                             beam_width=4, num_generated_test_graphs=1000, device="cuda"):
+        graphs = []
+        for triples, _ in test_loader:
+            z, *_ = self.enc(triples.to(device))
+            graphs.extend(self.beam_generate(seq_len, special_tokens, seq_to_triples, z, ent_base, rel_base,
+                                             beam=beam_width))
+            if len(graphs) >= num_generated_test_graphs:
+                return graphs[:num_generated_test_graphs]
+        return graphs
