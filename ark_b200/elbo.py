@@ -67,6 +67,7 @@ class SailEngine:
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._pending = []
+        self.prof = None
         self.stats = torch.zeros(4, device=dev)  # [ce, kl, steps, unused] accumulated on device
         self.refresh_shadow()
         if hasattr(model, "_attach_engine"):
@@ -80,9 +81,42 @@ class SailEngine:
     def _w(self, name):       # bf16 shadow view
         return self.flat.s(name)
 
-    def _gemm(self, A, am, B, bm, C, M, N, Kd, **kw):
+    def _gemm(self, A, am, B, bm, C, M, N, Kd, tag="gemm", **kw):
         backend = "tc" if (self.backend == "tc" and ops.tc_eligible(A, B)) else "simt"
-        ops.gemm(A, am, B, bm, C, M, N, Kd, backend=backend, **kw)
+        with self._timed(f"gemm_{backend}:{tag}", flops=2.0 * M * N * Kd):
+            ops.gemm(A, am, B, bm, C, M, N, Kd, backend=backend, **kw)
+
+    # ------------------------------------------------------------------ optional per-op device timing
+    class _Timer:
+        def __init__(self, eng, tag, flops, nbytes):
+            self.eng, self.tag, self.flops, self.nbytes = eng, tag, flops, nbytes
+
+        def __enter__(self):
+            if self.eng.prof is not None:
+                self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *exc):
+            if self.eng.prof is not None:
+                self.e1.record()
+                self.eng.prof.append((self.tag, self.e0, self.e1, self.flops, self.nbytes))
+
+    def _timed(self, tag, flops=0.0, nbytes=0.0):
+        """CUDA events around one op on the launching stream when `self.prof` is a list (bench.py's roofline
+        pass); free otherwise."""
+        return SailEngine._Timer(self, tag, flops, nbytes)
+
+    def profile_summary(self):
+        """tag -> dict(ms, calls, flops, bytes) from the recorded events (synchronises)."""
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, e0, e1, fl, nb in self.prof:
+            a = agg.setdefault(tag, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+            a["ms"] += e0.elapsed_time(e1)
+            a["calls"] += 1
+            a["flops"] += fl
+            a["bytes"] += nb
+        return agg
 
     # ------------------------------------------------------------------ forward + backward
     def forward_backward(self, triples, seq, lay: PackedLayout, eps, beta, n_tok_global=None, batch_global=None,
@@ -103,23 +137,24 @@ class SailEngine:
 
         # ---------------- encoder forward (models.py:46-64)
         g_b, inv_cnt = new(B, d3, dtype=bf), new(B)
-        ops.gather_pool_fwd(triples, lay.perm_dev, f.p("enc.e_emb.weight"), f.p("enc.r_emb.weight"), self.pad_rid,
-                            None, g_b, inv_cnt)
+        with self._timed("gather_pool_fwd", nbytes=3.0 * lay.n_triples * d * 4 + 3.0 * lay.n_triples * 8 + B * d3 * 2):
+            ops.gather_pool_fwd(triples, lay.perm_dev, f.p("enc.e_emb.weight"), f.p("enc.r_emb.weight"), self.pad_rid,
+                                None, g_b, inv_cnt)
         acts, pres = [g_b], []
         for k in range(self.n_mlp):
             a_next, pre = new(B, d3, dtype=bf), new(B, d3)
-            self._gemm(acts[-1], K, self._w(f"enc.mlp.{2 * k}.weight"), K, a_next, B, d3, d3,
+            self._gemm(acts[-1], K, self._w(f"enc.mlp.{2 * k}.weight"), K, a_next, B, d3, d3, tag="enc_mlp",
                        bias=f.p(f"enc.mlp.{2 * k}.bias"), epilogue=ops.EPI_GELU, aux=pre)
             acts.append(a_next)
             pres.append(pre)
         w_heads = f.fused(f.shadow, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
         b_heads = f.fused(f.param, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
         heads = new(B, 2 * dz)
-        self._gemm(acts[-1], K, w_heads, K, heads, B, 2 * dz, d3, bias=b_heads)
+        self._gemm(acts[-1], K, w_heads, K, heads, B, 2 * dz, d3, tag="enc_heads", bias=b_heads)
         z, z_b = new(B, dz), new(B, dz, dtype=bf)
         ops.reparam_kl_fwd(heads, eps, lay.perm_dev, dz, True, 1.0 / (b_g * dz), z, z_b, out[1:2])
         h0 = new(B, d)
-        self._gemm(z_b, K, self._w("dec.z_proj.weight"), K, h0, B, d, dz, bias=f.p("dec.z_proj.bias"),
+        self._gemm(z_b, K, self._w("dec.z_proj.weight"), K, h0, B, d, dz, tag="z_proj", bias=f.p("dec.z_proj.bias"),
                    epilogue=ops.EPI_TANH)
 
         # ---------------- decoder forward (models.py:136-142) over packed rows
@@ -133,14 +168,16 @@ class SailEngine:
         gh_ws = new(b0, d3)
         for k in range(nl):
             gi = new(N, d3)
-            self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, bias=f.p(f"dec.gru.bias_ih_l{k}"))
+            self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, tag="gru_gi",
+                       bias=f.p(f"dec.gru.bias_ih_l{k}"))
             hp_f, hp_b = new(N, d), new(N, d, dtype=bf)
             hp_f[:b0].copy_(h0[:b0])
             ops.cast_bf16(hp_f[:b0], hp_b[:b0])
             y, y_b = new(N, d), new(N, d, dtype=bf)
             gates = tuple(new(N, d) for _ in range(4))
-            ops.gru_layer_fwd(hp_b, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
-                              lay.bt, lay.off, L, d, y, y_b, gates, gh_ws, use_tc)
+            with self._timed("gru_layer_fwd", flops=2.0 * N * d * d3):
+                ops.gru_layer_fwd(hp_b, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
+                                  lay.bt, lay.off, L, d, y, y_b, gates, gh_ws, use_tc)
             mask = None
             if train and self.p_drop > 0 and k < nl - 1:
                 mask = new(N, d, dtype=torch.uint8)
@@ -151,18 +188,19 @@ class SailEngine:
             del gi, y
         logits = new(N, ldv, dtype=bf)
         w_out = self._w("dec.tok_emb.weight") if self.tied else self._w("dec.out.weight")
-        self._gemm(u_b, K, w_out, K, logits, N, V, d, bias=f.p("dec.out.bias"))
+        self._gemm(u_b, K, w_out, K, logits, N, V, d, tag="vocab_fwd", bias=f.p("dec.out.bias"))
         # CE forward+backward in place (ablation_study.py:64-69): logits -> (softmax-onehot)/N_tok
-        ops.softmax_ce(logits, V, tgt, 1.0 / n_tok_g, True, out[0:1], None)
+        with self._timed("softmax_ce", nbytes=2.0 * N * V * 2 + 12.0 * N):
+            ops.softmax_ce(logits, V, tgt, 1.0 / n_tok_g, True, out[0:1], None)
         if not train:
             return out
 
         # ---------------- decoder backward
         g_wout = f.g("dec.tok_emb.weight") if self.tied else f.g("dec.out.weight")
-        self._gemm(logits, MN, u_b, MN, g_wout, V, d, N)                      # dW = dLogits^T . Y
+        self._gemm(logits, MN, u_b, MN, g_wout, V, d, N, tag="vocab_dW")                      # dW = dLogits^T . Y
         ops.colsum(logits, N, V, f.g("dec.out.bias"))
         dy = new(N, d)
-        self._gemm(logits, K, w_out, MN, dy, N, d, V)                         # dY = dLogits . W
+        self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")                         # dY = dLogits . W
         del logits
         self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
         dh0 = None
@@ -172,55 +210,58 @@ class SailEngine:
             u_in, hp_f, hp_b, gates, mask = saved[k]
             if mask is not None:
                 ops.dropout_bwd(dy, mask, self.p_drop, dy)
-            dh_k = ops.gru_layer_bwd(dy, gates, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), lay.bt, lay.off, L, d,
-                                     dgi, dgh, dh_a, dh_b, use_tc)
+            with self._timed("gru_layer_bwd", flops=2.0 * N * d * d3):
+                dh_k = ops.gru_layer_bwd(dy, gates, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), lay.bt, lay.off, L, d,
+                                         dgi, dgh, dh_a, dh_b, use_tc)
             if dh0 is None:
                 dh0 = dh_k.clone()
             else:
                 ops.add_(dh0, dh_k, dh0, None)
-            self._gemm(dgi, MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N)
-            self._gemm(dgh, MN, hp_b, MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N)
+            self._gemm(dgi, MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
+            self._gemm(dgh, MN, hp_b, MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
             ops.colsum(dgi, N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
             ops.colsum(dgh, N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
-            self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3)   # grad w.r.t. layer input
+            self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3, tag="gru_dX")   # grad w.r.t. layer input
             self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
         if not self.tied:
             f.g("dec.tok_emb.weight").zero_()
-        ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
+        with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
+            ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
         self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
 
         # ---------------- h0 = tanh(W_z z + b_z), reparameterisation, KL
         dpre, dpre_b = new(B, d), new(B, d, dtype=bf)
         ops.tanh_bwd(dh0, h0, dpre, dpre_b)
-        self._gemm(dpre_b, MN, z_b, MN, f.g("dec.z_proj.weight"), d, dz, B)
+        self._gemm(dpre_b, MN, z_b, MN, f.g("dec.z_proj.weight"), d, dz, B, tag="z_proj_bwd")
         ops.colsum(dpre, B, d, f.g("dec.z_proj.bias"))
         dz_in = new(B, dz)
-        self._gemm(dpre_b, K, self._w("dec.z_proj.weight"), MN, dz_in, B, dz, d)
+        self._gemm(dpre_b, K, self._w("dec.z_proj.weight"), MN, dz_in, B, dz, d, tag="z_proj_bwd")
         ld_dh = _up8(2 * dz)
         dheads = torch.zeros(B, ld_dh, device=dev)
         dheads_b = torch.zeros(B, ld_dh, device=dev, dtype=bf)
         ops.reparam_kl_bwd(heads, eps, lay.perm_dev, dz_in, dz, True, beta / (b_g * dz), dheads, dheads_b)
         g_wh = f.fused(f.grad, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
         g_bh = f.fused(f.grad, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
-        self._gemm(dheads_b[:, :2 * dz], MN, acts[-1], MN, g_wh, 2 * dz, d3, B)
+        self._gemm(dheads_b[:, :2 * dz], MN, acts[-1], MN, g_wh, 2 * dz, d3, B, tag="enc_heads_bwd")
         ops.colsum(dheads, B, 2 * dz, g_bh)
         da = new(B, d3)
-        self._gemm(dheads_b[:, :2 * dz], K, w_heads, MN, da, B, d3, 2 * dz)
+        self._gemm(dheads_b[:, :2 * dz], K, w_heads, MN, da, B, d3, 2 * dz, tag="enc_heads_bwd")
         self._grad_ready("dec.z_proj.weight", "enc.logv.bias")
 
         # ---------------- encoder MLP + pooled gather backward
         for k in range(self.n_mlp - 1, -1, -1):
             dp_b = new(B, d3, dtype=bf)
             ops.gelu_bwd(da, pres[k], None, dp_b)
-            self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B)
+            self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B, tag="enc_mlp_bwd")
             ops.colsum(dp_b, B, d3, f.g(f"enc.mlp.{2 * k}.bias"))
             da = new(B, d3)
-            self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3)
+            self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3, tag="enc_mlp_bwd")
             self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
         gE, gR = f.g("enc.e_emb.weight"), f.g("enc.r_emb.weight")
-        gR.zero_()
-        gE.zero_()
-        ops.gather_pool_bwd(da, triples, lay.perm_dev, inv_cnt, self.pad_rid, self.pad_eid, gE, gR)
+        with self._timed("gather_pool_bwd", nbytes=gE.numel() * 4.0 + B * d3 * 4 + 3.0 * lay.n_triples * d * 8):
+            gR.zero_()
+            gE.zero_()
+            ops.gather_pool_bwd(da, triples, lay.perm_dev, inv_cnt, self.pad_rid, self.pad_eid, gE, gR)
         self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight")
         return out
 
@@ -261,8 +302,9 @@ class SailEngine:
         self._sync_grads()
         self.step_count += 1
         f = self.flat
-        ops.adam_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.lr if lr is None else lr,
-                      self.betas[0], self.betas[1], self.eps, self.step_count)
+        with self._timed("adam_flat", nbytes=30.0 * f.numel):
+            ops.adam_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.lr if lr is None else lr,
+                          self.betas[0], self.betas[1], self.eps, self.step_count)
 
     def train_step(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
         """zero_grad + forward + backward (+ all-reduce) + Adam: ablation_study.py:43,59-76."""
@@ -271,6 +313,10 @@ class SailEngine:
         self.stats[0:2] += out
         self.stats[2] += 1
         return out
+
+    def eval_step(self, triples, seq, lay, eps, beta):
+        """Forward only (validation loss, ablation_study.py:92-187 without the generation part)."""
+        return self.forward_backward(triples, seq, lay, eps, beta, train=False)
 
     def read_stats(self, beta, reset=True):
         """(avg_loss, avg_ce, avg_kl) since the last reset — ONE device->host read instead of the reference's

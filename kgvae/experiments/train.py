@@ -1,0 +1,291 @@
+"""``python -m kgvae.experiments.train --config configs/autoreg_<dataset>.yaml`` — KG-VAE training on B200.
+
+Same CLI, YAML schema, epoch flow, logged keys and checkpoint dictionary as the reference trainer
+(/root/reference/kgvae/experiments/train.py:241-624), with the SAIL / ELBO branches the reference keeps in
+ablation_study.py:59-81,589-591 merged in (SURVEY.md finding 3), and underneath:
+
+  * the train step is the fused ark_b200 ELBO engine (no autograd graph, no [B,L,V] probabilities);
+  * the optimiser is the fused flat Adam (same `optimizer_state_dict` layout);
+  * loss scalars are accumulated on the device and read back once per epoch instead of 3 .item() per step;
+  * data parallelism: run the same module under ``torchrun --nproc_per_node=G`` (one rank per GPU; NCCL
+    gradient all-reduce overlapped with backward; global CE/KL normalisers so the result equals the
+    single-process step on the concatenated batch);
+  * when `intelligraphs` is not installed (or ``synthetic: true``) the five dataset names resolve to
+    synthetic graphs of the same shape (ark_b200/synthetic.py) so the path runs offline.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import time
+import warnings
+
+import numpy as np
+import torch
+import yaml
+
+from ark_b200.layout import pack_layout
+from ark_b200.optim import FusedAdam
+from ark_b200.synthetic import DATASET_SHAPES
+from kgvae.model.models import SAIL
+from kgvae.model.utils import GraphSeqDataset, build_batch, canonical_graph_string, ints_to_labels, seq_to_triples
+
+SPECIAL = {"PAD": 0, "BOS": 1, "EOS": 2}
+
+
+# --------------------------------------------------------------------------------------------- logging
+class _NullRun:
+    id = "offline"
+
+
+class _Log:
+    """wandb when it is importable and not disabled; otherwise a dict-printing stand-in with the same calls."""
+
+    def __init__(self, project, entity, config, name, rank):
+        self.wandb, self.config, self.run = None, dict(config), _NullRun()
+        if rank == 0 and os.environ.get("WANDB_MODE", "") != "disabled":
+            try:
+                import wandb
+                kw = dict(project=project, config=config, name=name, anonymous="allow")
+                if entity:
+                    kw["entity"] = entity
+                wandb.init(**kw)
+                self.wandb, self.config, self.run = wandb, dict(wandb.config), wandb.run
+            except Exception as e:  # no network / not installed
+                print(f"[train] wandb unavailable ({type(e).__name__}); logging to stdout")
+
+    def log(self, d):
+        if self.wandb is not None:
+            self.wandb.log(d)
+        else:
+            print("[log]", {k: (round(v, 6) if isinstance(v, float) else v) for k, v in d.items()})
+
+    def finish(self):
+        if self.wandb is not None:
+            self.wandb.finish()
+
+
+# --------------------------------------------------------------------------------------------- data
+def load_graphs(config, seed=1234):
+    """(train, val, test, (e2i,i2e), (r2i,i2r), (min_edges,max_edges)) — intelligraphs when present, else
+    synthetic graphs shaped like the named dataset."""
+    name = config["dataset"]
+    mode = str(config.get("synthetic", "auto")).lower()
+    if mode not in ("true", "1"):
+        try:
+            from intelligraphs.data_loaders import load_data_as_list
+            tr, va, te, ent, rel, edges, *_ = load_data_as_list(name)
+            return tr, va, te, ent, rel, edges
+        except ImportError:
+            if mode == "false":
+                raise
+            print(f"[train] intelligraphs not installed: using synthetic {name}-shaped graphs")
+    nE, nR, lo, hi, _ = DATASET_SHAPES[name]
+    rng = np.random.default_rng(seed)
+
+    def make(n):
+        sizes = rng.integers(lo, hi + 1, n)
+        return [[(int(rng.integers(nE)), int(rng.integers(nR)), int(rng.integers(nE))) for _ in range(k)] for k in sizes]
+
+    tr = make(int(config.get("synthetic_train_graphs", 4096)))
+    va = make(int(config.get("synthetic_val_graphs", 256)))
+    te = make(int(config.get("synthetic_val_graphs", 256)))
+    e2i = {f"e{i}": i for i in range(nE)}
+    r2i = {f"r{i}": i for i in range(nR)}
+    return tr, va, te, (e2i, {v: k for k, v in e2i.items()}), (r2i, {v: k for k, v in r2i.items()}), (lo, hi)
+
+
+class BatchLoader:
+    """Rank-sharded, vectorised replacement of DataLoader(GraphSeqDataset) for the train step.
+
+    Global batch g covers graphs [g*B*W, (g+1)*B*W); rank r owns the r-th slice of B graphs (drop_last).
+    Every rank can see all lengths, so the GLOBAL non-PAD token count of a step needs no collective.
+    Yields (triples, seq, n_tok_global) with pinned host tensors in the reference's format.
+    """
+
+    def __init__(self, graphs, vocab, batch_size, rank=0, world=1, shuffle=False, drop_last=True, permute=False,
+                 seed=0):
+        self.graphs, self.v, self.B, self.rank, self.world = graphs, vocab, batch_size, rank, world
+        self.shuffle, self.drop_last, self.permute, self.epoch, self.seed = shuffle, drop_last, permute, 0, seed
+        self.lens = np.fromiter((3 * len(g) + 1 for g in graphs), dtype=np.int64, count=len(graphs))
+
+    def __len__(self):
+        per = self.B * self.world
+        return len(self.graphs) // per if self.drop_last else math.ceil(len(self.graphs) / per)
+
+    def __iter__(self):
+        order = np.arange(len(self.graphs))
+        if self.shuffle:
+            np.random.default_rng(self.seed + self.epoch).shuffle(order)
+        self.epoch += 1
+        per = self.B * self.world
+        for g in range(len(self)):
+            idx = order[g * per:(g + 1) * per]
+            mine = idx[self.rank * self.B:(self.rank + 1) * self.B]
+            if len(mine) == 0:
+                continue
+            gs = [self.graphs[i] for i in mine]
+            if self.permute and not self.v["use_padding"]:      # reference: utils.py:133-134
+                rng = np.random.default_rng(self.seed + 7919 * self.epoch + g)
+                gs = [[gr[j] for j in rng.permutation(len(gr))] for gr in gs]
+            tri, seq = build_batch(gs, special_tokens=SPECIAL, ent_base=self.v["ENT_BASE"], rel_base=self.v["REL_BASE"],
+                                   seq_len=self.v["seq_len"], max_triples=self.v["max_edges"],
+                                   use_padding=self.v["use_padding"], pad_eid=self.v["pad_eid"],
+                                   pad_rid=self.v["pad_rid"], pin=True)
+            yield tri, seq, int(self.lens[idx].sum()), len(idx)
+
+
+# --------------------------------------------------------------------------------------------- loops
+def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None):
+    """One epoch of ELBO steps (reference: ablation_study.py:31-88, SAIL branch :59-81).
+    Returns (avg_loss, avg_recon, avg_kl, avg_entity_loss) like the reference."""
+    if config.get("model_type", "ARK") not in ("SAIL",):
+        raise NotImplementedError("only model_type 'SAIL' runs on the fused path (see DESIGN.md)")
+    model.train()
+    eng = model.engine()
+    eng.stats.zero_()
+    for i, batch in enumerate(dataloader):
+        triples, seq = batch[0], batch[1]
+        ntg = batch[2] if len(batch) > 2 else None
+        bg = batch[3] if len(batch) > 3 else None
+        optimizer.zero_grad()
+        model.elbo_backward(triples, seq, b, eps=None if eps_fn is None else eps_fn(i), n_tok_global=ntg,
+                            batch_global=bg)
+        optimizer.step()
+    loss, ce, kl = eng.read_stats(b)            # one device->host read for the whole epoch
+    return loss, ce, kl, 0.0
+
+
+@torch.no_grad()
+def validate(model, dataloader, config, device, b=1.0):
+    """Validation loss terms (reference: ablation_study.py:92-187, loss part), forward only."""
+    model.eval()
+    eng = model.engine()
+    acc, n = torch.zeros(2, device=eng.device), 0
+    for batch in dataloader:
+        triples, seq = batch[0].to(eng.device), batch[1].to(eng.device)
+        lay = pack_layout(batch[1]).to(eng.device)
+        eps = torch.randn(triples.shape[0], config["d_latent"], device=eng.device)
+        acc += eng.eval_step(triples.contiguous(), seq.contiguous(), lay, eps, b)
+        n += 1
+    ce, kl = (acc / max(n, 1)).tolist()
+    return ce + b * kl, ce, kl
+
+
+def cosine_lr(base, epoch, t_max, eta_min):
+    return eta_min + (base - eta_min) * (1 + math.cos(math.pi * epoch / t_max)) / 2
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=str, required=True, help="Path to config file")
+    ap.add_argument("--wandb-project", type=str, default="submission", help="Weights & Biases project name")
+    ap.add_argument("--wandb-entity", type=str, default=None, help="Weights & Biases entity")
+    ap.add_argument("--checkpoint-dir", type=str, default="checkpoints", help="Directory to save checkpoints")
+    ap.add_argument("--max-epochs", type=int, default=None, help="(new) stop early, for smoke runs")
+    args = ap.parse_args(argv)
+
+    with open(args.config) as f:
+        config = yaml.safe_load(f)
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    if not torch.cuda.is_available():
+        raise RuntimeError("kgvae.experiments.train runs on B200 GPUs only (ark_b200 has no CPU path)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+        group = torch.distributed.group.WORLD
+
+    log = _Log(args.wandb_project, args.wandb_entity or os.getenv("WANDB_ENTITY"), config,
+               config.get("experiment_name", "ARK_experiment"), rank)
+    config.update(log.config)                                   # sweep overrides (reference train.py:273)
+    config["learning_rate"] = float(config.get("learning_rate", 1e-3))
+    run_dir = os.path.join(args.checkpoint_dir, str(log.run.id))
+    if rank == 0:
+        os.makedirs(run_dir, exist_ok=True)
+        with open(os.path.join(run_dir, "effective_config.yaml"), "w") as f:
+            yaml.safe_dump(config, f)
+    log.log({"objective": 1e12})
+    if config.get("use_test_for_final_eval", False) and rank == 0:
+        warnings.warn("Test set evaluation ENABLED! Only use for final evaluation, NOT for hyperparameter tuning!",
+                      UserWarning, stacklevel=2)
+
+    model_type = config.get("model_type", "ARK")
+    if model_type != "SAIL":
+        raise NotImplementedError(
+            f"model_type '{model_type}': this build accelerates the KG-VAE ELBO path (model_type: SAIL). "
+            "ARK / t-ARK / t-SAIL are the next rows of the scope table (DESIGN.md).")
+
+    train_g, val_g, test_g, (e2i, i2e), (r2i, i2r), (min_edges, max_edges) = load_graphs(config)
+    n_ent, n_rel = len(e2i), len(r2i)
+    use_padding = config.get("use_padding", config["dataset"].startswith("wd-"))
+    pad_eid = pad_rid = None
+    if use_padding:                                            # reference: ablation_study.py:436-447
+        pad_eid, pad_rid = n_ent, n_rel
+        n_ent, n_rel = n_ent + 1, n_rel + 1
+    ent_base = 3
+    rel_base = ent_base + n_ent
+    vocab = {"ENT_BASE": ent_base, "REL_BASE": rel_base, "seq_len": 3 * max_edges + 2, "max_edges": max_edges,
+             "use_padding": use_padding, "pad_eid": pad_eid, "pad_rid": pad_rid}
+    config.update({"n_entities": n_ent, "n_relations": n_rel, "pad_eid": pad_eid, "pad_rid": pad_rid,
+                   "seq_len": vocab["seq_len"], "vocab_size": rel_base + n_rel, "special_tokens": SPECIAL,
+                   "ENT_BASE": ent_base, "REL_BASE": rel_base})
+
+    B = config["batch_size"]
+    train_loader = BatchLoader(train_g, vocab, B, rank, world, shuffle=config["shuffle_train"], drop_last=True,
+                               permute=config.get("permute_triples", False))
+    val_loader = BatchLoader(val_g, vocab, B, 0, 1, drop_last=False)
+    if rank == 0:
+        print(f"Dataset: {config['dataset']}  Entities: {n_ent}, Relations: {n_rel}")
+        print(f"Train batches: {len(train_loader)}, Val batches: {len(val_loader)}  world={world}")
+
+    torch.manual_seed(0)
+    model = SAIL(config).to(device)
+    optimizer = FusedAdam(model, lr=config["learning_rate"], dist_group=group,
+                          bucket_mb=float(config.get("ddp_bucket_mb", 32)))
+    scheduler = None
+    if config.get("lr_scheduler", False):
+        scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=config["num_epochs"],
+                                                               eta_min=config.get("eta_min", 1e-6))
+    best_val = float("inf")
+    n_epochs = config["num_epochs"] if args.max_epochs is None else min(config["num_epochs"], args.max_epochs)
+    for epoch in range(n_epochs):
+        b = config["beta0"] + (config["beta1"] - config["beta0"]) * epoch / config["num_epochs"]
+        t0 = time.perf_counter()
+        tr = train_epoch(model, train_loader, optimizer, config, device, b)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_tri = sum(len(g) for g in train_g[:len(train_loader) * B * world])
+        va = validate(model, val_loader, config, device, b) if rank == 0 else (0.0, 0.0, 0.0)
+        if rank == 0:
+            print(f"\nEpoch {epoch + 1}/{config['num_epochs']}  loss {tr[0]:.4f} ce {tr[1]:.4f} kl {tr[2]:.4f}  "
+                  f"val {va[0]:.4f}  {n_tri / dt:,.0f} triples/s")
+            log.log({"epoch": epoch, "train/loss": tr[0], "train/reconstruction_loss": tr[1], "train/kl_loss": tr[2],
+                     "val/loss": va[0], "val/reconstruction_loss": va[1], "val/kl_loss": va[2], "beta": b,
+                     "learning_rate": optimizer.param_groups[0]["lr"], "triples_per_sec": n_tri / dt,
+                     "step_ms": 1e3 * dt / max(len(train_loader), 1)})
+        if scheduler is not None:
+            scheduler.step()
+        if rank == 0:
+            ckpt = {"epoch": epoch, "model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+                    "optimizer_state_dict": optimizer.state_dict(),
+                    "scheduler_state_dict": scheduler.state_dict() if scheduler else None, "val_loss": va[0],
+                    "config": config, "vocabs": {"e2i": e2i, "i2e": i2e, "r2i": r2i, "i2r": i2r},
+                    "dataset_meta": {"min_edges": min_edges, "max_edges": max_edges}}
+            tag = f"{config['dataset']}_{model_type}"
+            if va[0] < best_val:
+                best_val = va[0]
+                torch.save(ckpt, os.path.join(run_dir, f"{tag}_best_model.pt"), _use_new_zipfile_serialization=False)
+            if (epoch + 1) % int(config.get("save_every", 50)) == 0:
+                torch.save(ckpt, os.path.join(run_dir, f"{tag}_checkpoint_epoch_{epoch + 1}.pt"),
+                           _use_new_zipfile_serialization=False)
+    log.finish()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return model
+
+
+if __name__ == "__main__":
+    main()

@@ -175,22 +175,31 @@ class SAIL(nn.Module):
             SailEngine(self, **kw)          # attaches itself
         return self._engine
 
-    def elbo_step(self, triples, seq, beta, eps=None, layout: PackedLayout = None, lr=None,
-                  n_tok_global=None, batch_global=None):
-        """NEW fused entry: one optimisation step of ``CE + beta*KL`` (ablation_study.py:43,59-76) that never
-        materialises [B,L,V] probabilities.  ``triples``/``seq`` are the reference's LongTensors; ``eps`` defaults
-        to ``torch.randn(B, d_latent)`` from torch's global CUDA generator, the draw the reference makes at
+    def elbo_backward(self, triples, seq, beta, eps=None, layout: PackedLayout = None,
+                      n_tok_global=None, batch_global=None):
+        """NEW fused entry: forward + backward of ``CE + beta*KL`` (ablation_study.py:59-75) that never
+        materialises [B,L,V] probabilities; gradients land in every parameter's ``.grad`` (overwritten).
+        ``triples``/``seq`` are the reference's LongTensors (host or device); ``eps`` defaults to
+        ``torch.randn(B, d_latent)`` from torch's global CUDA generator — the draw the reference makes at
         models.py:63.  Returns a device tensor [ce, kl] (no host sync)."""
         eng = self.engine()
         if layout is None:
-            seq_host = seq if not seq.is_cuda else seq.cpu()
-            layout = pack_layout(seq_host).to(eng.device)
-        triples = triples.to(eng.device, non_blocking=True)
-        seq = seq.to(eng.device, non_blocking=True)
+            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+        triples = triples.to(eng.device, non_blocking=True).contiguous()
+        seq = seq.to(eng.device, non_blocking=True).contiguous()
         if eps is None:
             eps = torch.randn(triples.shape[0], self.config["d_latent"], device=eng.device)
-        return eng.train_step(triples.contiguous(), seq.contiguous(), layout, eps.contiguous(), float(beta), lr,
-                              n_tok_global, batch_global)
+        out = eng.forward_backward(triples, seq, layout, eps.contiguous(), float(beta), n_tok_global, batch_global)
+        eng.stats[0:2] += out
+        eng.stats[2] += 1
+        return out
+
+    def elbo_step(self, triples, seq, beta, eps=None, layout: PackedLayout = None, lr=None,
+                  n_tok_global=None, batch_global=None):
+        """elbo_backward + the fused Adam update: one full optimisation step (ablation_study.py:43,59-76)."""
+        out = self.elbo_backward(triples, seq, beta, eps, layout, n_tok_global, batch_global)
+        self._engine.adam_step(lr)
+        return out
 
     # ---- reference interface -----------------------------------------------------------------------
     def kl_mean(self, mu, logv):

@@ -200,3 +200,39 @@ def test_dropout_train_mode_is_statistically_sane():
     assert a[0] != b[0]                                  # fresh Philox masks every step
     assert abs(a[0] - c[0]) / c[0] < 0.1 and abs(b[0] - c[0]) / c[0] < 0.1
     assert torch.isfinite(eng.flat.grad).all()
+
+
+def test_train_epoch_matches_reference_golden():
+    """The drop-in kgvae.experiments.train.train_epoch against the reference's ablation_study.train_epoch
+    (3 batches, dec_dropout 0, Adam lr 5e-3) with the reference's eps draws injected."""
+    from ark_b200.optim import FusedAdam
+    from kgvae.experiments.train import train_epoch
+    arr = dict(np.load(os.path.join(GOLDEN, "train_epoch.npz")))
+    with open(os.path.join(GOLDEN, "train_epoch.json")) as f:
+        meta = json.load(f)
+    params = {k[len("param::"):]: v for k, v in arr.items() if k.startswith("param::")}
+    model = _model_from(params, meta["cfg"])
+    opt = FusedAdam(model, lr=meta["lr"])
+    batches = [(torch.from_numpy(arr[f"triples{i}"]), torch.from_numpy(arr[f"seq{i}"])) for i in range(3)]
+    res = train_epoch(model, batches, opt, meta["cfg"], DEV, meta["beta"],
+                      eps_fn=lambda i: torch.from_numpy(arr[f"eps{i}"]).to(DEV))
+    np.testing.assert_allclose(res[:3], arr["result"], rtol=2e-2)
+    sd = opt.state_dict()
+    assert len(sd["state"]) == len(list(model.parameters())) and "exp_avg" in sd["state"][0]
+
+
+def test_state_dict_roundtrip_keeps_engine_in_sync():
+    arr, meta, params, _ = load_sail_golden("wd")
+    model = _model_from(params, meta["cfg"])
+    eng = model.engine()
+    triples, seq = torch.from_numpy(arr["triples"]).to(DEV), torch.from_numpy(arr["seq"])
+    lay = pack_layout(seq).to(DEV)
+    eps = torch.from_numpy(arr["eps"]).to(DEV)
+    a = eng.forward_backward(triples, seq.to(DEV), lay, eps, 0.25, train=False).clone()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(0.5)
+    model.load_state_dict(sd)            # post-hook refreshes the bf16 shadow
+    b = eng.forward_backward(triples, seq.to(DEV), lay, eps, 0.25, train=False)
+    assert torch.equal(a, b)

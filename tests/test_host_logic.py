@@ -1,0 +1,169 @@
+"""CPU-side tests: C-ABI exports, packing layout, flat parameter storage, batch sharding, and the
+data-parallel normaliser logic (2-process gloo) checked with the numpy oracle.  No GPU compute."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from ark_b200 import _C
+from ark_b200.flat import FlatParams, sail_param_order
+from ark_b200.layout import pack_layout, unpack_rows
+from ark_b200.synthetic import model_config, synth_batch, vocab_layout
+from oracle import sail_oracle as O
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _C.lib()
+    header = open(_C.HEADER).read()
+    declared = set(re.findall(r"\b(ark_\w+)\s*\(", header))
+    assert declared and declared == set(lib.protos)
+    dll = ctypes.CDLL(_C.LIB_PATH)
+    for name in declared:
+        assert hasattr(dll, name), name
+    assert dll.ark_abi_version() == 1
+
+
+def test_argument_validation_happens_before_any_launch():
+    lib = _C.lib()
+    with pytest.raises(_C.ArkError, match="null pointer"):
+        lib.call("ark_softmax_ce", None, 1, 4, 10, 16, None, 1.0, 1, None, None, None)
+    with pytest.raises(_C.ArkError, match="multiple of 8"):
+        lib.call("ark_softmax_ce", ctypes.c_void_p(256), 1, 4, 10, 10, ctypes.c_void_p(256), 1.0, 1, None, None, None)
+    with pytest.raises(_C.ArkError, match="TMA needs"):
+        lib.call("ark_gemm_bf16_tc", ctypes.c_void_p(256), 0, 10, ctypes.c_void_p(512), 0, 16, ctypes.c_void_p(1024), 0,
+                 16, 4, 4, 10, None, 0, 0, None, None)
+
+
+def test_product_path_refuses_cpu_tensors():
+    from kgvae.model.models import SAIL
+    cfg = model_config("syn-paths", d_model=16, d_latent=4, n_layers=1)
+    m = SAIL(cfg)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.enc(torch.zeros(2, 3, 3, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.engine()
+
+
+def test_pack_layout_properties():
+    lay_cfg = vocab_layout("wd-movies")
+    tri, seq, n_tri = synth_batch(lay_cfg, 37, seed=3)
+    lay = pack_layout(seq)
+    lens = (seq[:, 1:] != 0).sum(1).numpy()
+    assert lay.n_tok == lens.sum() and lay.n_triples == n_tri == int(((lens - 1) // 3).sum())
+    assert (np.diff(lay.bt) <= 0).all() and lay.bt[0] == 37 and lay.L == lens.max()
+    assert (lens[lay.perm][:-1] >= lens[lay.perm][1:]).all()
+    assert (lay.off[1:] - lay.off[:-1] == lay.bt).all()
+    # pack -> unpack round trip of the target tokens
+    rows = []
+    for t in range(lay.L):
+        rows += [seq[lay.perm[j], t + 1].item() for j in range(lay.bt[t])]
+    dense = unpack_rows(torch.tensor(rows), lay, 37, seq.shape[1] - 1, fill=0)
+    assert torch.equal(dense, seq[:, 1:])
+    # valid triples <-> mask agreement with the reference rule (relation != pad_rid)
+    assert int((tri[:, :, 1] != lay_cfg["pad_rid"]).sum()) == n_tri
+
+
+def test_synthetic_batches_follow_reference_token_layout():
+    for ds in ("syn-paths", "wd-articles"):
+        lay = vocab_layout(ds)
+        tri, seq, _ = synth_batch(lay, 5, seed=1)
+        olay = O.vocab_layout(lay["n_entities_raw"], lay["n_relations_raw"], lay["max_edges"], lay["use_padding"])
+        for k in ("vocab_size", "seq_len", "ENT_BASE", "REL_BASE", "pad_eid", "pad_rid", "n_entities", "n_relations"):
+            assert lay[k] == olay[k]
+        for b in range(5):
+            g = [tuple(int(x) for x in t) for t in tri[b] if lay["pad_rid"] is None or t[1] != lay["pad_rid"]]
+            assert O.triples_to_seq(g, olay).tolist() == seq[b].tolist()
+
+
+def test_flat_params_alias_module_and_keep_state_dict():
+    from kgvae.model.models import SAIL
+    cfg = model_config("wd-movies", d_model=16, d_latent=4, n_layers=2)
+    cfg.update(vocab_layout("wd-movies"))
+    cfg.update(n_entities=50, n_relations=4, vocab_size=57, pad_eid=49, pad_rid=3)
+    torch.manual_seed(0)
+    m = SAIL(cfg)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = FlatParams(sail_param_order(m), "cpu")
+    after = m.state_dict()
+    assert list(before) == list(after)
+    for k in before:
+        assert torch.equal(before[k], after[k])
+    assert m.dec.out.weight is m.dec.tok_emb.weight
+    # module parameters alias the flat buffer; mu/logv are adjacent (one fused [2dz, 3d] operand)
+    flat.param.add_(1.0)
+    assert torch.equal(m.enc.mu.weight.data, before["enc.mu.weight"] + 1)
+    fused = flat.fused(flat.param, "enc.mu.weight", "enc.logv.weight", (8, 48))
+    assert torch.equal(fused[:4], m.enc.mu.weight.data) and torch.equal(fused[4:], m.enc.logv.weight.data)
+    for name, (off, n, shape) in flat.slots.items():
+        assert off % 4 == 0
+    assert flat.slots["dec.out.bias"][0] == 0        # first gradient to become final
+
+
+def test_batch_loader_shards_and_global_counts():
+    from kgvae.experiments.train import BatchLoader
+    rng = np.random.default_rng(0)
+    graphs = [[(int(rng.integers(9)), int(rng.integers(2)), int(rng.integers(9))) for _ in range(int(rng.integers(1, 5)))]
+              for _ in range(37)]
+    v = {"ENT_BASE": 3, "REL_BASE": 13, "seq_len": 14, "max_edges": 4, "use_padding": True, "pad_eid": 9, "pad_rid": 2}
+    seen = []
+    for r in range(2):
+        for tri, seq, ntg, bg in BatchLoader(graphs, v, 4, rank=r, world=2):
+            assert tri.shape == (4, 4, 3) and seq.shape == (4, 14) and bg == 8
+            seen.append((r, seq, ntg))
+    assert len(seen) == 2 * (37 // 8)
+    for g in range(37 // 8):
+        a, b = seen[g], seen[37 // 8 + g]
+        local = int((a[1][:, 1:] != 0).sum() + (b[1][:, 1:] != 0).sum())
+        assert a[2] == b[2] == local                    # every rank derives the same GLOBAL token count
+
+
+_DDP_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import sail_oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+rng = np.random.default_rng(0)
+lay = O.vocab_layout(30, 3, 5, True)
+graphs = [[(int(rng.integers(30)), int(rng.integers(3)), int(rng.integers(30))) for _ in range(int(rng.integers(1, 6)))] for _ in range(8)]
+tri, seq = O.build_batch(graphs, lay)
+cfg = dict(lay, model_type="SAIL", d_model=8, d_latent=4, n_layers=2)
+prng = np.random.default_rng(1)
+shapes = {"enc.e_emb.weight": (31, 8), "enc.r_emb.weight": (4, 8), "enc.mlp.0.weight": (24, 24), "enc.mlp.0.bias": (24,),
+          "enc.mlp.2.weight": (24, 24), "enc.mlp.2.bias": (24,), "enc.mu.weight": (4, 24), "enc.mu.bias": (4,),
+          "enc.logv.weight": (4, 24), "enc.logv.bias": (4,), "dec.tok_emb.weight": (38, 8), "dec.z_proj.weight": (8, 4),
+          "dec.z_proj.bias": (8,), "dec.out.bias": (38,)}
+for k in range(2):
+    shapes.update({f"dec.gru.weight_ih_l{k}": (24, 8), f"dec.gru.weight_hh_l{k}": (24, 8), f"dec.gru.bias_ih_l{k}": (24,), f"dec.gru.bias_hh_l{k}": (24,)})
+params = {k: prng.standard_normal(s) * 0.3 for k, s in shapes.items()}
+eps = prng.standard_normal((8, 4))
+whole_l, whole_g, _ = O.elbo_step(params, cfg, tri, seq, eps, 0.5)
+sl = slice(rank * 4, rank * 4 + 4)
+n_tok_global = int((seq[:, 1:] != 0).sum())
+loc_l, loc_g, _ = O.elbo_step(params, cfg, tri[sl], seq[sl], eps[sl], 0.5, n_tok_global=n_tok_global, batch_global=8)
+flat = torch.from_numpy(np.concatenate([loc_g[k].ravel() for k in sorted(loc_g)]))
+dist.all_reduce(flat)                                   # ncclSum in production; gradients are SUMMED, never averaged
+ref = np.concatenate([whole_g[k].ravel() for k in sorted(whole_g)])
+st = torch.tensor([loc_l["ce"], loc_l["kl"]], dtype=torch.float64)
+dist.all_reduce(st)
+assert np.allclose(flat.numpy(), ref, rtol=1e-9, atol=1e-12), np.abs(flat.numpy() - ref).max()
+assert np.allclose(st.numpy(), [whole_l["ce"], whole_l["kl"]], rtol=1e-12)
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_two_rank_gloo_gradient_sum_equals_whole_batch(tmp_path):
+    script = tmp_path / "ddp_worker.py"
+    script.write_text(_DDP_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == 2
