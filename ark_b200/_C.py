@@ -73,6 +73,10 @@ class _Lib:
             msg = self._dll.ark_last_error()
             raise ArkError(f"{name} failed (code {rc}): {msg.decode() if msg else ''}")
 
+    def raw(self, name):
+        """The bare ctypes function (for entry points whose int result is a value, not a status)."""
+        return getattr(self._dll, name)
+
     def launch_count(self) -> int:
         return int(self._dll.ark_launch_count())
 

@@ -111,6 +111,25 @@ __global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restric
   }
 }
 
+__global__ void __launch_bounds__(256) dropout_bf16_kernel(const uint16_t* __restrict__ x, int64_t n, float p,
+                                                           uint64_t seed, uint64_t offset, uint16_t* __restrict__ y,
+                                                           uint8_t* __restrict__ mask) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = q * 4;
+  if (i >= n) return;
+  const uint64_t c = offset + (uint64_t)q;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  const float scale = 1.f / (1.f - p);
+  for (int k = 0; k < 4 && i + k < n; ++k) {
+    const float u = (float)(rr[k] >> 8) * (1.f / 16777216.f);
+    const bool keep = u >= p;
+    if (mask) mask[i + k] = keep ? 1 : 0;
+    y[i + k] = keep ? f32_to_bf16_bits(bf16_bits_to_f32(x[i + k]) * scale) : (uint16_t)0;
+  }
+}
+
 __global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask,
                                                           int64_t n, float scale, float* __restrict__ dx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,6 +274,15 @@ extern "C" int ark_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed
   dropout_fwd_kernel<<<blocks_for((n + 3) / 4, 256, 0), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y,
                                                                                        y_bf16, mask);
   return launched("dropout_fwd");
+}
+
+extern "C" int ark_dropout_bf16(const uint16_t* x, int64_t n, float p, uint64_t seed, uint64_t offset, uint16_t* y,
+                                uint8_t* mask, void* stream) {
+  ARK_REQUIRE(x && y, ARK_E_BADARG, "dropout_bf16: null pointer");
+  ARK_REQUIRE(p >= 0.f && p < 1.f, ARK_E_BADARG, "dropout_bf16: p must be in [0,1)");
+  if (n <= 0) return 0;
+  dropout_bf16_kernel<<<blocks_for((n + 3) / 4, 256, 0), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, mask);
+  return launched("dropout_bf16");
 }
 
 extern "C" int ark_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, void* stream) {

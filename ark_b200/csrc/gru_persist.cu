@@ -1,0 +1,565 @@
+// K6 (persistent): one GRU layer through ALL time steps in ONE cooperative launch, forward and backward.
+//
+// Replaces nn.GRU's recurrence (kgvae/model/models.py:121-127,141) — in the reference a cuDNN/ATen loop of
+// L dependent steps per layer; in the first version of this library 2 launches per step (launch-bound:
+// 5.6-14 us/step measured).  Here the L steps run inside one kernel:
+//
+//   grid = (d/DJ hidden slices) x (ceil(B/128) batch tiles), one CTA per SM, all co-resident.
+//   CTA (ji, bi) keeps ITS slice of W_hh resident in shared memory for the whole sequence
+//     forward : rows {g*d + j0 .. j0+DJ} (g = r,z,n) of W_hh[3d,d]    -> UMMA B operand [3*DJ x d], K = d
+//     backward: rows {j0 .. j0+DJ} of W_hh^T[d,3d]                     -> UMMA B operand [DJ x 3d],  K = 3d
+//   per step it streams the A operand (h_{t-1} rows, resp. dgh_{t+1} rows: bf16, written to HBM/L2 by all
+//   CTAs of the batch tile in the previous step) through a TMA ring, accumulates in TMEM, and runs the gate
+//   math in the epilogue warps straight out of TMEM.  The recurrent state of the CTA's own (row, slice)
+//   elements never leaves registers.  CTAs of one batch tile synchronise through ONE release/acquire counter
+//   per tile in global memory (different batch tiles never wait for each other).
+//
+// Rows are the packed, length-sorted layout of ark_b200/layout.py: step t owns rows [off[t], off[t]+bt[t]),
+// bt non-increasing, so a thread always serves the same graph and inactive tiles simply leave the loop.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+#include "gru_math.cuh"
+#include <cooperative_groups.h>
+
+namespace ark {
+
+constexpr int GP_BM = 128;
+constexpr int GP_BK = 64;
+constexpr int GP_A_BYTES = GP_BM * GP_BK * 2;  // 16 KB per ring stage
+
+struct GruPersistFwdParams {
+  const int32_t* bt;
+  const int32_t* off;
+  int L, d;
+  int32_t* sync;       // [n batch tiles], zeroed before launch
+  const float* gi;     // [N, 3d] = W_ih x + b_ih
+  const float* b_hh;   // [3d]
+  const float* h0;     // [bt[0], d] fp32 initial state
+  uint16_t* hp_b;      // [N, d] bf16 packed h_prev rows (block 0 pre-filled with bf16(h0)); written for t+1
+  uint16_t* y_b;       // [N, d] bf16 outputs
+  uint16_t *r, *z, *n, *ghn;  // [N, d] bf16 saved gates (may all be null)
+};
+
+struct GruPersistBwdParams {
+  const int32_t* bt;
+  const int32_t* off;
+  int L, d;
+  int32_t* sync;
+  const float* dy;                          // [N, d] gradient w.r.t. the layer outputs
+  const uint16_t *r, *z, *n, *ghn, *hp_b;   // saved by the forward kernel
+  uint16_t *dgi_b, *dgh_b;                  // [N, 3d] bf16 (dgh_b is also the A operand of the next step)
+  float* dh0;                               // [bt[0], d]
+  int dh0_accumulate;
+};
+
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(int32_t* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_counter(const int32_t* p, int target) {
+  for (uint32_t spin = 0; ld_acquire(p) < target; ++spin) {
+    if (spin > (1u << 24)) {
+      printf("arkb200: gru_persist tile counter timed out (block %d,%d want %d have %d)\n", blockIdx.x, blockIdx.y,
+             target, ld_acquire(p));
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void ld8_bf16(const uint16_t* p, float* x) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), e = unpack_bf16x2(v.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = e.x; x[7] = e.y;
+}
+__device__ __forceinline__ void st16_bf16(uint16_t* p, const float* x) {
+  uint4 a, b;
+  a.x = pack_bf16x2(x[0], x[1]); a.y = pack_bf16x2(x[2], x[3]); a.z = pack_bf16x2(x[4], x[5]); a.w = pack_bf16x2(x[6], x[7]);
+  b.x = pack_bf16x2(x[8], x[9]); b.y = pack_bf16x2(x[10], x[11]); b.z = pack_bf16x2(x[12], x[13]); b.w = pack_bf16x2(x[14], x[15]);
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + 8) = b;
+}
+__device__ __forceinline__ void ld16_f32(const float* p, float* x) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p + i);
+    x[i] = v.x; x[i + 1] = v.y; x[i + 2] = v.z; x[i + 3] = v.w;
+  }
+}
+
+template <int DJ, int STAGES>
+struct GpSmem {
+  static constexpr int W_BYTES(int d) { return 3 * DJ * d * 2; }
+  static constexpr int total(int d) { return W_BYTES(d) + STAGES * GP_A_BYTES + (2 * STAGES + 2) * 8 + 16 + 1024; }
+};
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <int DJ, int STAGES>
+__global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmW,
+                                                                 const GruPersistFwdParams p) {
+  constexpr int NROWS = 3 * DJ;  // UMMA N
+  constexpr uint32_t TMEM_COLS = NROWS <= 32 ? 32 : (NROWS <= 64 ? 64 : (NROWS <= 128 ? 128 : 256));
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.d, L = p.L;
+  const int nkc = d / GP_BK;
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + 3 * DJ * d * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_sm + STAGES * GP_A_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* w_bar = empty_bar + STAGES;
+  uint64_t* tmem_full_bar = w_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ji = blockIdx.x, bi = blockIdx.y, ns = gridDim.x;
+  const int j0 = ji * DJ, m0 = bi * GP_BM;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // resident weights: nkc chunks of [3*DJ rows x 64 k] (gate-major rows), 128B-swizzled
+      ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(3 * DJ * d * 2));
+      for (int kc = 0; kc < nkc; ++kc)
+        for (int g = 0; g < 3; ++g)
+          ptx::tma_load_2d(w_sm + kc * (NROWS * 128) + g * (DJ * 128), &tmW, w_bar, kc * GP_BK, g * d + j0);
+      int it = 0;
+      for (int t = 0; t < L; ++t) {
+        if (m0 >= p.bt[t]) break;
+        if (t > 0) wait_counter(p.sync + bi, t * ns);   // every slice of h_{t-1} is in global memory
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const int row0 = p.off[t] + m0;
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[s], GP_A_BYTES);
+          ptx::tma_load_2d(a_sm + s * GP_A_BYTES, &tmA, &full_bar[s], kc * GP_BK, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(GP_BM, NROWS, 0, 0);
+      ptx::mbar_wait(w_bar, 0);
+      const uint32_t w_addr = ptx::smem_u32(w_sm), a_addr0 = ptx::smem_u32(a_sm);
+      int it = 0;
+      for (int t = 0; t < L; ++t) {
+        if (m0 >= p.bt[t]) break;
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < GP_BK / 16; ++kk) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES + kk * 32, 16, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128) + kk * 32, 16, 1024);
+            ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+        }
+        ptx::umma_commit(tmem_full_bar);
+      }
+    }
+  } else {
+    // ===================== epilogue: gate math, one thread per batch row =====================
+    const int q = warp & 3;
+    const int b = m0 + q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t d3 = 3 * (int64_t)d;
+    float hreg[DJ];
+    if (b < p.bt[0]) {
+#pragma unroll
+      for (int c = 0; c < DJ; c += 16) ld16_f32(p.h0 + (int64_t)b * d + j0 + c, hreg + c);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DJ; ++i) hreg[i] = 0.f;
+    }
+    for (int t = 0; t < L; ++t) {
+      const int Bt = p.bt[t];
+      if (m0 >= Bt) break;
+      const int Bn = (t + 1 < L) ? p.bt[t + 1] : 0;
+      const bool active = b < Bt;
+      const int64_t row = (int64_t)p.off[t] + b;
+      const int64_t row_n = (t + 1 < L) ? (int64_t)p.off[t + 1] + b : 0;
+      ptx::mbar_wait(tmem_full_bar, t & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < DJ; c += 16) {
+        uint32_t ar[16], az[16], an[16];
+        ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, ar);
+        ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(DJ + c), az);
+        ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(2 * DJ + c), an);
+        ptx::tmem_ld_wait();
+        if (active) {
+          float gr[16], gz[16], gn[16], o_r[16], o_z[16], o_n[16], o_g[16], o_h[16];
+          const float* gp = p.gi + row * d3 + j0 + c;
+          ld16_f32(gp, gr);
+          ld16_f32(gp + d, gz);
+          ld16_f32(gp + 2 * d, gn);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int j = j0 + c + i;
+            const GruFwd o = gru_fwd_math(gr[i], gz[i], gn[i], __uint_as_float(ar[i]) + __ldg(p.b_hh + j),
+                                          __uint_as_float(az[i]) + __ldg(p.b_hh + d + j),
+                                          __uint_as_float(an[i]) + __ldg(p.b_hh + 2 * d + j), hreg[c + i]);
+            hreg[c + i] = o.h;
+            o_r[i] = o.r; o_z[i] = o.z; o_n[i] = o.n; o_g[i] = o.ghn; o_h[i] = o.h;
+          }
+          const int64_t o = row * d + j0 + c;
+          st16_bf16(p.y_b + o, o_h);
+          if (b < Bn) st16_bf16(p.hp_b + row_n * d + j0 + c, o_h);
+          if (p.r) {
+            st16_bf16(p.r + o, o_r);
+            st16_bf16(p.z + o, o_z);
+            st16_bf16(p.n + o, o_n);
+            st16_bf16(p.ghn + o, o_g);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores -> TMA (async proxy) readers
+      epi_bar_sync();
+      if (warp == 2 && lane == 0) red_release_add(p.sync + bi, 1);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =====================================================================================================
+// backward through time
+// =====================================================================================================
+template <int DJ, int STAGES>
+__global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmW,
+                                                                 const GruPersistBwdParams p) {
+  constexpr int NROWS = DJ;  // UMMA N
+  constexpr uint32_t TMEM_COLS = NROWS <= 32 ? 32 : (NROWS <= 64 ? 64 : 128);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.d, L = p.L;
+  const int nkc = 3 * d / GP_BK;
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + 3 * DJ * d * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_sm + STAGES * GP_A_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* w_bar = empty_bar + STAGES;
+  uint64_t* tmem_full_bar = w_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ji = blockIdx.x, bi = blockIdx.y, ns = gridDim.x;
+  const int j0 = ji * DJ, m0 = bi * GP_BM;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // Iterations t = L-1 .. 0 (cell backward of step t) and t = -1 (gradient of the initial state).
+  // Iteration t consumes dgh_{t+1} (if step t+1 had rows in this tile) through the tensor cores.
+  auto tile_active = [&](int t) { return m0 < p.bt[t < 0 ? 0 : t]; };
+  auto has_mma = [&](int t) { return (t + 1 <= L - 1) && (m0 < p.bt[t + 1]); };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(3 * DJ * d * 2));
+      for (int kc = 0; kc < nkc; ++kc)
+        ptx::tma_load_2d(w_sm + kc * (NROWS * 128), &tmW, w_bar, kc * GP_BK, j0);
+      int it = 0, done = 0;  // done = iterations this tile has completed
+      for (int t = L - 1; t >= -1; --t) {
+        if (!tile_active(t)) continue;
+        if (has_mma(t)) {
+          wait_counter(p.sync + bi, done * ns);   // every slice of dgh_{t+1} is in global memory
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const int row0 = p.off[t + 1] + m0;
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % STAGES;
+            ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[s], GP_A_BYTES);
+            ptx::tma_load_2d(a_sm + s * GP_A_BYTES, &tmA, &full_bar[s], kc * GP_BK, row0);
+          }
+        }
+        ++done;
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(GP_BM, NROWS, 0, 0);
+      ptx::mbar_wait(w_bar, 0);
+      const uint32_t w_addr = ptx::smem_u32(w_sm), a_addr0 = ptx::smem_u32(a_sm);
+      int it = 0;
+      for (int t = L - 1; t >= -1; --t) {
+        if (!tile_active(t) || !has_mma(t)) continue;
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < GP_BK / 16; ++kk) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES + kk * 32, 16, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128) + kk * 32, 16, 1024);
+            ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+        }
+        ptx::umma_commit(tmem_full_bar);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int b = m0 + q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t d3 = 3 * (int64_t)d;
+    float carry[DJ];  // dh_{t+1} * z_{t+1}: the direct path into h_t (valid for rows of step t+1)
+#pragma unroll
+    for (int i = 0; i < DJ; ++i) carry[i] = 0.f;
+    int n_mma = 0;
+    for (int t = L - 1; t >= -1; --t) {
+      if (!tile_active(t)) continue;
+      const bool mma = has_mma(t);
+      const int B_next = (t + 1 <= L - 1) ? p.bt[t + 1] : 0;
+      const bool from_next = b < B_next;                 // this row existed at step t+1
+      const bool active = b < p.bt[t < 0 ? 0 : t];
+      if (mma) {
+        ptx::mbar_wait(tmem_full_bar, n_mma & 1);
+        ptx::tc_fence_after();
+        ++n_mma;
+      }
+#pragma unroll 1
+      for (int c = 0; c < DJ; c += 16) {
+        uint32_t acc[16];
+        if (mma) {
+          ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, acc);
+          ptx::tmem_ld_wait();
+        }
+        if (!active) continue;
+        float dh[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dh[i] = from_next ? carry[c + i] + (mma ? __uint_as_float(acc[i]) : 0.f) : 0.f;
+        if (t < 0) {
+          float* o = p.dh0 + (int64_t)b * d + j0 + c;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 v = make_float4(dh[i], dh[i + 1], dh[i + 2], dh[i + 3]);
+            if (p.dh0_accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(o + i);
+              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+            }
+            *reinterpret_cast<float4*>(o + i) = v;
+          }
+          continue;
+        }
+        const int64_t row = (int64_t)p.off[t] + b;
+        const int64_t o = row * d + j0 + c;
+        float dyv[16], r[16], z[16], n[16], g[16], hp[16];
+        ld16_f32(p.dy + o, dyv);
+        ld8_bf16(p.r + o, r); ld8_bf16(p.r + o + 8, r + 8);
+        ld8_bf16(p.z + o, z); ld8_bf16(p.z + o + 8, z + 8);
+        ld8_bf16(p.n + o, n); ld8_bf16(p.n + o + 8, n + 8);
+        ld8_bf16(p.ghn + o, g); ld8_bf16(p.ghn + o + 8, g + 8);
+        ld8_bf16(p.hp_b + o, hp); ld8_bf16(p.hp_b + o + 8, hp + 8);
+        float dar[16], daz[16], dan[16], danr[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const GruBwd w = gru_bwd_math(dh[i] + dyv[i], r[i], z[i], n[i], g[i], hp[i]);
+          dar[i] = w.dar; daz[i] = w.daz; dan[i] = w.dan; danr[i] = w.dan_r;
+          carry[c + i] = w.dh_prev;
+        }
+        const int64_t o3 = row * d3 + j0 + c;
+        st16_bf16(p.dgi_b + o3, dar);
+        st16_bf16(p.dgi_b + o3 + d, daz);
+        st16_bf16(p.dgi_b + o3 + 2 * d, dan);
+        st16_bf16(p.dgh_b + o3, dar);
+        st16_bf16(p.dgh_b + o3 + d, daz);
+        st16_bf16(p.dgh_b + o3 + 2 * d, danr);
+      }
+      ptx::tc_fence_before();
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores -> TMA (async proxy) readers
+      epi_bar_sync();
+      if (warp == 2 && lane == 0) red_release_add(p.sync + bi, 1);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// [R, C] bf16 -> [C, R] bf16 (W_hh^T for the backward kernel; 32x32 tiles through padded smem)
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const uint16_t* __restrict__ in, int R, int C,
+                                                             uint16_t* __restrict__ out) {
+  __shared__ uint16_t tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < R && c0 + tx < C) tile[i][tx] = in[(int64_t)(r0 + i) * C + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < C && r0 + tx < R) out[(int64_t)(c0 + i) * R + r0 + tx] = tile[tx][i];
+}
+
+// ---------------------------------------------------------------------------------------------- host
+static int pick_dj(int64_t d, int64_t bt0, int* stages_out) {
+  if (d % 64 != 0 || d < 64 || bt0 <= 0) return 0;
+  const int64_t nbt = (bt0 + GP_BM - 1) / GP_BM;
+  const int cand[3] = {16, 32, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int dj = cand[i];
+    if (d % dj) continue;
+    if (nbt * (d / dj) > kNumSMs) continue;
+    for (int st = 4; st >= 2; --st) {
+      const int64_t smem = 3LL * dj * d * 2 + (int64_t)st * GP_A_BYTES + 2048;
+      if (smem <= 227 * 1024) {
+        *stages_out = st;
+        return dj;
+      }
+    }
+  }
+  return 0;
+}
+
+template <typename Params, typename Kern>
+static int launch_coop(Kern kern, const CUtensorMap& tmA, const CUtensorMap& tmW, const Params& prm, dim3 grid,
+                       int smem, cudaStream_t s, const char* who) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return fail((int)e, "%s: smem attribute (%d B): %s", who, smem, cudaGetErrorString(e));
+  void* args[] = {(void*)&tmA, (void*)&tmW, (void*)&prm};
+  e = cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(192), args, (size_t)smem, s);
+  if (e != cudaSuccess) return fail((int)e, "%s: cooperative launch grid=(%u,%u): %s", who, grid.x, grid.y, cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+}  // namespace ark
+
+using namespace ark;
+
+extern "C" int ark_gru_persist_supported(int64_t d, int64_t bt0) {
+  int st;
+  return pick_dj(d, bt0, &st);
+}
+
+extern "C" int ark_transpose_bf16(const uint16_t* in, int64_t R, int64_t C, uint16_t* out, void* stream) {
+  ARK_REQUIRE(in && out && R > 0 && C > 0, ARK_E_BADARG, "transpose_bf16: bad arguments");
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32));
+  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (int)R, (int)C, out);
+  return launched("transpose_bf16");
+}
+
+extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16_t* Whh_b, const float* gi,
+                                   const float* b_hh, const int32_t* bt_dev, const int32_t* off_dev, int64_t L,
+                                   int64_t bt0, int64_t N, int64_t d, uint16_t* y_b, uint16_t* r, uint16_t* z,
+                                   uint16_t* n, uint16_t* ghn, int32_t* sync_ws, void* stream) {
+  ARK_REQUIRE(hp_b && h0 && Whh_b && gi && b_hh && bt_dev && off_dev && y_b && sync_ws, ARK_E_BADARG,
+              "gru_persist_fwd: null pointer");
+  ARK_REQUIRE((r && z && n && ghn) || (!r && !z && !n && !ghn), ARK_E_BADARG,
+              "gru_persist_fwd: gate outputs must be all set or all NULL");
+  ARK_REQUIRE(L > 0 && N > 0 && bt0 > 0, ARK_E_BADARG, "gru_persist_fwd: bad sizes");
+  int stages = 0;
+  const int dj = pick_dj(d, bt0, &stages);
+  ARK_REQUIRE(dj > 0, ARK_E_SHAPE, "gru_persist_fwd: unsupported shape d=%lld bt0=%lld (need d %% 64 == 0 and the "
+              "grid to fit 148 SMs)", (long long)d, (long long)bt0);
+  ARK_REQUIRE(aligned16(hp_b) && aligned16(Whh_b) && aligned16(gi) && aligned16(h0) && aligned16(y_b), ARK_E_ALIGN,
+              "gru_persist_fwd: 16-byte alignment");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nbt = (int)((bt0 + GP_BM - 1) / GP_BM);
+  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * nbt, s);
+  if (e != cudaSuccess) return fail((int)e, "gru_persist_fwd: memset: %s", cudaGetErrorString(e));
+  CUtensorMap tmA, tmW;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, hp_b, (uint64_t)d, (uint64_t)N, (uint64_t)d, GP_BK, GP_BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmW, Whh_b, (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, GP_BK, dj))) return rc;
+  GruPersistFwdParams prm;
+  prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.gi = gi; prm.b_hh = b_hh;
+  prm.h0 = h0; prm.hp_b = hp_b; prm.y_b = y_b; prm.r = r; prm.z = z; prm.n = n; prm.ghn = ghn;
+  dim3 grid((unsigned)(d / dj), (unsigned)nbt);
+  const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 2048);
+#define ARK_GP_FWD(DJ, ST) \
+  if (dj == DJ && stages == ST) return launch_coop(gru_persist_fwd_kernel<DJ, ST>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd")
+  ARK_GP_FWD(16, 4); ARK_GP_FWD(16, 3); ARK_GP_FWD(16, 2);
+  ARK_GP_FWD(32, 4); ARK_GP_FWD(32, 3); ARK_GP_FWD(32, 2);
+  ARK_GP_FWD(64, 4); ARK_GP_FWD(64, 3); ARK_GP_FWD(64, 2);
+#undef ARK_GP_FWD
+  return fail(ARK_E_SHAPE, "gru_persist_fwd: no kernel instance for dj=%d stages=%d", dj, stages);
+}
+
+extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uint16_t* z, const uint16_t* n,
+                                   const uint16_t* ghn, const uint16_t* hp_b, const uint16_t* WhhT_b,
+                                   const int32_t* bt_dev, const int32_t* off_dev, int64_t L, int64_t bt0, int64_t N,
+                                   int64_t d, uint16_t* dgi_b, uint16_t* dgh_b, float* dh0, int dh0_accumulate,
+                                   int32_t* sync_ws, void* stream) {
+  ARK_REQUIRE(dy && r && z && n && ghn && hp_b && WhhT_b && bt_dev && off_dev && dgi_b && dgh_b && dh0 && sync_ws,
+              ARK_E_BADARG, "gru_persist_bwd: null pointer");
+  ARK_REQUIRE(L > 0 && N > 0 && bt0 > 0, ARK_E_BADARG, "gru_persist_bwd: bad sizes");
+  int stages = 0;
+  const int dj = pick_dj(d, bt0, &stages);
+  ARK_REQUIRE(dj > 0, ARK_E_SHAPE, "gru_persist_bwd: unsupported shape d=%lld bt0=%lld", (long long)d, (long long)bt0);
+  ARK_REQUIRE(aligned16(dy) && aligned16(WhhT_b) && aligned16(dgi_b) && aligned16(dgh_b) && aligned16(dh0), ARK_E_ALIGN,
+              "gru_persist_bwd: 16-byte alignment");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nbt = (int)((bt0 + GP_BM - 1) / GP_BM);
+  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * nbt, s);
+  if (e != cudaSuccess) return fail((int)e, "gru_persist_bwd: memset: %s", cudaGetErrorString(e));
+  CUtensorMap tmA, tmW;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, dgh_b, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d), GP_BK, GP_BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmW, WhhT_b, (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), GP_BK, dj))) return rc;
+  GruPersistBwdParams prm;
+  prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.dy = dy; prm.r = r;
+  prm.z = z; prm.n = n; prm.ghn = ghn; prm.hp_b = hp_b; prm.dgi_b = dgi_b; prm.dgh_b = dgh_b; prm.dh0 = dh0;
+  prm.dh0_accumulate = dh0_accumulate;
+  dim3 grid((unsigned)(d / dj), (unsigned)nbt);
+  const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 2048);
+#define ARK_GP_BWD(DJ, ST) \
+  if (dj == DJ && stages == ST) return launch_coop(gru_persist_bwd_kernel<DJ, ST>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd")
+  ARK_GP_BWD(16, 4); ARK_GP_BWD(16, 3); ARK_GP_BWD(16, 2);
+  ARK_GP_BWD(32, 4); ARK_GP_BWD(32, 3); ARK_GP_BWD(32, 2);
+  ARK_GP_BWD(64, 4); ARK_GP_BWD(64, 3); ARK_GP_BWD(64, 2);
+#undef ARK_GP_BWD
+  return fail(ARK_E_SHAPE, "gru_persist_bwd: no kernel instance for dj=%d stages=%d", dj, stages);
+}

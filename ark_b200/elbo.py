@@ -68,6 +68,7 @@ class SailEngine:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._pending = []
         self.prof = None
+        self.force_unfused_gru = False   # tests: compare the persistent GRU kernel with the per-step path
         self.stats = torch.zeros(4, device=dev)  # [ce, kl, steps, unused] accumulated on device
         self.refresh_shadow()
         if hasattr(model, "_attach_engine"):
@@ -165,27 +166,39 @@ class SailEngine:
         b0 = int(lay.bt[0])
         saved = []
         u_b = x_b
-        gh_ws = new(b0, d3)
+        persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru
+        gh_ws = None if persist else new(b0, d3)
+        sync_ws = new((b0 + 127) // 128, dtype=torch.int32) if persist else None
         for k in range(nl):
             gi = new(N, d3)
             self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, tag="gru_gi",
                        bias=f.p(f"dec.gru.bias_ih_l{k}"))
-            hp_f, hp_b = new(N, d), new(N, d, dtype=bf)
-            hp_f[:b0].copy_(h0[:b0])
-            ops.cast_bf16(hp_f[:b0], hp_b[:b0])
-            y, y_b = new(N, d), new(N, d, dtype=bf)
-            gates = tuple(new(N, d) for _ in range(4))
-            with self._timed("gru_layer_fwd", flops=2.0 * N * d * d3):
-                ops.gru_layer_fwd(hp_b, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
-                                  lay.bt, lay.off, L, d, y, y_b, gates, gh_ws, use_tc)
+            hp_b, y_b = new(N, d, dtype=bf), new(N, d, dtype=bf)
+            if persist:
+                # one cooperative launch for all L steps: W_hh slice resident in smem, state in registers
+                ops.cast_bf16(h0[:b0], hp_b[:b0])
+                gates = tuple(new(N, d, dtype=bf) for _ in range(4))
+                with self._timed("gru_persist_fwd", flops=2.0 * N * d * d3):
+                    ops.gru_persist_fwd(hp_b, h0, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
+                                        lay.bt_dev, lay.off_dev, L, b0, d, y_b, gates, sync_ws)
+                hp_f = None
+            else:
+                hp_f = new(N, d)
+                hp_f[:b0].copy_(h0[:b0])
+                ops.cast_bf16(hp_f[:b0], hp_b[:b0])
+                y = new(N, d)
+                gates = tuple(new(N, d) for _ in range(4))
+                with self._timed("gru_layer_fwd", flops=2.0 * N * d * d3):
+                    ops.gru_layer_fwd(hp_b, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
+                                      lay.bt, lay.off, L, d, y, y_b, gates, gh_ws, use_tc)
             mask = None
             if train and self.p_drop > 0 and k < nl - 1:
                 mask = new(N, d, dtype=torch.uint8)
-                ops.dropout_fwd(y, self.p_drop, self.seed, self.philox_offset, None, y_b, mask)
+                ops.dropout_bf16(y_b, self.p_drop, self.seed, self.philox_offset, y_b, mask)
                 self.philox_offset += (N * d + 3) // 4
             saved.append((u_b, hp_f, hp_b, gates, mask))
             u_b = y_b
-            del gi, y
+            del gi
         logits = new(N, ldv, dtype=bf)
         w_out = self._w("dec.tok_emb.weight") if self.tied else self._w("dec.out.weight")
         self._gemm(u_b, K, w_out, K, logits, N, V, d, tag="vocab_fwd", bias=f.p("dec.out.bias"))
@@ -203,20 +216,29 @@ class SailEngine:
         self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")                         # dY = dLogits . W
         del logits
         self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
-        dh0 = None
+        dh0 = new(b0, d)
         dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
-        dh_a, dh_b = new(b0, d), new(b0, d)
+        if persist:
+            whh_t = new(d, d3, dtype=bf)
+        else:
+            dh_a, dh_b = new(b0, d), new(b0, d)
         for k in range(nl - 1, -1, -1):
             u_in, hp_f, hp_b, gates, mask = saved[k]
             if mask is not None:
                 ops.dropout_bwd(dy, mask, self.p_drop, dy)
-            with self._timed("gru_layer_bwd", flops=2.0 * N * d * d3):
-                dh_k = ops.gru_layer_bwd(dy, gates, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), lay.bt, lay.off, L, d,
-                                         dgi, dgh, dh_a, dh_b, use_tc)
-            if dh0 is None:
-                dh0 = dh_k.clone()
+            if persist:
+                ops.transpose_bf16(self._w(f"dec.gru.weight_hh_l{k}"), whh_t)
+                with self._timed("gru_persist_bwd", flops=2.0 * N * d * d3):
+                    ops.gru_persist_bwd(dy, gates, hp_b, whh_t, lay.bt_dev, lay.off_dev, L, b0, d, dgi, dgh, dh0,
+                                        k != nl - 1, sync_ws)
             else:
-                ops.add_(dh0, dh_k, dh0, None)
+                with self._timed("gru_layer_bwd", flops=2.0 * N * d * d3):
+                    dh_k = ops.gru_layer_bwd(dy, gates, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), lay.bt, lay.off, L, d,
+                                             dgi, dgh, dh_a, dh_b, use_tc)
+                if k == nl - 1:
+                    dh0.copy_(dh_k)
+                else:
+                    ops.add_(dh0, dh_k, dh0, None)
             self._gemm(dgi, MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
             self._gemm(dgh, MN, hp_b, MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
             ops.colsum(dgi, N, d3, f.g(f"dec.gru.bias_ih_l{k}"))

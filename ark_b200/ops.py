@@ -209,3 +209,38 @@ def adam_flat(p, g, m, v, shadow, lr, beta1, beta2, eps, step, grad_scale=1.0):
     _C.lib().call("ark_adam_flat", _ptr(p, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32),
                   _ptr(v, torch.float32), _ptr(shadow, torch.bfloat16), p.numel(), float(lr), float(beta1),
                   float(beta2), float(eps), int(step), float(grad_scale), _stream())
+
+
+def gru_persist_supported(d, bt0) -> int:
+    return int(_C.lib().raw("ark_gru_persist_supported")(int(d), int(bt0)))
+
+
+def transpose_bf16(x, out):
+    R, C = x.shape
+    _contig(x, out)
+    _C.lib().call("ark_transpose_bf16", _ptr(x, torch.bfloat16), R, C, _ptr(out, torch.bfloat16), _stream())
+
+
+def gru_persist_fwd(hp_b, h0, Whh_b, gi, b_hh, bt_dev, off_dev, L, bt0, d, y_b, gates, sync_ws):
+    r, z, n, ghn = gates if gates is not None else (None, None, None, None)
+    _contig(hp_b, h0, Whh_b, gi, y_b)
+    _C.lib().call("ark_gru_persist_fwd", _ptr(hp_b, torch.bfloat16), _ptr(h0, torch.float32), _ptr(Whh_b, torch.bfloat16),
+                  _ptr(gi, torch.float32), _ptr(b_hh, torch.float32), _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32),
+                  L, bt0, hp_b.shape[0], d, _ptr(y_b, torch.bfloat16), _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16),
+                  _ptr(n, torch.bfloat16), _ptr(ghn, torch.bfloat16), _ptr(sync_ws, torch.int32), _stream())
+
+
+def gru_persist_bwd(dy, gates, hp_b, WhhT_b, bt_dev, off_dev, L, bt0, d, dgi_b, dgh_b, dh0, accumulate, sync_ws):
+    r, z, n, ghn = gates
+    _contig(dy, hp_b, WhhT_b, dgi_b, dgh_b, dh0)
+    _C.lib().call("ark_gru_persist_bwd", _ptr(dy, torch.float32), _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16),
+                  _ptr(n, torch.bfloat16), _ptr(ghn, torch.bfloat16), _ptr(hp_b, torch.bfloat16),
+                  _ptr(WhhT_b, torch.bfloat16), _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32), L, bt0,
+                  hp_b.shape[0], d, _ptr(dgi_b, torch.bfloat16), _ptr(dgh_b, torch.bfloat16), _ptr(dh0, torch.float32),
+                  int(accumulate), _ptr(sync_ws, torch.int32), _stream())
+
+
+def dropout_bf16(x, p, seed, offset, y, mask=None):
+    _contig(x, y, mask)
+    _C.lib().call("ark_dropout_bf16", _ptr(x, torch.bfloat16), x.numel(), float(p), int(seed), int(offset),
+                  _ptr(y, torch.bfloat16), _ptr(mask, torch.uint8), _stream())

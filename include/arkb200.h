@@ -153,6 +153,27 @@ int ark_gru_layer_bwd(const float* dy, const float* r, const float* z, const flo
                       const int32_t* off_host, int64_t L, int64_t d, void* dgi, void* dgh,
                       float* dh_a, float* dh_b, float** dh0_out, int use_tc, void* stream);
 
+/* Persistent GRU layer (cooperative launch, W_hh slice resident in shared memory for all L steps, tcgen05
+ * MMA + gate math fused, recurrent state in registers; see ark_b200/csrc/gru_persist.cu).  bt_dev / off_dev
+ * are DEVICE int32 arrays [L].  Saved tensors are bf16.  ark_gru_persist_supported returns the hidden-slice
+ * width the launcher would use (16/32/64) or 0 when the shape is not supported (d % 64 != 0, or the
+ * (d/slice) x ceil(bt0/128) grid does not fit the 148 SMs): callers then use ark_gru_layer_fwd/bwd. */
+int ark_gru_persist_supported(int64_t d, int64_t bt0);
+/* hp_b [N,d]: block 0 pre-filled with bf16(h0); blocks 1.. are written here.  h0 f32 [bt0,d].
+ * gi f32 [N,3d]; outputs y_b and (optional, all or none) r,z,n,ghn bf16 [N,d]; sync_ws int32 [ceil(bt0/128)]. */
+int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16_t* Whh_b, const float* gi, const float* b_hh,
+                        const int32_t* bt_dev, const int32_t* off_dev, int64_t L, int64_t bt0, int64_t N, int64_t d,
+                        uint16_t* y_b, uint16_t* r, uint16_t* z, uint16_t* n, uint16_t* ghn,
+                        int32_t* sync_ws, void* stream);
+/* WhhT_b = W_hh^T bf16 [d,3d] (ark_transpose_bf16).  dy f32 [N,d].  Writes dgi_b/dgh_b bf16 [N,3d] and
+ * dh0 f32 [bt0,d] (+= when dh0_accumulate != 0). */
+int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uint16_t* z, const uint16_t* n, const uint16_t* ghn,
+                        const uint16_t* hp_b, const uint16_t* WhhT_b, const int32_t* bt_dev, const int32_t* off_dev,
+                        int64_t L, int64_t bt0, int64_t N, int64_t d, uint16_t* dgi_b, uint16_t* dgh_b,
+                        float* dh0, int dh0_accumulate, int32_t* sync_ws, void* stream);
+/* out[C,R] = in[R,C]^T (bf16) */
+int ark_transpose_bf16(const uint16_t* in, int64_t R, int64_t C, uint16_t* out, void* stream);
+
 /* ---- elementwise helpers ----
  * dpre = dact * gelu'(pre) (erf form, models.py:37) -> f32 and/or bf16 */
 int ark_gelu_bwd(const float* dact, const float* pre, int64_t n, float* dpre, uint16_t* dpre_bf16, void* stream);
@@ -167,6 +188,9 @@ int ark_cast_f32_to_bf16(const float* x, int64_t n, uint16_t* y, void* stream);
  * by (seed, offset+element); mask uint8 [n] saved for backward. */
 int ark_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset,
                     float* y, uint16_t* y_bf16, uint8_t* mask, void* stream);
+/* same Philox stream on a bf16 tensor (the GRU layer outputs of the training path); y may alias x */
+int ark_dropout_bf16(const uint16_t* x, int64_t n, float p, uint64_t seed, uint64_t offset,
+                     uint16_t* y, uint8_t* mask, void* stream);
 int ark_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, void* stream);
 
 /* ---- K10: dense Adam over a flat parameter buffer (torch.optim.Adam defaults, ablation_study.py:571) ----

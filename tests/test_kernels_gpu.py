@@ -336,3 +336,71 @@ def test_gru_layer_fwd_bwd_matches_torch(use_tc):
     assert _rel(dx, x.grad[bi, ti]) < 2e-2
     assert _rel(dgi.float().t() @ xp, gru.weight_ih_l0.grad) < 2e-2
     assert _rel(dgh.float().t() @ hp_f, gru.weight_hh_l0.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------------- persistent GRU (cooperative)
+@pytest.mark.parametrize("d,lens", [
+    (64, [9, 9, 7, 7, 7, 4, 4, 2, 1, 1]),                      # 4 slices, one ragged batch tile
+    (128, [5] * 130),                                           # two batch tiles (130 rows), dense
+    (256, list(range(40, 0, -1)) * 4),                          # 160 graphs, very ragged, tile 1 retires early
+    (512, [30, 22, 22, 9, 3, 3, 3, 1]),                         # wd-articles-like small batch
+    (1024, [10] * 256),                                         # syn-types shape: 64 slices x 2 tiles = 128 CTAs
+])
+def test_gru_persist_fwd_bwd_matches_torch(d, lens):
+    torch.manual_seed(d)
+    lens = np.array(sorted(lens, reverse=True), dtype=np.int32)
+    B, L = len(lens), int(lens.max())
+    assert ops.gru_persist_supported(d, B) > 0
+    bt = np.array([(lens > t).sum() for t in range(L)], dtype=np.int32)
+    off = np.zeros(L + 1, dtype=np.int32)
+    off[1:] = np.cumsum(bt)
+    N = int(off[-1])
+    gru = torch.nn.GRU(d, d, 1, batch_first=True).to(DEV)
+    with torch.no_grad():
+        for prm in gru.parameters():
+            prm.copy_(prm.to(torch.bfloat16).float())
+    Wih, Whh = gru.weight_ih_l0.detach(), gru.weight_hh_l0.detach()
+    x = torch.randn(B, L, d, device=DEV).to(torch.bfloat16).float().requires_grad_()
+    h0 = torch.tanh(torch.randn(B, d, device=DEV)).to(torch.bfloat16).float().requires_grad_()
+    y_ref, _ = gru(x, h0[None])
+    dy_dense = torch.randn(B, L, d, device=DEV)
+    mask = torch.from_numpy(lens).to(DEV)[:, None] > torch.arange(L, device=DEV)[None]
+    (y_ref * dy_dense * mask[..., None]).sum().backward()
+
+    bi = torch.cat([torch.arange(int(bt[t])) for t in range(L)]).to(DEV)
+    ti = torch.cat([torch.full((int(bt[t]),), t) for t in range(L)]).to(DEV)
+    xp = x.detach()[bi, ti]
+    gi = (xp @ Wih.t() + gru.bias_ih_l0.detach()).contiguous()
+    bf = torch.bfloat16
+    hp_b = torch.zeros(N, d, device=DEV, dtype=bf)
+    hp_b[:B] = h0.detach().to(bf)
+    y_b = torch.empty(N, d, device=DEV, dtype=bf)
+    gates = tuple(torch.empty(N, d, device=DEV, dtype=bf) for _ in range(4))
+    sync = torch.empty((B + 127) // 128, device=DEV, dtype=torch.int32)
+    bt_d, off_d = torch.from_numpy(bt).to(DEV), torch.from_numpy(off[:-1].copy()).to(DEV)
+    Wb = Whh.to(bf).contiguous()
+    ops.gru_persist_fwd(hp_b, h0.detach().contiguous(), Wb, gi, gru.bias_hh_l0.detach(), bt_d, off_d, L, B, d, y_b,
+                        gates, sync)
+    torch.cuda.synchronize()
+    assert _rel(y_b, y_ref.detach()[bi, ti]) < 1e-2
+    # the packed h_prev rows of step t+1 are the outputs of step t (prefix of the sorted batch)
+    for t in range(L - 1):
+        n = int(bt[t + 1])
+        assert torch.equal(hp_b[off[t + 1]:off[t + 1] + n], y_b[off[t]:off[t] + n])
+    WT = torch.empty(d, 3 * d, device=DEV, dtype=bf)
+    ops.transpose_bf16(Wb, WT)
+    assert torch.equal(WT, Wb.t().contiguous())
+    dy = dy_dense[bi, ti].contiguous()
+    dgi = torch.empty(N, 3 * d, device=DEV, dtype=bf)
+    dgh = torch.empty(N, 3 * d, device=DEV, dtype=bf)
+    dh0 = torch.full((B, d), 7.0, device=DEV)
+    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0, False, sync)
+    torch.cuda.synchronize()
+    assert _rel(dh0, h0.grad) < 3e-2
+    assert _rel(dgi.float() @ Wih, x.grad[bi, ti]) < 3e-2
+    assert _rel(dgi.float().t() @ xp, gru.weight_ih_l0.grad) < 3e-2
+    assert _rel(dgh.float().t() @ hp_b.float(), gru.weight_hh_l0.grad) < 3e-2
+    # accumulate mode adds to what is there
+    dh0b = dh0.clone()
+    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0b, True, sync)
+    torch.testing.assert_close(dh0b, 2 * dh0, rtol=1e-5, atol=1e-6)
