@@ -92,6 +92,34 @@ __device__ __forceinline__ void ld16_f32(const float* p, float* x) {
   }
 }
 
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// same expression tree as gru_fwd_math with MUFU tanh / sigmoid(x) = 0.5 + 0.5 tanh(x/2)
+__device__ __forceinline__ GruFwd gru_fwd_math_fast(float gi_r, float gi_z, float gi_n, float gh_r, float gh_z,
+                                                    float gh_n, float h_prev) {
+  GruFwd o;
+  o.r = fmaf(0.5f, tanh_fast(0.5f * (gi_r + gh_r)), 0.5f);
+  o.z = fmaf(0.5f, tanh_fast(0.5f * (gi_z + gh_z)), 0.5f);
+  o.ghn = gh_n;
+  o.n = tanh_fast(fmaf(o.r, gh_n, gi_n));
+  o.h = fmaf(o.z, h_prev - o.n, o.n);
+  return o;
+}
+__device__ __forceinline__ void st4_bf16(uint16_t* p, const float* x) {
+  uint2 v;
+  v.x = pack_bf16x2(x[0], x[1]);
+  v.y = pack_bf16x2(x[2], x[3]);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+__device__ __forceinline__ void ld4_bf16(const uint16_t* p, float* x) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
+
 template <int DJ, int STAGES>
 struct GpSmem {
   static constexpr int W_BYTES(int d) { return 3 * DJ * d * 2; }
@@ -113,7 +141,10 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
   const int nkc = d / GP_BK;
   uint8_t* w_sm = smem;
   uint8_t* a_sm = smem + 3 * DJ * d * 2;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_sm + STAGES * GP_A_BYTES);
+  float* acc_sm = reinterpret_cast<float*>(a_sm + STAGES * GP_A_BYTES);   // [128][ACC_LD] TMEM -> smem staging
+  constexpr int ACC_LD = NROWS + 1;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc_sm + GP_BM * ACC_LD + 1);
+  full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~(uintptr_t)7);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* w_bar = empty_bar + STAGES;
   uint64_t* tmem_full_bar = w_bar + 1;
@@ -188,66 +219,99 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
       }
     }
   } else {
-    // ===================== epilogue: gate math, one thread per batch row =====================
+    // ===================== epilogue =====================
+    // (1) each warp drains its 32 TMEM lanes (batch rows) into smem; (2) the 128 threads then share the
+    // (row, 4-unit group) work items evenly — with 16 live rows that is 64 busy threads instead of 16 —
+    // with 16-byte gi loads and 8-byte bf16 stores.  Work item e = tid + 128*i is FIXED over time, so the
+    // recurrent state of its 4 units stays in registers.  gi for step t is fetched BEFORE waiting for the
+    // MMA of step t (it does not depend on h).
+    constexpr int G = DJ / 4;                    // groups per row
     const int q = warp & 3;
-    const int b = m0 + q * 32 + lane;
+    const int tid = threadIdx.x - 64;            // 0..127
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int64_t d3 = 3 * (int64_t)d;
-    float hreg[DJ];
-    if (b < p.bt[0]) {
+    float hreg[G][4];
+    const int bt0 = p.bt[0];
 #pragma unroll
-      for (int c = 0; c < DJ; c += 16) ld16_f32(p.h0 + (int64_t)b * d + j0 + c, hreg + c);
-    } else {
-#pragma unroll
-      for (int i = 0; i < DJ; ++i) hreg[i] = 0.f;
+    for (int i = 0; i < G; ++i) {
+      const int e = tid + 128 * i, bl = e / G, j = j0 + (e % G) * 4;
+      const int b = m0 + bl;
+      const float4 hv = (b < bt0) ? *reinterpret_cast<const float4*>(p.h0 + (int64_t)b * d + j) : make_float4(0, 0, 0, 0);
+      hreg[i][0] = hv.x; hreg[i][1] = hv.y; hreg[i][2] = hv.z; hreg[i][3] = hv.w;
     }
+    float4 gpre[G][3];
+    auto prefetch_gi = [&](int t) {
+      const int Bt = p.bt[t];
+      const int64_t base = (int64_t)p.off[t] + m0;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int e = tid + 128 * i, bl = e / G, j = j0 + (e % G) * 4;
+        if (m0 + bl < Bt) {
+          const float* gp = p.gi + (base + bl) * d3 + j;
+          gpre[i][0] = *reinterpret_cast<const float4*>(gp);
+          gpre[i][1] = *reinterpret_cast<const float4*>(gp + d);
+          gpre[i][2] = *reinterpret_cast<const float4*>(gp + 2 * d);
+        }
+      }
+    };
+    if (m0 < bt0) prefetch_gi(0);
     for (int t = 0; t < L; ++t) {
       const int Bt = p.bt[t];
       if (m0 >= Bt) break;
       const int Bn = (t + 1 < L) ? p.bt[t + 1] : 0;
-      const bool active = b < Bt;
-      const int64_t row = (int64_t)p.off[t] + b;
-      const int64_t row_n = (t + 1 < L) ? (int64_t)p.off[t + 1] + b : 0;
+      const int64_t base = (int64_t)p.off[t] + m0;
+      const int64_t base_n = (t + 1 < L) ? (int64_t)p.off[t + 1] + m0 : 0;
       ptx::mbar_wait(tmem_full_bar, t & 1);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < DJ; c += 16) {
-        uint32_t ar[16], az[16], an[16];
-        ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, ar);
-        ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(DJ + c), az);
-        ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(2 * DJ + c), an);
-        ptx::tmem_ld_wait();
-        if (active) {
-          float gr[16], gz[16], gn[16], o_r[16], o_z[16], o_n[16], o_g[16], o_h[16];
-          const float* gp = p.gi + row * d3 + j0 + c;
-          ld16_f32(gp, gr);
-          ld16_f32(gp + d, gz);
-          ld16_f32(gp + 2 * d, gn);
+      if (m0 + q * 32 < Bt) {                     // warp-uniform: skip lane quadrants without live rows
+        float* dst = acc_sm + (q * 32 + lane) * ACC_LD;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int j = j0 + c + i;
-            const GruFwd o = gru_fwd_math(gr[i], gz[i], gn[i], __uint_as_float(ar[i]) + __ldg(p.b_hh + j),
-                                          __uint_as_float(az[i]) + __ldg(p.b_hh + d + j),
-                                          __uint_as_float(an[i]) + __ldg(p.b_hh + 2 * d + j), hreg[c + i]);
-            hreg[c + i] = o.h;
-            o_r[i] = o.r; o_z[i] = o.z; o_n[i] = o.n; o_g[i] = o.ghn; o_h[i] = o.h;
-          }
-          const int64_t o = row * d + j0 + c;
-          st16_bf16(p.y_b + o, o_h);
-          if (b < Bn) st16_bf16(p.hp_b + row_n * d + j0 + c, o_h);
-          if (p.r) {
-            st16_bf16(p.r + o, o_r);
-            st16_bf16(p.z + o, o_z);
-            st16_bf16(p.n + o, o_n);
-            st16_bf16(p.ghn + o, o_g);
-          }
+        for (int c = 0; c < NROWS; c += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) dst[c + k] = __uint_as_float(v[k]);
         }
       }
       ptx::tc_fence_before();
-      __threadfence();
-      asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores -> TMA (async proxy) readers
       epi_bar_sync();
-      if (warp == 2 && lane == 0) red_release_add(p.sync + bi, 1);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int e = tid + 128 * i, bl = e / G, jl = (e % G) * 4;
+        const int b = m0 + bl;
+        if (b < Bt) {
+          const float* ap = acc_sm + bl * ACC_LD + jl;
+          const float gr[4] = {gpre[i][0].x, gpre[i][0].y, gpre[i][0].z, gpre[i][0].w};
+          const float gz[4] = {gpre[i][1].x, gpre[i][1].y, gpre[i][1].z, gpre[i][1].w};
+          const float gn[4] = {gpre[i][2].x, gpre[i][2].y, gpre[i][2].z, gpre[i][2].w};
+          const float4 b_r = __ldg(reinterpret_cast<const float4*>(p.b_hh + j0 + jl));
+          const float4 b_z = __ldg(reinterpret_cast<const float4*>(p.b_hh + d + j0 + jl));
+          const float4 b_n = __ldg(reinterpret_cast<const float4*>(p.b_hh + 2 * d + j0 + jl));
+          const float br[4] = {b_r.x, b_r.y, b_r.z, b_r.w}, bz[4] = {b_z.x, b_z.y, b_z.z, b_z.w};
+          const float bn[4] = {b_n.x, b_n.y, b_n.z, b_n.w};
+          float o_r[4], o_z[4], o_n[4], o_g[4], o_h[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const GruFwd o = gru_fwd_math_fast(gr[k], gz[k], gn[k], ap[k] + br[k], ap[DJ + k] + bz[k],
+                                               ap[2 * DJ + k] + bn[k], hreg[i][k]);
+            hreg[i][k] = o.h;
+            o_r[k] = o.r; o_z[k] = o.z; o_n[k] = o.n; o_g[k] = o.ghn; o_h[k] = o.h;
+          }
+          const int64_t o = (base + bl) * d + j0 + jl;
+          st4_bf16(p.y_b + o, o_h);
+          if (b < Bn) st4_bf16(p.hp_b + (base_n + bl) * d + j0 + jl, o_h);
+          if (p.r) {
+            st4_bf16(p.r + o, o_r);
+            st4_bf16(p.z + o, o_z);
+            st4_bf16(p.n + o, o_n);
+            st4_bf16(p.ghn + o, o_g);
+          }
+        }
+      }
+      epi_bar_sync();                             // all stores of the tile issued (and acc_sm free again)
+      if (tid == 0) red_release_add(p.sync + bi, 1);   // release: cumulative over the barrier above
+      if (t + 1 < L && m0 < Bn) prefetch_gi(t + 1);
     }
   }
   ptx::tc_fence_before();
@@ -270,7 +334,10 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
   const int nkc = 3 * d / GP_BK;
   uint8_t* w_sm = smem;
   uint8_t* a_sm = smem + 3 * DJ * d * 2;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_sm + STAGES * GP_A_BYTES);
+  float* acc_sm = reinterpret_cast<float*>(a_sm + STAGES * GP_A_BYTES);   // [128][ACC_LD]
+  constexpr int ACC_LD = NROWS + 1;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc_sm + GP_BM * ACC_LD + 1);
+  full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~(uintptr_t)7);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* w_bar = empty_bar + STAGES;
   uint64_t* tmem_full_bar = w_bar + 1;
@@ -351,78 +418,112 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
       }
     }
   } else {
+    // same two-phase epilogue as the forward kernel: TMEM -> smem, then (row, 4-unit group) work items
+    // spread over the 128 threads; dy and the saved gates of step t are fetched BEFORE the MMA wait.
+    constexpr int G = DJ / 4;
     const int q = warp & 3;
-    const int b = m0 + q * 32 + lane;
+    const int tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int64_t d3 = 3 * (int64_t)d;
-    float carry[DJ];  // dh_{t+1} * z_{t+1}: the direct path into h_t (valid for rows of step t+1)
+    float carry[G][4];   // dh_{t+1} * z_{t+1}: the direct path into h_t (valid for rows of step t+1)
 #pragma unroll
-    for (int i = 0; i < DJ; ++i) carry[i] = 0.f;
+    for (int i = 0; i < G; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) carry[i][k] = 0.f;
+    float4 dyp[G];
+    uint2 sp[G][5];
+    auto prefetch = [&](int t) {
+      const int Bt = p.bt[t];
+      const int64_t base = (int64_t)p.off[t] + m0;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int e = tid + 128 * i, bl = e / G, jl = (e % G) * 4;
+        if (m0 + bl < Bt) {
+          const int64_t o = (base + bl) * d + j0 + jl;
+          dyp[i] = *reinterpret_cast<const float4*>(p.dy + o);
+          sp[i][0] = *reinterpret_cast<const uint2*>(p.r + o);
+          sp[i][1] = *reinterpret_cast<const uint2*>(p.z + o);
+          sp[i][2] = *reinterpret_cast<const uint2*>(p.n + o);
+          sp[i][3] = *reinterpret_cast<const uint2*>(p.ghn + o);
+          sp[i][4] = *reinterpret_cast<const uint2*>(p.hp_b + o);
+        }
+      }
+    };
+    int t_first = L - 1;
+    while (t_first >= 0 && !tile_active(t_first)) --t_first;
+    if (t_first >= 0) prefetch(t_first);
     int n_mma = 0;
-    for (int t = L - 1; t >= -1; --t) {
-      if (!tile_active(t)) continue;
+    for (int t = t_first; t >= -1; --t) {
       const bool mma = has_mma(t);
       const int B_next = (t + 1 <= L - 1) ? p.bt[t + 1] : 0;
-      const bool from_next = b < B_next;                 // this row existed at step t+1
-      const bool active = b < p.bt[t < 0 ? 0 : t];
+      const int Bt = p.bt[t < 0 ? 0 : t];
       if (mma) {
         ptx::mbar_wait(tmem_full_bar, n_mma & 1);
         ptx::tc_fence_after();
         ++n_mma;
-      }
-#pragma unroll 1
-      for (int c = 0; c < DJ; c += 16) {
-        uint32_t acc[16];
-        if (mma) {
-          ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, acc);
-          ptx::tmem_ld_wait();
-        }
-        if (!active) continue;
-        float dh[16];
+        if (m0 + q * 32 < B_next) {
+          float* dst = acc_sm + (q * 32 + lane) * ACC_LD;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dh[i] = from_next ? carry[c + i] + (mma ? __uint_as_float(acc[i]) : 0.f) : 0.f;
-        if (t < 0) {
-          float* o = p.dh0 + (int64_t)b * d + j0 + c;
+          for (int c = 0; c < NROWS; c += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 v = make_float4(dh[i], dh[i + 1], dh[i + 2], dh[i + 3]);
-            if (p.dh0_accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(o + i);
-              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-            }
-            *reinterpret_cast<float4*>(o + i) = v;
+            for (int k = 0; k < 16; ++k) dst[c + k] = __uint_as_float(v[k]);
           }
+        }
+        ptx::tc_fence_before();
+      }
+      epi_bar_sync();
+      const int64_t base = (t >= 0) ? (int64_t)p.off[t] + m0 : 0;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int e = tid + 128 * i, bl = e / G, jl = (e % G) * 4;
+        const int b = m0 + bl;
+        if (b >= Bt) continue;
+        const bool from_next = b < B_next;
+        float dh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          dh[k] = from_next ? carry[i][k] + (mma ? acc_sm[bl * ACC_LD + jl + k] : 0.f) : 0.f;
+        if (t < 0) {
+          float* o = p.dh0 + (int64_t)b * d + j0 + jl;
+          float4 v = make_float4(dh[0], dh[1], dh[2], dh[3]);
+          if (p.dh0_accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(o);
+            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+          }
+          *reinterpret_cast<float4*>(o) = v;
           continue;
         }
-        const int64_t row = (int64_t)p.off[t] + b;
-        const int64_t o = row * d + j0 + c;
-        float dyv[16], r[16], z[16], n[16], g[16], hp[16];
-        ld16_f32(p.dy + o, dyv);
-        ld8_bf16(p.r + o, r); ld8_bf16(p.r + o + 8, r + 8);
-        ld8_bf16(p.z + o, z); ld8_bf16(p.z + o + 8, z + 8);
-        ld8_bf16(p.n + o, n); ld8_bf16(p.n + o + 8, n + 8);
-        ld8_bf16(p.ghn + o, g); ld8_bf16(p.ghn + o + 8, g + 8);
-        ld8_bf16(p.hp_b + o, hp); ld8_bf16(p.hp_b + o + 8, hp + 8);
-        float dar[16], daz[16], dan[16], danr[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const GruBwd w = gru_bwd_math(dh[i] + dyv[i], r[i], z[i], n[i], g[i], hp[i]);
-          dar[i] = w.dar; daz[i] = w.daz; dan[i] = w.dan; danr[i] = w.dan_r;
-          carry[c + i] = w.dh_prev;
+        const float dyv[4] = {dyp[i].x, dyp[i].y, dyp[i].z, dyp[i].w};
+        float r[4], z[4], n[4], g[4], hp[4];
+        {
+          float2 a, c2;
+          a = unpack_bf16x2(sp[i][0].x); c2 = unpack_bf16x2(sp[i][0].y); r[0] = a.x; r[1] = a.y; r[2] = c2.x; r[3] = c2.y;
+          a = unpack_bf16x2(sp[i][1].x); c2 = unpack_bf16x2(sp[i][1].y); z[0] = a.x; z[1] = a.y; z[2] = c2.x; z[3] = c2.y;
+          a = unpack_bf16x2(sp[i][2].x); c2 = unpack_bf16x2(sp[i][2].y); n[0] = a.x; n[1] = a.y; n[2] = c2.x; n[3] = c2.y;
+          a = unpack_bf16x2(sp[i][3].x); c2 = unpack_bf16x2(sp[i][3].y); g[0] = a.x; g[1] = a.y; g[2] = c2.x; g[3] = c2.y;
+          a = unpack_bf16x2(sp[i][4].x); c2 = unpack_bf16x2(sp[i][4].y); hp[0] = a.x; hp[1] = a.y; hp[2] = c2.x; hp[3] = c2.y;
         }
-        const int64_t o3 = row * d3 + j0 + c;
-        st16_bf16(p.dgi_b + o3, dar);
-        st16_bf16(p.dgi_b + o3 + d, daz);
-        st16_bf16(p.dgi_b + o3 + 2 * d, dan);
-        st16_bf16(p.dgh_b + o3, dar);
-        st16_bf16(p.dgh_b + o3 + d, daz);
-        st16_bf16(p.dgh_b + o3 + 2 * d, danr);
+        float dar[4], daz[4], dan[4], danr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const GruBwd w = gru_bwd_math(dh[k] + dyv[k], r[k], z[k], n[k], g[k], hp[k]);
+          dar[k] = w.dar; daz[k] = w.daz; dan[k] = w.dan; danr[k] = w.dan_r;
+          carry[i][k] = w.dh_prev;
+        }
+        const int64_t o3 = (base + bl) * d3 + j0 + jl;
+        st4_bf16(p.dgi_b + o3, dar);
+        st4_bf16(p.dgi_b + o3 + d, daz);
+        st4_bf16(p.dgi_b + o3 + 2 * d, dan);
+        st4_bf16(p.dgh_b + o3, dar);
+        st4_bf16(p.dgh_b + o3 + d, daz);
+        st4_bf16(p.dgh_b + o3 + 2 * d, danr);
       }
-      ptx::tc_fence_before();
-      __threadfence();
-      asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores -> TMA (async proxy) readers
       epi_bar_sync();
-      if (warp == 2 && lane == 0) red_release_add(p.sync + bi, 1);
+      if (tid == 0) red_release_add(p.sync + bi, 1);
+      if (t - 1 >= 0) prefetch(t - 1);
     }
   }
   ptx::tc_fence_before();
@@ -453,7 +554,7 @@ static int pick_dj(int64_t d, int64_t bt0, int* stages_out) {
     if (d % dj) continue;
     if (nbt * (d / dj) > kNumSMs) continue;
     for (int st = 4; st >= 2; --st) {
-      const int64_t smem = 3LL * dj * d * 2 + (int64_t)st * GP_A_BYTES + 2048;
+      const int64_t smem = 3LL * dj * d * 2 + (int64_t)st * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048;
       if (smem <= 227 * 1024) {
         *stages_out = st;
         return dj;
@@ -518,7 +619,7 @@ extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16
   prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.gi = gi; prm.b_hh = b_hh;
   prm.h0 = h0; prm.hp_b = hp_b; prm.y_b = y_b; prm.r = r; prm.z = z; prm.n = n; prm.ghn = ghn;
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
-  const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 2048);
+  const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
 #define ARK_GP_FWD(DJ, ST) \
   if (dj == DJ && stages == ST) return launch_coop(gru_persist_fwd_kernel<DJ, ST>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd")
   ARK_GP_FWD(16, 4); ARK_GP_FWD(16, 3); ARK_GP_FWD(16, 2);
@@ -554,7 +655,7 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
   prm.z = z; prm.n = n; prm.ghn = ghn; prm.hp_b = hp_b; prm.dgi_b = dgi_b; prm.dgh_b = dgh_b; prm.dh0 = dh0;
   prm.dh0_accumulate = dh0_accumulate;
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
-  const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 2048);
+  const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
 #define ARK_GP_BWD(DJ, ST) \
   if (dj == DJ && stages == ST) return launch_coop(gru_persist_bwd_kernel<DJ, ST>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd")
   ARK_GP_BWD(16, 4); ARK_GP_BWD(16, 3); ARK_GP_BWD(16, 2);
