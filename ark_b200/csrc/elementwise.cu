@@ -67,6 +67,57 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, in
   }
 }
 
+// vector variant: each thread owns 4 consecutive columns (8 B of bf16 / 16 B of f32 per row), a warp covers 128
+// columns of a row contiguously; requires N % 4 == 0, ld % 4 == 0 and a 16-byte aligned base.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum4_kernel(const T* __restrict__ X, int64_t M, int N, int64_t ld,
+                                                      float* __restrict__ out) {
+  __shared__ float4 part[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) {
+    const int64_t stride = (int64_t)gridDim.y * 8;
+    int64_t r = (int64_t)blockIdx.y * 8 + ty;
+    for (; r + stride < M; r += 2 * stride) {       // two independent loads in flight
+      float4 a, b;
+      if constexpr (sizeof(T) == 2) {
+        const uint2 ua = *reinterpret_cast<const uint2*>(X + r * ld + col);
+        const uint2 ub = *reinterpret_cast<const uint2*>(X + (r + stride) * ld + col);
+        const float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y), b0 = unpack_bf16x2(ub.x), b1 = unpack_bf16x2(ub.y);
+        a = make_float4(a0.x, a0.y, a1.x, a1.y);
+        b = make_float4(b0.x, b0.y, b1.x, b1.y);
+      } else {
+        a = *reinterpret_cast<const float4*>(X + r * ld + col);
+        b = *reinterpret_cast<const float4*>(X + (r + stride) * ld + col);
+      }
+      acc.x += a.x + b.x; acc.y += a.y + b.y; acc.z += a.z + b.z; acc.w += a.w + b.w;
+    }
+    for (; r < M; r += stride) {
+      float4 a;
+      if constexpr (sizeof(T) == 2) {
+        const uint2 ua = *reinterpret_cast<const uint2*>(X + r * ld + col);
+        const float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y);
+        a = make_float4(a0.x, a0.y, a1.x, a1.y);
+      } else {
+        a = *reinterpret_cast<const float4*>(X + r * ld + col);
+      }
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    float4 s4 = part[0][tx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      s4.x += part[k][tx].x; s4.y += part[k][tx].y; s4.z += part[k][tx].z; s4.w += part[k][tx].w;
+    }
+    atomicAdd(out + col, s4.x); atomicAdd(out + col + 1, s4.y);
+    atomicAdd(out + col + 2, s4.z); atomicAdd(out + col + 3, s4.w);
+  }
+}
+
 __global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
                                                   float* __restrict__ y, uint16_t* __restrict__ yb) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,11 +143,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 
 __global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restrict__ x, int64_t n, float p,
                                                           uint64_t seed, uint64_t offset, float* __restrict__ y,
-                                                          uint16_t* __restrict__ yb, uint8_t* __restrict__ mask) {
+                                                          uint16_t* __restrict__ yb, uint8_t* __restrict__ mask,
+                                                          const uint64_t* __restrict__ offset_dev) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = q * 4;
   if (i >= n) return;
-  const uint64_t c = offset + (uint64_t)q;
+  const uint64_t c = offset + (offset_dev ? *offset_dev : 0ull) + (uint64_t)q;
   const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -113,11 +165,12 @@ __global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) dropout_bf16_kernel(const uint16_t* __restrict__ x, int64_t n, float p,
                                                            uint64_t seed, uint64_t offset, uint16_t* __restrict__ y,
-                                                           uint8_t* __restrict__ mask) {
+                                                           uint8_t* __restrict__ mask,
+                                                           const uint64_t* __restrict__ offset_dev) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = q * 4;
   if (i >= n) return;
-  const uint64_t c = offset + (uint64_t)q;
+  const uint64_t c = offset + (offset_dev ? *offset_dev : 0ull) + (uint64_t)q;
   const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -142,7 +195,11 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v,
                                                         uint16_t* __restrict__ shadow, int64_t n, float step_size,
                                                         float beta1, float beta2, float eps, float inv_sqrt_bc2,
-                                                        float grad_scale) {
+                                                        float grad_scale, const float* __restrict__ hyper) {
+  if (hyper) {   // CUDA-graph replay: step-dependent scalars live in device memory
+    step_size = hyper[0];
+    inv_sqrt_bc2 = hyper[1];
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 4 <= n) {
@@ -236,18 +293,22 @@ extern "C" int ark_colsum(const void* X, int dtype, int64_t M, int64_t N, int64_
     if (e != cudaSuccess) return fail((int)e, "colsum: memset: %s", cudaGetErrorString(e));
   }
   if (M == 0) return 0;
+  const bool vec = (N % 4 == 0) && (ld % 4 == 0) && aligned16(X);
+  const int64_t gx = vec ? (N + 127) / 128 : (N + 31) / 32;
   int64_t gy = (M + 63) / 64;
-  const int64_t gx = (N + 31) / 32;
   const int64_t want = 4 * kNumSMs;  // enough CTAs to cover the machine, few enough atomics
   if (gx * gy > want) gy = (want + gx - 1) / gx;
   if (gy < 1) gy = 1;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  if (dtype == ARK_BF16)
-    colsum_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)X, M, (int)N, ld, out);
-  else if (dtype == ARK_F32)
-    colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)X, M, (int)N, ld, out);
-  else
+  if (dtype == ARK_BF16) {
+    if (vec) colsum4_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)X, M, (int)N, ld, out);
+    else colsum_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)X, M, (int)N, ld, out);
+  } else if (dtype == ARK_F32) {
+    if (vec) colsum4_kernel<float><<<grid, 256, 0, s>>>((const float*)X, M, (int)N, ld, out);
+    else colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)X, M, (int)N, ld, out);
+  } else {
     return fail(ARK_E_BADARG, "colsum: unknown dtype %d", dtype);
+  }
   return launched("colsum");
 }
 
@@ -267,21 +328,22 @@ extern "C" int ark_cast_f32_to_bf16(const float* x, int64_t n, uint16_t* y, void
 }
 
 extern "C" int ark_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, float* y,
-                               uint16_t* y_bf16, uint8_t* mask, void* stream) {
+                               uint16_t* y_bf16, uint8_t* mask, const uint64_t* offset_dev, void* stream) {
   ARK_REQUIRE(x && (y || y_bf16), ARK_E_BADARG, "dropout_fwd: null pointer");
   ARK_REQUIRE(p >= 0.f && p < 1.f, ARK_E_BADARG, "dropout_fwd: p must be in [0,1)");
   if (n <= 0) return 0;
   dropout_fwd_kernel<<<blocks_for((n + 3) / 4, 256, 0), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y,
-                                                                                       y_bf16, mask);
+                                                                                       y_bf16, mask, offset_dev);
   return launched("dropout_fwd");
 }
 
 extern "C" int ark_dropout_bf16(const uint16_t* x, int64_t n, float p, uint64_t seed, uint64_t offset, uint16_t* y,
-                                uint8_t* mask, void* stream) {
+                                uint8_t* mask, const uint64_t* offset_dev, void* stream) {
   ARK_REQUIRE(x && y, ARK_E_BADARG, "dropout_bf16: null pointer");
   ARK_REQUIRE(p >= 0.f && p < 1.f, ARK_E_BADARG, "dropout_bf16: p must be in [0,1)");
   if (n <= 0) return 0;
-  dropout_bf16_kernel<<<blocks_for((n + 3) / 4, 256, 0), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, mask);
+  dropout_bf16_kernel<<<blocks_for((n + 3) / 4, 256, 0), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, mask,
+                                                                                        offset_dev);
   return launched("dropout_bf16");
 }
 
@@ -306,6 +368,18 @@ extern "C" int ark_adam_flat(float* p, const float* g, float* m, float* v, uint1
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   adam_flat_kernel<<<blocks_for(n, 1024, 16 * kNumSMs), 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, shadow, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
+      p, g, m, v, shadow, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale, nullptr);
   return launched("adam_flat");
+}
+
+extern "C" int ark_adam_flat_dyn(float* p, const float* g, float* m, float* v, uint16_t* shadow, int64_t n,
+                                 const float* hyper, float beta1, float beta2, float eps, float grad_scale,
+                                 void* stream) {
+  ARK_REQUIRE(p && g && m && v && hyper, ARK_E_BADARG, "adam_flat_dyn: null pointer");
+  ARK_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!shadow || aligned16(shadow)),
+              ARK_E_ALIGN, "adam_flat_dyn: 16-byte alignment");
+  if (n <= 0) return 0;
+  adam_flat_kernel<<<blocks_for(n, 1024, 16 * kNumSMs), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, shadow, n, 0.f, beta1, beta2, eps, 1.f, grad_scale, hyper);
+  return launched("adam_flat_dyn");
 }

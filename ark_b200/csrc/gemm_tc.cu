@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                                                       const int M, const int N, const int K,
                                                       const int a_row0, const int b_row0) {
   using L = TcSmem<BN, STAGES>;
+  static_assert(TC_BM * (BN + 4) * 4 <= L::BAR_OFFSET, "epilogue staging must fit in the TMA ring");
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -50,7 +51,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+  // swap_raster: the fast grid index walks the M tiles (A is the smaller operand), so each B tile is
+  // fetched once and A stays L2-resident; otherwise the fast index walks the N tiles.
+  const int n0 = (ep.swap_raster ? blockIdx.y : blockIdx.x) * BN, m0 = (ep.swap_raster ? blockIdx.x : blockIdx.y) * TC_BM;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
 
   if (threadIdx.x == 0) {
@@ -128,73 +131,82 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     const int q = warp & 3;  // TMEM lanes [32q, 32q+32)
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
-    const int64_t row = (int64_t)m0 + q * 32 + lane;
+    // Phase 1: each warp drains its 32 TMEM lanes (tile rows), applies bias / activation in registers and parks
+    // the finished values in shared memory (the TMA ring is idle by now: every k-block has been consumed).
+    // Phase 2: the 128 epilogue threads write the tile out ROW-CONTIGUOUSLY — a warp stores 512 contiguous bytes
+    // per instruction instead of 32 scattered 16-byte pieces.
+    constexpr int LD = BN + 4;                       // +4 floats: conflict-free float4 row-per-lane writes
+    float* stage = reinterpret_cast<float*>(smem);
+    const int r_loc = q * 32 + lane;
+    const int64_t row = (int64_t)m0 + r_loc;
     const bool row_ok = row < M;
-    const bool vec_ok = (ep.ldc % (ep.c_bf16 ? 8 : 4) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
-                        (!ep.aux || (reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN / 16; ++c) {
       uint32_t r[16];
       ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
       ptx::tmem_ld_wait();
       const int nb = n0 + c * 16;
-      if (!row_ok || nb >= N) continue;
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-      const bool full = (nb + 16 <= N);
       if (ep.bias) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (full || nb + i < N) v[i] += __ldg(ep.bias + nb + i);
+          if (nb + i < N) v[i] += __ldg(ep.bias + nb + i);
       }
-      const int64_t o = row * ep.ldc + nb;
-      if (ep.aux) {
-        if (full && vec_ok) {
+      if (ep.aux && row_ok) {                          // pre-activation (small encoder GEMMs only): direct store
+        const int64_t o = row * ep.ldc + nb;
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(ep.aux + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-          #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (nb + i < N) ep.aux[o + i] = v[i];
-        }
+        for (int i = 0; i < 16; ++i)
+          if (nb + i < N) ep.aux[o + i] = v[i];
       }
       if (ep.epilogue != ARK_EPI_NONE) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], ep.epilogue);
       }
+      float* sp = stage + r_loc * LD + c * 16;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(sp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int tid = threadIdx.x - 64;
+    const bool vec_ok = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
+    constexpr int F4_PER_ROW = BN / 4;
+#pragma unroll 4
+    for (int item = tid; item < TC_BM * F4_PER_ROW; item += 128) {
+      const int rl = item / F4_PER_ROW, c4 = item % F4_PER_ROW;
+      const int64_t grow = (int64_t)m0 + rl;
+      const int col = n0 + c4 * 4;
+      if (grow >= M || col >= N) continue;
+      const float4 w = *reinterpret_cast<const float4*>(stage + rl * LD + c4 * 4);
+      const int64_t o = grow * ep.ldc + col;
       if (ep.c_bf16) {
         uint16_t* cp = reinterpret_cast<uint16_t*>(ep.C) + o;
-        if (full && vec_ok) {
-          uint4 p0, p1;
-          p0.x = pack_bf16x2(v[0], v[1]); p0.y = pack_bf16x2(v[2], v[3]);
-          p0.z = pack_bf16x2(v[4], v[5]); p0.w = pack_bf16x2(v[6], v[7]);
-          p1.x = pack_bf16x2(v[8], v[9]); p1.y = pack_bf16x2(v[10], v[11]);
-          p1.z = pack_bf16x2(v[12], v[13]); p1.w = pack_bf16x2(v[14], v[15]);
-          *reinterpret_cast<uint4*>(cp) = p0;
-          *reinterpret_cast<uint4*>(cp + 8) = p1;
+        if (vec_ok && col + 4 <= N) {
+          uint2 pk;
+          pk.x = pack_bf16x2(w.x, w.y);
+          pk.y = pack_bf16x2(w.z, w.w);
+          *reinterpret_cast<uint2*>(cp) = pk;
         } else {
-          #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (nb + i < N) cp[i] = f32_to_bf16_bits(v[i]);
+          const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col + i < N) cp[i] = f32_to_bf16_bits(e[i]);
         }
       } else {
         float* cp = reinterpret_cast<float*>(ep.C) + o;
-        if (full && vec_ok) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            if (ep.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(cp + i);
-              w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-            }
-            *reinterpret_cast<float4*>(cp + i) = w;
+        if (vec_ok && col + 4 <= N) {
+          float4 x = w;
+          if (ep.accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(cp);
+            x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
           }
+          *reinterpret_cast<float4*>(cp) = x;
         } else {
-          #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (nb + i < N) cp[i] = ep.accumulate ? cp[i] + v[i] : v[i];
+          const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col + i < N) cp[i] = ep.accumulate ? cp[i] + e[i] : e[i];
         }
       }
     }
@@ -215,8 +227,11 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiPa
     if (e != cudaSuccess) return fail((int)e, "gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + TC_BM - 1) / TC_BM));
-  kern<<<grid, 192, L::TOTAL, s>>>(tmA, tmB, ep, M, N, K, a_row0, b_row0);
+  const unsigned nt = (unsigned)((N + BN - 1) / BN), mt = (unsigned)((M + TC_BM - 1) / TC_BM);
+  EpiParams ep2 = ep;
+  ep2.swap_raster = (M < N && nt <= 65535u) ? 1 : 0;
+  dim3 grid(ep2.swap_raster ? mt : nt, ep2.swap_raster ? nt : mt);
+  kern<<<grid, 192, L::TOTAL, s>>>(tmA, tmB, ep2, M, N, K, a_row0, b_row0);
   return launched("gemm_bf16_tc");
 }
 

@@ -13,6 +13,7 @@ struct EpiParams {
   int c_bf16;
   int epilogue;
   int accumulate;
+  int swap_raster;   // set by the launcher
 };
 
 int tc_pick_bn(int64_t M, int64_t N);

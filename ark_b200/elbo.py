@@ -68,6 +68,11 @@ class SailEngine:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._pending = []
         self.prof = None
+        self._capturing = False
+        self._graphs = {}
+        self.dyn_f = torch.zeros(2, device=dev)                      # [lr/(1-b1^t), 1/sqrt(1-b2^t)] for graph replay
+        self.dyn_i = torch.zeros(1, device=dev, dtype=torch.int64)   # running Philox offset for graph replay
+        self.launches_replayed = 0       # kernels of libarkb200 executed through graph replays
         self.force_unfused_gru = False   # tests: compare the persistent GRU kernel with the per-step path
         self.stats = torch.zeros(4, device=dev)  # [ce, kl, steps, unused] accumulated on device
         self.refresh_shadow()
@@ -133,6 +138,7 @@ class SailEngine:
         n_tok_g = float(N if n_tok_global is None else n_tok_global)
         b_g = int(B if batch_global is None else batch_global)
         out = torch.zeros(2, device=dev) if stats_out is None else stats_out
+        self._drop_calls = 0
         use_tc = 1 if self.backend == "tc" else 0
         new = lambda *s, dtype=f32: torch.empty(*s, device=dev, dtype=dtype)  # noqa: E731
 
@@ -194,8 +200,13 @@ class SailEngine:
             mask = None
             if train and self.p_drop > 0 and k < nl - 1:
                 mask = new(N, d, dtype=torch.uint8)
-                ops.dropout_bf16(y_b, self.p_drop, self.seed, self.philox_offset, y_b, mask)
-                self.philox_offset += (N * d + 3) // 4
+                if self._capturing:   # replayed graphs read the running Philox offset from device memory
+                    ops.dropout_bf16(y_b, self.p_drop, self.seed, self._drop_calls * ((N * d + 3) // 4), y_b, mask,
+                                     self.dyn_i)
+                else:
+                    ops.dropout_bf16(y_b, self.p_drop, self.seed, self.philox_offset, y_b, mask)
+                    self.philox_offset += (N * d + 3) // 4
+                self._drop_calls += 1
             saved.append((u_b, hp_f, hp_b, gates, mask))
             u_b = y_b
             del gi
@@ -335,6 +346,63 @@ class SailEngine:
         self.stats[0:2] += out
         self.stats[2] += 1
         return out
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def train_step_graphed(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
+        """Same as train_step, but the ~190 launches of the step are captured ONCE per batch layout
+        (B, T, per-step row counts, normalisers, beta) into a CUDA graph and replayed: the host cost of a step
+        drops to a few small input copies + one graph launch.  Layouts that never repeat (ragged real data)
+        should use train_step.  Not used under data parallelism (the NCCL side stream stays eager)."""
+        if self.world > 1:
+            return self.train_step(triples, seq, lay, eps, beta, lr, n_tok_global, batch_global)
+        key = (tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(), float(beta), n_tok_global, batch_global)
+        ent = self._graphs.get(key)
+        self.step_count += 1
+        lr = self.lr if lr is None else float(lr)
+        b1, b2 = self.betas
+        # pageable sources: the driver stages them at call time, so the next step may overwrite nothing in flight
+        self.dyn_f.copy_(torch.tensor([lr / (1.0 - b1 ** self.step_count), 1.0 / math.sqrt(1.0 - b2 ** self.step_count)],
+                                      dtype=torch.float32))
+        self.dyn_i.copy_(torch.tensor([self.philox_offset], dtype=torch.int64))
+        if ent is None:
+            dev = self.device
+            st = {"triples": triples.to(dev, copy=True), "seq": seq.to(dev, copy=True), "eps": eps.to(dev, copy=True),
+                  "lay": PackedLayout(perm=lay.perm, lens=lay.lens, bt=lay.bt, off=lay.off, n_tok=lay.n_tok,
+                                      n_triples=lay.n_triples, L=lay.L, perm_dev=lay.perm_dev.clone(),
+                                      bt_dev=lay.bt_dev.clone(), off_dev=lay.off_dev.clone())}
+
+            def body():
+                out = self.forward_backward(st["triples"], st["seq"], st["lay"], st["eps"], beta, n_tok_global,
+                                            batch_global, train=True)
+                f = self.flat
+                ops.adam_flat_dyn(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.dyn_f, b1, b2, self.eps)
+                self.stats[0:2] += out
+                self.stats[2] += 1
+                return out
+
+            # warm-up outside capture is NOT wanted (it would apply an extra optimiser step): capture directly
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            from . import _C
+            n0 = _C.lib().launch_count()
+            self._capturing = True
+            try:
+                with torch.cuda.graph(g):
+                    st["out"] = body()
+            finally:
+                self._capturing = False
+            st["graph"], st["philox_per_step"] = g, self._drop_calls * ((lay.n_tok * self.d + 3) // 4)
+            st["n_launch"] = _C.lib().launch_count() - n0
+            self._graphs[key] = ent = st
+        else:
+            ent["triples"].copy_(triples, non_blocking=True)
+            ent["seq"].copy_(seq, non_blocking=True)
+            ent["eps"].copy_(eps, non_blocking=True)
+            ent["lay"].perm_dev.copy_(lay.perm_dev, non_blocking=True)
+        ent["graph"].replay()
+        self.launches_replayed += ent["n_launch"]
+        self.philox_offset += ent["philox_per_step"]
+        return ent["out"]
 
     def eval_step(self, triples, seq, lay, eps, beta):
         """Forward only (validation loss, ablation_study.py:92-187 without the generation part)."""

@@ -192,10 +192,11 @@ def cast_bf16(x, y):
     _C.lib().call("ark_cast_f32_to_bf16", _ptr(x, torch.float32), x.numel(), _ptr(y, torch.bfloat16), _stream())
 
 
-def dropout_fwd(x, p, seed, offset, y=None, y_bf16=None, mask=None):
+def dropout_fwd(x, p, seed, offset, y=None, y_bf16=None, mask=None, offset_dev=None):
     _contig(x, y, y_bf16, mask)
     _C.lib().call("ark_dropout_fwd", _ptr(x, torch.float32), x.numel(), float(p), int(seed), int(offset),
-                  _ptr(y, torch.float32), _ptr(y_bf16, torch.bfloat16), _ptr(mask, torch.uint8), _stream())
+                  _ptr(y, torch.float32), _ptr(y_bf16, torch.bfloat16), _ptr(mask, torch.uint8),
+                  _ptr(offset_dev, torch.int64), _stream())
 
 
 def dropout_bwd(dy, mask, p, dx):
@@ -240,7 +241,14 @@ def gru_persist_bwd(dy, gates, hp_b, WhhT_b, bt_dev, off_dev, L, bt0, d, dgi_b, 
                   int(accumulate), _ptr(sync_ws, torch.int32), _stream())
 
 
-def dropout_bf16(x, p, seed, offset, y, mask=None):
+def dropout_bf16(x, p, seed, offset, y, mask=None, offset_dev=None):
     _contig(x, y, mask)
     _C.lib().call("ark_dropout_bf16", _ptr(x, torch.bfloat16), x.numel(), float(p), int(seed), int(offset),
-                  _ptr(y, torch.bfloat16), _ptr(mask, torch.uint8), _stream())
+                  _ptr(y, torch.bfloat16), _ptr(mask, torch.uint8), _ptr(offset_dev, torch.int64), _stream())
+
+
+def adam_flat_dyn(p, g, m, v, shadow, hyper, beta1, beta2, eps, grad_scale=1.0):
+    _contig(p, g, m, v, shadow, hyper)
+    _C.lib().call("ark_adam_flat_dyn", _ptr(p, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32),
+                  _ptr(v, torch.float32), _ptr(shadow, torch.bfloat16), p.numel(), _ptr(hyper, torch.float32),
+                  float(beta1), float(beta2), float(eps), float(grad_scale), _stream())

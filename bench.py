@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--backend", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -191,23 +192,26 @@ def main():
     bg = batch * world
     beta = 0.5
 
-    def step(i):
+    use_graph = (world == 1) and not args.no_graph
+
+    def step(i, graph=use_graph):
         j = i % NB
-        return eng.train_step(dbs[j].triples, dbs[j].seq, dbs[j].layout, eps[j], beta,
-                              n_tok_global=ntok_g[j], batch_global=bg)
+        fn = eng.train_step_graphed if graph else eng.train_step
+        return fn(dbs[j].triples, dbs[j].seq, dbs[j].layout, eps[j], beta, n_tok_global=ntok_g[j], batch_global=bg)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3) + (NB if use_graph else 0)):   # graph mode: first visit of a layout captures
         step(i)
     barrier()
     lib = _C.lib()
     sampler = ClockSampler(local)
     sampler.start()
     lib.reset_launch_count()
+    replayed0 = eng.launches_replayed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -215,7 +219,7 @@ def main():
         step(i)
     e1.record()
     barrier()
-    launches = lib.launch_count()
+    launches = lib.launch_count() + (eng.launches_replayed - replayed0)   # eager launches + kernels inside replayed graphs
     clocks = sampler.result()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -231,14 +235,16 @@ def main():
         pinned = [b.host for b in dbs]
         h2d = pinned[0][0].numel() * 8 + pinned[0][1].numel() * 8 + (batch + 2 * dbs[0].layout.L) * 4
         for i in range(2):
-            model.elbo_step(pinned[i % NB][0], pinned[i % NB][1], beta, n_tok_global=ntok_g[i % NB], batch_global=bg).tolist()
+            model.elbo_step(pinned[i % NB][0], pinned[i % NB][1], beta, n_tok_global=ntok_g[i % NB], batch_global=bg,
+                            graph=use_graph).tolist()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
         for i in range(args.steps):
             j = i % NB
-            out = model.elbo_step(pinned[j][0], pinned[j][1], beta, n_tok_global=ntok_g[j], batch_global=bg)
+            out = model.elbo_step(pinned[j][0], pinned[j][1], beta, n_tok_global=ntok_g[j], batch_global=bg,
+                                  graph=use_graph)
             out.tolist()                                    # device->host read of the step's (ce, kl)
         f1.record()
         barrier()
@@ -253,7 +259,7 @@ def main():
     # ---------------- roofline pass: CUDA events around every op of the same steps (rank 0 reports)
     eng.prof = []
     for i in range(min(args.steps, 8)):
-        step(i)
+        step(i, graph=False)          # events cannot be recorded inside a replayed graph: eager launches
     agg = eng.profile_summary()
     n_prof = min(args.steps, 8)
     eng.prof = None
@@ -307,7 +313,7 @@ def main():
                        "triples_per_step": triples_done / args.steps, "tokens_per_step_rank0": dbs[0].layout.n_tok,
                        "dense": bool(args.dense), "parallelism": f"dp{world}",
                        "l2": "per-step working set (params+grads+Adam state+activations) exceeds the 126 MB L2; "
-                             "no explicit flush", "gemm_backend": args.backend,
+                             "no explicit flush", "gemm_backend": args.backend, "cuda_graph": bool(use_graph),
                        "precision": "bf16 GEMM operands, fp32 accumulate/master/state"},
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roof, "final_loss": {"loss": final[0], "ce": final[1], "kl": final[2]},

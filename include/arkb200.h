@@ -185,12 +185,13 @@ int ark_colsum(const void* X, int dtype, int64_t M, int64_t N, int64_t ld, float
 int ark_add_f32(const float* a, const float* b, int64_t n, float* y, uint16_t* y_bf16, void* stream);
 int ark_cast_f32_to_bf16(const float* x, int64_t n, uint16_t* y, void* stream);
 /* inter-layer dropout (nn.GRU dropout=dec_dropout, train mode): y = x * keep/(1-p), Philox4x32-10 keyed
- * by (seed, offset+element); mask uint8 [n] saved for backward. */
+ * by (seed, offset + *offset_dev + element); offset_dev (device uint64, may be NULL) lets a captured CUDA graph
+ * draw fresh masks on every replay; mask uint8 [n] saved for backward. */
 int ark_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset,
-                    float* y, uint16_t* y_bf16, uint8_t* mask, void* stream);
+                    float* y, uint16_t* y_bf16, uint8_t* mask, const uint64_t* offset_dev, void* stream);
 /* same Philox stream on a bf16 tensor (the GRU layer outputs of the training path); y may alias x */
 int ark_dropout_bf16(const uint16_t* x, int64_t n, float p, uint64_t seed, uint64_t offset,
-                     uint16_t* y, uint8_t* mask, void* stream);
+                     uint16_t* y, uint8_t* mask, const uint64_t* offset_dev, void* stream);
 int ark_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, void* stream);
 
 /* ---- K10: dense Adam over a flat parameter buffer (torch.optim.Adam defaults, ablation_study.py:571) ----
@@ -198,6 +199,10 @@ int ark_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, fl
  * multiplies g first (1 for summed DP gradients). */
 int ark_adam_flat(float* p, const float* g, float* m, float* v, uint16_t* shadow, int64_t n,
                   float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+/* Same update with the step-dependent scalars in DEVICE memory: hyper[0] = lr/(1-beta1^step),
+ * hyper[1] = 1/sqrt(1-beta2^step) — so the launch can be replayed from a CUDA graph. */
+int ark_adam_flat_dyn(float* p, const float* g, float* m, float* v, uint16_t* shadow, int64_t n,
+                      const float* hyper, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -195,11 +195,19 @@ class SAIL(nn.Module):
         return out
 
     def elbo_step(self, triples, seq, beta, eps=None, layout: PackedLayout = None, lr=None,
-                  n_tok_global=None, batch_global=None):
-        """elbo_backward + the fused Adam update: one full optimisation step (ablation_study.py:43,59-76)."""
-        out = self.elbo_backward(triples, seq, beta, eps, layout, n_tok_global, batch_global)
-        self._engine.adam_step(lr)
-        return out
+                  n_tok_global=None, batch_global=None, graph=False):
+        """elbo_backward + the fused Adam update: one full optimisation step (ablation_study.py:43,59-76).
+        ``graph=True`` replays a CUDA graph captured per batch layout (fixed-size datasets such as syn-*)."""
+        if not graph:
+            out = self.elbo_backward(triples, seq, beta, eps, layout, n_tok_global, batch_global)
+            self._engine.adam_step(lr)
+            return out
+        eng = self.engine()
+        if layout is None:
+            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+        if eps is None:
+            eps = torch.randn(triples.shape[0], self.config["d_latent"], device=eng.device)
+        return eng.train_step_graphed(triples, seq, layout, eps, float(beta), lr, n_tok_global, batch_global)
 
     # ---- reference interface -----------------------------------------------------------------------
     def kl_mean(self, mu, logv):

@@ -255,3 +255,25 @@ def test_persistent_gru_agrees_with_per_step_path():
     gb = eng.flat.grad.clone()
     torch.testing.assert_close(a, b, rtol=5e-3, atol=1e-5)
     assert ((ga - gb).norm() / gb.norm()).item() < 2e-2
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """Replaying the captured step (device-resident Adam scalars / Philox offset) == launching it eagerly."""
+    cfg, tri, seq, rng = _random_case(21, nE=60, nR=4, lo=4, hi=4, pad=False, d=64, dz=8, nl=2, B=40)
+    eps = [torch.from_numpy(rng.standard_normal((40, 8)).astype(np.float32)).to(DEV) for _ in range(3)]
+    seq_t = torch.from_numpy(seq)
+    lay = pack_layout(seq_t).to(DEV)
+    tri_d, seq_d = torch.from_numpy(tri).to(DEV), seq_t.to(DEV)
+    res = []
+    for graphed in (False, True):
+        torch.manual_seed(6)
+        model = SAIL(dict(cfg)).to(DEV)
+        eng = model.engine(lr=3e-3)
+        outs = []
+        for s in range(3):
+            fn = eng.train_step_graphed if graphed else eng.train_step
+            outs.append(fn(tri_d, seq_d, lay, eps[s], 0.5).clone())
+        res.append((torch.stack(outs), eng.flat.param.clone(), eng.step_count))
+    assert res[0][2] == res[1][2] == 3
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-4, atol=1e-6)
