@@ -10,6 +10,16 @@ namespace ark {
 
 constexpr int kCeThreads = 512;
 
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2(float x) {   // 2^x on the MUFU pipe; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The kernel is as much instruction-issue bound as HBM bound (a bf16 logit is 2 bytes of traffic), so the
+// inner loops are written to cost ~5.6 (pass 1) + ~3.6 (pass 2) instructions per element: one FFMA feeds the
+// MUFU directly (x*log2e - max*log2e), the gradient scale is folded into the exponent.
 struct OnlineLse {
   float m, s;  // running max, running sum of exp(x - m)
   __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
@@ -18,15 +28,17 @@ struct OnlineLse {
 #pragma unroll
     for (int i = 1; i < 8; ++i) mx = fmaxf(mx, x[i]);
     const float mn = fmaxf(m, mx);
+    const float nb = -mn * kLog2e;
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc += __expf(x[i] - mn);
-    s = s * __expf(m - mn) + acc;  // exp(-inf - finite) = 0 on the first push
+    for (int i = 0; i < 8; ++i) acc += ex2(fmaf(x[i], kLog2e, nb));
+    s = fmaf(s, ex2(fmaf(m, kLog2e, nb)), acc);  // ex2(-inf) = 0 on the first push
     m = mn;
   }
   __device__ __forceinline__ void push(float x) {
     const float mn = fmaxf(m, x);
-    s = s * __expf(m - mn) + __expf(x - mn);
+    const float nb = -mn * kLog2e;
+    s = fmaf(s, ex2(fmaf(m, kLog2e, nb)), ex2(fmaf(x, kLog2e, nb)));
     m = mn;
   }
 };
@@ -57,8 +69,9 @@ __device__ __forceinline__ void st1(float* p, float x) { *p = x; }
 
 // one CTA per row (grid-stride over rows).  Requires ldv % 8 == 0 and a 16B-aligned base so that every
 // row starts on a 16-byte boundary: all accesses inside [0, V8) are 128-bit.
-template <typename T>
-__global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(
+// U = independent 16-byte loads per thread in flight (4 for long rows, 2 for short ones)
+template <typename T, int U>
+__global__ void __launch_bounds__(kCeThreads, U == 4 ? 2 : 4) softmax_ce_kernel(
     T* __restrict__ logits, int64_t N, int V, int64_t ldv, const int32_t* __restrict__ tgt, float grad_scale,
     int write_grad, float* __restrict__ loss_acc, float* __restrict__ lse_out) {
   __shared__ float red[33];
@@ -68,14 +81,26 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(
     T* x = logits + row * ldv;
     OnlineLse st;
     st.init();
-    for (int c = threadIdx.x * 8; c < V8; c += kCeThreads * 8) {
-      float v[8];
-      load8(x + c, v);
-      st.push8(v);
+    {
+      // bytes in flight decide the DRAM rate here: 4 independent 16-byte loads per thread before any math
+      constexpr int S = kCeThreads * 8;
+      int c = threadIdx.x * 8;
+      for (; c + (U - 1) * S < V8; c += U * S) {
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) load8(x + c + u * S, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) st.push8(v[u]);
+      }
+      for (; c < V8; c += S) {
+        float v[8];
+        load8(x + c, v);
+        st.push8(v);
+      }
     }
     for (int c = V8 + threadIdx.x; c < V; c += kCeThreads) st.push(ld1(x + c));
     const float M = block_max(st.m, red);
-    const float contrib = (st.m == -INFINITY) ? 0.f : st.s * __expf(st.m - M);
+    const float contrib = (st.m == -INFINITY) ? 0.f : st.s * ex2((st.m - M) * kLog2e);
     const float S = block_sum(contrib, red);
     const float lse = M + __logf(S);
     const int t = tgt[row];
@@ -85,18 +110,43 @@ __global__ void __launch_bounds__(kCeThreads) softmax_ce_kernel(
     }
     if (write_grad) {
       __syncthreads();  // thread 0 has read x[t] before anyone overwrites it
-      for (int c = threadIdx.x * 8; c < V8; c += kCeThreads * 8) {
+      // grad = scale*exp(x - lse) = 2^(x*log2e + kk), kk = log2(scale) - lse*log2e
+      const float kk = fmaf(-lse, kLog2e, __log2f(grad_scale));
+      constexpr int S = kCeThreads * 8;
+      int c = threadIdx.x * 8;
+      for (; c + (U - 1) * S < V8; c += U * S) {
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) load8(x + c + u * S, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[u][i] = ex2(fmaf(v[u][i], kLog2e, kk));
+          if ((unsigned)(t - (c + u * S)) < 8u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i == t - (c + u * S)) v[u][i] -= grad_scale;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) store8(x + c + u * S, v[u]);
+      }
+      for (; c < V8; c += kCeThreads * 8) {
         float v[8];
         load8(x + c, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = grad_scale * __expf(v[i] - lse);
-        if (t >= c && t < c + 8) v[t - c] -= grad_scale;
+        for (int i = 0; i < 8; ++i) v[i] = ex2(fmaf(v[i], kLog2e, kk));
+        if ((unsigned)(t - c) < 8u) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i == t - c) v[i] -= grad_scale;
+        }
         store8(x + c, v);
       }
       for (int c = V8 + threadIdx.x; c < (int)ldv; c += kCeThreads) {
         float g = 0.f;
         if (c < V) {
-          g = grad_scale * __expf(ld1(x + c) - lse);
+          g = ex2(fmaf(ld1(x + c), kLog2e, kk));
           if (c == t) g -= grad_scale;
         }
         st1(x + c, g);
@@ -118,14 +168,18 @@ extern "C" int ark_softmax_ce(void* logits, int dtype, int64_t N, int64_t V, int
               "softmax_ce: ldv=%lld must be a multiple of 8 and the base 16-byte aligned", (long long)ldv);
   if (N == 0) return 0;
   // 2 CTAs of 512 threads per SM keep one row loading while another computes/stores
-  const unsigned grid = (unsigned)(N < 4 * kNumSMs ? N : 4 * kNumSMs);
-  if (dtype == ARK_BF16)
-    softmax_ce_kernel<uint16_t><<<grid, kCeThreads, 0, (cudaStream_t)stream>>>(
-        (uint16_t*)logits, N, (int)V, ldv, tgt, grad_scale, write_grad, loss_acc, lse);
-  else if (dtype == ARK_F32)
-    softmax_ce_kernel<float><<<grid, kCeThreads, 0, (cudaStream_t)stream>>>((float*)logits, N, (int)V, ldv, tgt,
-                                                                           grad_scale, write_grad, loss_acc, lse);
-  else
+  const bool deep = V >= 40000;   // long rows: 4 loads in flight per thread, 2 CTAs/SM; short rows: 2 loads, 4 CTAs/SM
+  const int per_sm = deep ? 2 : 4;
+  const unsigned grid = (unsigned)(N < per_sm * kNumSMs ? N : per_sm * kNumSMs);
+  cudaStream_t s = (cudaStream_t)stream;
+#define ARK_CE_GO(TT, UU) softmax_ce_kernel<TT, UU><<<grid, kCeThreads, 0, s>>>((TT*)logits, N, (int)V, ldv, tgt, grad_scale, write_grad, loss_acc, lse)
+  if (dtype == ARK_BF16) {
+    if (deep) ARK_CE_GO(uint16_t, 4); else ARK_CE_GO(uint16_t, 2);
+  } else if (dtype == ARK_F32) {
+    if (deep) ARK_CE_GO(float, 4); else ARK_CE_GO(float, 2);
+  } else {
     return fail(ARK_E_BADARG, "softmax_ce: unknown dtype %d", dtype);
+  }
+#undef ARK_CE_GO
   return launched("softmax_ce");
 }
