@@ -7,8 +7,8 @@
 // Operand majors: K-major (contraction contiguous) and MN-major (stored [K, M|N]) are both consumed
 // directly, so dX = dY.W and dW = dY^T.X need no transposed copies in HBM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA issuer
-// (one elected lane), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).  One output tile per CTA;
+// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA issuer
+// (one elected lane), warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp-2)/4).  One output tile per CTA;
 // 96 KB of smem per CTA lets two CTAs share an SM so one tile's epilogue overlaps the other's main loop.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -19,14 +19,24 @@ namespace ark {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_EPI_THREADS = 256;              // 8 epilogue warps: 2 per TMEM lane quadrant (column halves)
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;  // + warp 0 (TMA producer) + warp 1 (TMEM owner, MMA issuer)
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PERSIST>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_LD = BN + 4;  // +4 floats: conflict-free float4 row-per-lane writes
+  static constexpr int STAGING_BYTES = TC_BM * STAGING_LD * 4;
+  // one-tile kernel: the epilogue staging tile aliases the (by then idle) TMA ring;
+  // persistent kernel: the next tile's main loop runs during the epilogue, so staging has its own memory
+  static constexpr int STAGING_OFFSET = PERSIST ? RING_BYTES : 0;
+  static constexpr int BAR_OFFSET = PERSIST ? RING_BYTES + STAGING_BYTES : RING_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;  // barriers, tmem ptr, bias tile, slack
+  static_assert(PERSIST || STAGING_BYTES <= RING_BYTES, "epilogue staging must fit in the TMA ring");
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ float apply_act(float v, int epilogue) {
@@ -35,26 +45,39 @@ __device__ __forceinline__ float apply_act(float v, int epilogue) {
   return v;
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+// PERSIST = false: one output tile per CTA (grid = #tiles), two CTAs per SM overlap each other's epilogue.
+// PERSIST = true : grid = #SMs, each CTA walks tiles blockIdx.x, +gridDim.x, ...; the accumulator is double
+//                  buffered in TMEM (2 x BN columns) so the MMA warp starts tile i+1 while the epilogue warps
+//                  drain tile i — no per-tile launch / TMEM alloc / barrier init, no idle tensor pipe during stores.
+template <int BN, bool A_MN, bool B_MN, int STAGES, bool PERSIST>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
                                                       const int M, const int N, const int K,
                                                       const int a_row0, const int b_row0) {
-  using L = TcSmem<BN, STAGES>;
-  static_assert(TC_BM * (BN + 4) * 4 <= L::BAR_OFFSET, "epilogue staging must fit in the TMA ring");
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  using L = TcSmem<BN, STAGES, PERSIST>;
+  constexpr int NACC = PERSIST ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = (NACC * BN) < 32 ? 32 : NACC * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // swap_raster: the fast grid index walks the M tiles (A is the smaller operand), so each B tile is
-  // fetched once and A stays L2-resident; otherwise the fast index walks the N tiles.
-  const int n0 = (ep.swap_raster ? blockIdx.y : blockIdx.x) * BN, m0 = (ep.swap_raster ? blockIdx.x : blockIdx.y) * TC_BM;
+  const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + BN - 1) / BN;
+  const int num_tiles = mt * nt;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int tile_step = PERSIST ? (int)gridDim.x : num_tiles;   // one-tile kernel: a single trip
+  // swap_raster: consecutive tile indices walk the M tiles (A is the smaller operand), so a B tile is fetched
+  // once while A stays L2-resident; otherwise they walk the N tiles.
+  auto tile_origin = [&](int tile, int& m0, int& n0) {
+    const int mi = ep.swap_raster ? tile % mt : tile / nt;
+    const int ni = ep.swap_raster ? tile / mt : tile % nt;
+    m0 = mi * TC_BM;
+    n0 = ni * BN;
+  };
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -63,7 +86,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], TC_EPI_THREADS / 32);   // one arrival per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -78,26 +104,30 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* a_s = smem + s * L::STAGE_BYTES;
-        uint8_t* b_s = a_s + L::A_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        if (A_MN) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
+        int m0, n0;
+        tile_origin(tile, m0, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* a_s = smem + s * L::STAGE_BYTES;
+          uint8_t* b_s = a_s + L::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 64; ++j)
-            ptx::tma_load_2d(a_s + j * (TC_BK * 128), &tmA, &full_bar[s], a_row0 + m0 + 64 * j, kb * TC_BK);
-        } else {
-          ptx::tma_load_2d(a_s, &tmA, &full_bar[s], kb * TC_BK, a_row0 + m0);
-        }
-        if (B_MN) {
+            for (int j = 0; j < TC_BM / 64; ++j)
+              ptx::tma_load_2d(a_s + j * (TC_BK * 128), &tmA, &full_bar[s], a_row0 + m0 + 64 * j, kb * TC_BK);
+          } else {
+            ptx::tma_load_2d(a_s, &tmA, &full_bar[s], kb * TC_BK, a_row0 + m0);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            ptx::tma_load_2d(b_s + j * (TC_BK * 128), &tmB, &full_bar[s], b_row0 + n0 + 64 * j, kb * TC_BK);
-        } else {
-          ptx::tma_load_2d(b_s, &tmB, &full_bar[s], kb * TC_BK, b_row0 + n0);
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_2d(b_s + j * (TC_BK * 128), &tmB, &full_bar[s], b_row0 + n0 + 64 * j, kb * TC_BK);
+          } else {
+            ptx::tma_load_2d(b_s, &tmB, &full_bar[s], kb * TC_BK, b_row0 + n0);
+          }
         }
       }
     }
@@ -105,110 +135,178 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::A_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < TC_BK / 16; ++kk) {
-          // K-major: 16 bf16 = 32 B further along the swizzled 128 B row; rows of 8 are 1024 B apart.
-          // MN-major: 16 k-rows of 128 B = 2048 B further; 64-element MN groups are TC_BK*128 B apart.
-          const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(a_addr + kk * 2048, TC_BK * 128, 1024)
-                                      : ptx::make_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(b_addr + kk * 2048, TC_BK * 128, 1024)
-                                      : ptx::make_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-          ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step, ++lt) {
+        const int acc = PERSIST ? (lt & 1) : 0;
+        if (PERSIST) {   // the epilogue must have drained this accumulator (2 tiles ago)
+          ptx::mbar_wait(&tmem_empty_bar[acc], ((lt >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
         }
-        ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            // K-major: 16 bf16 = 32 B further along the swizzled 128 B row; rows of 8 are 1024 B apart.
+            // MN-major: 16 k-rows of 128 B = 2048 B further; 64-element MN groups are TC_BK*128 B apart.
+            const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(a_addr + kk * 2048, TC_BK * 128, 1024)
+                                        : ptx::make_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(b_addr + kk * 2048, TC_BK * 128, 1024)
+                                        : ptx::make_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
+            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        }
+        ptx::umma_commit(&tmem_full_bar[acc]);
       }
-      ptx::umma_commit(tmem_full_bar);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lanes [32q, 32q+32)
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
     // Phase 1: each warp drains its 32 TMEM lanes (tile rows), applies bias / activation in registers and parks
-    // the finished values in shared memory (the TMA ring is idle by now: every k-block has been consumed).
-    // Phase 2: the 128 epilogue threads write the tile out ROW-CONTIGUOUSLY — a warp stores 512 contiguous bytes
-    // per instruction instead of 32 scattered 16-byte pieces.
-    constexpr int LD = BN + 4;                       // +4 floats: conflict-free float4 row-per-lane writes
-    float* stage = reinterpret_cast<float*>(smem);
+    // the finished values in shared memory.  Phase 2: the 128 epilogue threads write the tile out
+    // ROW-CONTIGUOUSLY — a warp stores 512 contiguous bytes per instruction.
+    const int q = warp & 3;                 // TMEM lanes [32q, 32q+32)
+    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp drains
+    constexpr int LD = L::STAGING_LD;
+    constexpr int HALF_N = BN / 2;
+    float* stage = reinterpret_cast<float*>(smem + L::STAGING_OFFSET);
+    float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [BN] this tile's bias, staged once per tile
     const int r_loc = q * 32 + lane;
-    const int64_t row = (int64_t)m0 + r_loc;
-    const bool row_ok = row < M;
-#pragma unroll 1
-    for (int c = 0; c < BN / 16; ++c) {
-      uint32_t r[16];
-      ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
-      ptx::tmem_ld_wait();
-      const int nb = n0 + c * 16;
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-      if (ep.bias) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (nb + i < N) v[i] += __ldg(ep.bias + nb + i);
-      }
-      if (ep.aux && row_ok) {                          // pre-activation (small encoder GEMMs only): direct store
-        const int64_t o = row * ep.ldc + nb;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (nb + i < N) ep.aux[o + i] = v[i];
-      }
-      if (ep.epilogue != ARK_EPI_NONE) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], ep.epilogue);
-      }
-      float* sp = stage + r_loc * LD + c * 16;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(sp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int tid = threadIdx.x - 64;
-    const bool vec_ok = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
+    const bool vec_ok = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
+                        (!ep.aux || (reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0);
+    const bool plain = vec_ok && ep.epilogue == ARK_EPI_NONE && !ep.aux && (ep.ldc % 8 == 0);
     constexpr int F4_PER_ROW = BN / 4;
-#pragma unroll 4
-    for (int item = tid; item < TC_BM * F4_PER_ROW; item += 128) {
-      const int rl = item / F4_PER_ROW, c4 = item % F4_PER_ROW;
-      const int64_t grow = (int64_t)m0 + rl;
-      const int col = n0 + c4 * 4;
-      if (grow >= M || col >= N) continue;
-      const float4 w = *reinterpret_cast<const float4*>(stage + rl * LD + c4 * 4);
-      const int64_t o = grow * ep.ldc + col;
-      if (ep.c_bf16) {
-        uint16_t* cp = reinterpret_cast<uint16_t*>(ep.C) + o;
-        if (vec_ok && col + 4 <= N) {
-          uint2 pk;
-          pk.x = pack_bf16x2(w.x, w.y);
-          pk.y = pack_bf16x2(w.z, w.w);
-          *reinterpret_cast<uint2*>(cp) = pk;
-        } else {
-          const float e[4] = {w.x, w.y, w.z, w.w};
+    constexpr int G8_PER_ROW = BN / 8;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step, ++lt) {
+      int m0, n0;
+      tile_origin(tile, m0, n0);
+      const int acc = PERSIST ? (lt & 1) : 0;
+      // bias for the tile's columns: ONE coalesced global load per tile, issued before the MMA wait
+      if (tid < BN) bias_s[tid] = (ep.bias && n0 + tid < N) ? __ldg(ep.bias + n0 + tid) : 0.f;
+      ptx::mbar_wait(&tmem_full_bar[acc], PERSIST ? ((lt >> 1) & 1) : 0);
+      ptx::tc_fence_after();
+      // Phase 1: raw accumulators TMEM -> smem; all of this warp's loads are in flight before the single wait
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N);
+      float* sp = stage + r_loc * LD + half * HALF_N;
+      {
+        uint32_t r[HALF_N / 16][16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (col + i < N) cp[i] = f32_to_bf16_bits(e[i]);
+        for (int c = 0; c < HALF_N / 16; ++c) ptx::tmem_ld_32x32b_x16(t_addr + (uint32_t)(c * 16), r[c]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < HALF_N / 16; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<uint4*>(sp + c * 16 + i) = make_uint4(r[c][i], r[c][i + 1], r[c][i + 2], r[c][i + 3]);
+      }
+      if (PERSIST) {   // this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // Phase 2: bias (+ activation, aux) + stores, row-contiguous.
+      const bool full_tile = (m0 + TC_BM <= M) && (n0 + BN <= N);
+      if (plain && full_tile) {
+        // fast path (every large GEMM of the step): 8 columns per thread, no bounds checks, no activation
+        if (ep.c_bf16) {
+          uint16_t* cbase = reinterpret_cast<uint16_t*>(ep.C) + (int64_t)m0 * ep.ldc + n0;
+#pragma unroll 4
+          for (int item = tid; item < TC_BM * G8_PER_ROW; item += TC_EPI_THREADS) {
+            const int rl = item / G8_PER_ROW, c8 = (item % G8_PER_ROW) * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(stage + rl * LD + c8);
+            const float4 a1 = *reinterpret_cast<const float4*>(stage + rl * LD + c8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c8 + 4);
+            uint4 pk;
+            pk.x = pack_bf16x2(a0.x + b0.x, a0.y + b0.y);
+            pk.y = pack_bf16x2(a0.z + b0.z, a0.w + b0.w);
+            pk.z = pack_bf16x2(a1.x + b1.x, a1.y + b1.y);
+            pk.w = pack_bf16x2(a1.z + b1.z, a1.w + b1.w);
+            *reinterpret_cast<uint4*>(cbase + (int64_t)rl * ep.ldc + c8) = pk;
+          }
+        } else {
+          float* cbase = reinterpret_cast<float*>(ep.C) + (int64_t)m0 * ep.ldc + n0;
+          const bool accum = ep.accumulate != 0;
+#pragma unroll 4
+          for (int item = tid; item < TC_BM * F4_PER_ROW; item += TC_EPI_THREADS) {
+            const int rl = item / F4_PER_ROW, c4 = (item % F4_PER_ROW) * 4;
+            float4 w = *reinterpret_cast<const float4*>(stage + rl * LD + c4);
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + c4);
+            float* cp = cbase + (int64_t)rl * ep.ldc + c4;
+            w.x += bv.x; w.y += bv.y; w.z += bv.z; w.w += bv.w;
+            if (accum) {
+              const float4 old = *reinterpret_cast<const float4*>(cp);
+              w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+            }
+            *reinterpret_cast<float4*>(cp) = w;
+          }
         }
       } else {
-        float* cp = reinterpret_cast<float*>(ep.C) + o;
-        if (vec_ok && col + 4 <= N) {
-          float4 x = w;
-          if (ep.accumulate) {
-            const float4 old = *reinterpret_cast<const float4*>(cp);
-            x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
-          }
-          *reinterpret_cast<float4*>(cp) = x;
-        } else {
-          const float e[4] = {w.x, w.y, w.z, w.w};
+        // general path: edge tiles, activations, pre-activation output
+#pragma unroll 1
+        for (int item = tid; item < TC_BM * F4_PER_ROW; item += TC_EPI_THREADS) {
+          const int rl = item / F4_PER_ROW, c4 = item % F4_PER_ROW;
+          const int64_t grow = (int64_t)m0 + rl;
+          const int col = n0 + c4 * 4;
+          if (grow >= M || col >= N) continue;
+          float4 w = *reinterpret_cast<const float4*>(stage + rl * LD + c4 * 4);
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + c4 * 4);
+          w.x += bv.x; w.y += bv.y; w.z += bv.z; w.w += bv.w;
+          const int64_t o = grow * ep.ldc + col;
+          const bool v4 = vec_ok && col + 4 <= N;
+          if (ep.aux) {   // pre-activation, needed by the backward pass
+            if (v4) {
+              *reinterpret_cast<float4*>(ep.aux + o) = w;
+            } else {
+              const float e[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (col + i < N) cp[i] = ep.accumulate ? cp[i] + e[i] : e[i];
+              for (int i = 0; i < 4; ++i)
+                if (col + i < N) ep.aux[o + i] = e[i];
+            }
+          }
+          if (ep.epilogue != ARK_EPI_NONE) {
+            w.x = apply_act(w.x, ep.epilogue); w.y = apply_act(w.y, ep.epilogue);
+            w.z = apply_act(w.z, ep.epilogue); w.w = apply_act(w.w, ep.epilogue);
+          }
+          if (ep.c_bf16) {
+            uint16_t* cp = reinterpret_cast<uint16_t*>(ep.C) + o;
+            if (v4) {
+              uint2 pk;
+              pk.x = pack_bf16x2(w.x, w.y);
+              pk.y = pack_bf16x2(w.z, w.w);
+              *reinterpret_cast<uint2*>(cp) = pk;
+            } else {
+              const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (col + i < N) cp[i] = f32_to_bf16_bits(e[i]);
+            }
+          } else {
+            float* cp = reinterpret_cast<float*>(ep.C) + o;
+            if (v4) {
+              float4 x = w;
+              if (ep.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(cp);
+                x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
+              }
+              *reinterpret_cast<float4*>(cp) = x;
+            } else {
+              const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (col + i < N) cp[i] = ep.accumulate ? cp[i] + e[i] : e[i];
+            }
+          }
         }
       }
+      if (PERSIST) asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile free for the next drain
     }
   }
   ptx::tc_fence_before();
@@ -216,33 +314,34 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, bool PERSIST>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, int M, int N, int K,
                      int a_row0, int b_row0, cudaStream_t s) {
-  using L = TcSmem<BN, STAGES>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+  using L = TcSmem<BN, STAGES, PERSIST>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, PERSIST>;
   static bool attr_done = false;  // benign race: idempotent
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return fail((int)e, "gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  const unsigned nt = (unsigned)((N + BN - 1) / BN), mt = (unsigned)((M + TC_BM - 1) / TC_BM);
+  const int64_t nt = (N + BN - 1) / BN, mt = (M + TC_BM - 1) / TC_BM;
   EpiParams ep2 = ep;
-  ep2.swap_raster = (M < N && nt <= 65535u) ? 1 : 0;
-  dim3 grid(ep2.swap_raster ? mt : nt, ep2.swap_raster ? nt : mt);
-  kern<<<grid, 192, L::TOTAL, s>>>(tmA, tmB, ep2, M, N, K, a_row0, b_row0);
+  ep2.swap_raster = (M < N) ? 1 : 0;
+  const int64_t tiles = nt * mt;
+  const unsigned grid = (unsigned)(PERSIST ? (tiles < kNumSMs ? tiles : kNumSMs) : tiles);
+  kern<<<grid, TC_THREADS, L::TOTAL, s>>>(tmA, tmB, ep2, M, N, K, a_row0, b_row0);
   return launched("gemm_bf16_tc");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PERSIST>
 static int dispatch_major(int a_major, int b_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
                           const EpiParams& ep, int M, int N, int K, int a_row0, int b_row0, cudaStream_t s) {
   if (a_major == ARK_MAJOR_K && b_major == ARK_MAJOR_K)
-    return launch_tc<BN, false, false, STAGES>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
-  if (a_major == ARK_MAJOR_K) return launch_tc<BN, false, true, STAGES>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
-  if (b_major == ARK_MAJOR_K) return launch_tc<BN, true, false, STAGES>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
-  return launch_tc<BN, true, true, STAGES>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
+    return launch_tc<BN, false, false, STAGES, PERSIST>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
+  if (a_major == ARK_MAJOR_K) return launch_tc<BN, false, true, STAGES, PERSIST>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
+  if (b_major == ARK_MAJOR_K) return launch_tc<BN, true, false, STAGES, PERSIST>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
+  return launch_tc<BN, true, true, STAGES, PERSIST>(tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
 }
 
 int tc_pick_bn(int64_t M, int64_t N) {
@@ -259,8 +358,13 @@ int tc_make_operand_map(CUtensorMap* tm, const uint16_t* P, int major, int64_t r
 
 int tc_enqueue(const CUtensorMap& tmA, const CUtensorMap& tmB, int a_major, int b_major, int BN, const EpiParams& ep,
                int M, int N, int K, int a_row0, int b_row0, cudaStream_t s) {
-  if (BN == 128) return dispatch_major<128, 3>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
-  return dispatch_major<64, 4>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
+  if (BN == 128) {
+    // enough tiles to keep every SM busy for >= 2 rounds: persistent CTAs with a double-buffered accumulator
+    const int64_t tiles = (int64_t)((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
+    if (tiles >= 2 * kNumSMs) return dispatch_major<128, 4, true>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
+    return dispatch_major<128, 3, false>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
+  }
+  return dispatch_major<64, 4, false>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
 }
 
 int tc_check_operands(const char* who, const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb,
