@@ -352,7 +352,8 @@ class SailEngine:
         """Same as train_step, but the ~190 launches of the step are captured ONCE per batch layout
         (B, T, per-step row counts, normalisers, beta) into a CUDA graph and replayed: the host cost of a step
         drops to a few small input copies + one graph launch.  Layouts that never repeat (ragged real data)
-        should use train_step.  Not used under data parallelism (the NCCL side stream stays eager)."""
+        should use train_step.  NOT used under data parallelism: capturing the side-stream NCCL all-reduces
+        next to the cooperative GRU kernels hung at 2 ranks (round-1 finding), so DP steps stay eager."""
         if self.world > 1:
             return self.train_step(triples, seq, lay, eps, beta, lr, n_tok_global, batch_global)
         key = (tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(), float(beta), n_tok_global, batch_global)
@@ -375,6 +376,7 @@ class SailEngine:
                 out = self.forward_backward(st["triples"], st["seq"], st["lay"], st["eps"], beta, n_tok_global,
                                             batch_global, train=True)
                 f = self.flat
+                self._sync_grads()
                 ops.adam_flat_dyn(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.dyn_f, b1, b2, self.eps)
                 self.stats[0:2] += out
                 self.stats[2] += 1
