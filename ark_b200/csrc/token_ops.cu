@@ -8,13 +8,37 @@ namespace ark {
 // grid (L): block t writes rows off[t] .. off[t]+bt[t]
 __global__ void __launch_bounds__(256) pack_tokens_kernel(
     const int64_t* __restrict__ seq, const int32_t* __restrict__ perm, const int32_t* __restrict__ bt,
-    const int32_t* __restrict__ off, int seq_len, int32_t* __restrict__ tok_in, int32_t* __restrict__ tgt) {
+    const int32_t* __restrict__ off, int seq_len, int32_t* __restrict__ tok_in, int32_t* __restrict__ tgt,
+    int32_t* __restrict__ row_t) {
   const int t = blockIdx.x;
   const int n = bt[t], base = off[t];
   for (int b = threadIdx.x; b < n; b += blockDim.x) {
     const int64_t* row = seq + (int64_t)(perm ? perm[b] : b) * seq_len;
     tok_in[base + b] = (int32_t)row[t];
     tgt[base + b] = (int32_t)row[t + 1];
+    if (row_t) row_t[base + b] = t;
+  }
+}
+
+// X[row] = W[tok[row]] + P[pos[row]]  (decoder-only ARK: token + position embedding, models.py:340-342)
+__global__ void __launch_bounds__(256) tok_pos_gather_kernel(
+    const uint16_t* __restrict__ W, const uint16_t* __restrict__ P, const int32_t* __restrict__ tok,
+    const int32_t* __restrict__ pos, int64_t N, int d, uint16_t* __restrict__ Xb) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t sw = (int64_t)tok[row] * d, sp = (int64_t)pos[row] * d;
+  for (int c = lane * 8; c < d; c += 256) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(W + sw + c));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(P + sp + c));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = unpack_bf16x2(aw[k]), y = unpack_bf16x2(bw[k]);
+      o[k] = pack_bf16x2(x.x + y.x, x.y + y.y);
+    }
+    *reinterpret_cast<uint4*>(Xb + row * d + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -69,10 +93,12 @@ __global__ void __launch_bounds__(256) tok_scatter_add_kernel(
 using namespace ark;
 
 extern "C" int ark_pack_tokens(const int64_t* seq, const int32_t* perm, const int32_t* bt, const int32_t* off,
-                               int64_t B, int64_t seq_len, int64_t L, int32_t* tok_in, int32_t* tgt, void* stream) {
+                               int64_t B, int64_t seq_len, int64_t L, int32_t* tok_in, int32_t* tgt, int32_t* row_t,
+                               void* stream) {
   ARK_REQUIRE(seq && bt && off && tok_in && tgt, ARK_E_BADARG, "pack_tokens: null pointer");
   ARK_REQUIRE(B > 0 && L > 0 && L < seq_len, ARK_E_BADARG, "pack_tokens: need 0 < L < seq_len");
-  pack_tokens_kernel<<<(unsigned)L, 256, 0, (cudaStream_t)stream>>>(seq, perm, bt, off, (int)seq_len, tok_in, tgt);
+  pack_tokens_kernel<<<(unsigned)L, 256, 0, (cudaStream_t)stream>>>(seq, perm, bt, off, (int)seq_len, tok_in, tgt,
+                                                                    row_t);
   return launched("pack_tokens");
 }
 
@@ -92,6 +118,16 @@ extern "C" int ark_tok_gather_fwd(const void* W, int w_dtype, const int32_t* tok
   else
     return fail(ARK_E_BADARG, "tok_gather_fwd: unknown dtype %d", w_dtype);
   return launched("tok_gather_fwd");
+}
+
+extern "C" int ark_tok_pos_gather_fwd(const uint16_t* W, const uint16_t* P, const int32_t* tok, const int32_t* pos,
+                                      int64_t N, int64_t d, uint16_t* X_bf16, void* stream) {
+  ARK_REQUIRE(W && P && tok && pos && X_bf16, ARK_E_BADARG, "tok_pos_gather_fwd: null pointer");
+  ARK_REQUIRE(N >= 0 && d > 0 && d % 8 == 0, ARK_E_SHAPE, "tok_pos_gather_fwd: d must be a positive multiple of 8");
+  ARK_REQUIRE(aligned16(W) && aligned16(P) && aligned16(X_bf16), ARK_E_ALIGN, "tok_pos_gather_fwd: 16-byte alignment");
+  if (N == 0) return 0;
+  tok_pos_gather_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(W, P, tok, pos, N, (int)d, X_bf16);
+  return launched("tok_pos_gather_fwd");
 }
 
 extern "C" int ark_tok_scatter_add(const float* dX, const int32_t* tok, int64_t N, int64_t d, int64_t V, float* dW,

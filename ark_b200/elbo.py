@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .flat import FlatParams, sail_param_order
+from .flat import FlatParams, ark_param_order, sail_param_order
 from .layout import PackedLayout, pack_layout
 
 K, MN = ops.MAJOR_K, ops.MAJOR_MN
@@ -42,21 +42,23 @@ class SailEngine:
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gemm_backend="tc", dist_group=None,
                  bucket_mb=32.0, seed=0):
         cfg = model.config
-        if cfg["model_type"] != "SAIL":
-            raise NotImplementedError("SailEngine accelerates model_type 'SAIL' (MLP encoder + GRU decoder)")
+        if cfg["model_type"] not in ("SAIL", "ARK"):
+            raise NotImplementedError("SailEngine accelerates model_type 'SAIL' (MLP encoder + GRU decoder) and its "
+                                      "decoder-only sibling 'ARK'")
+        self.has_enc = cfg["model_type"] == "SAIL"
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("SailEngine needs the model on a CUDA device: there is no CPU path")
         self.model, self.cfg, self.device = model, cfg, dev
         self.d, self.dz, self.V = cfg["d_model"], cfg["d_latent"], cfg["vocab_size"]
         self.nl = model.dec.gru.num_layers
-        self.n_mlp = len([m for m in model.enc.mlp if isinstance(m, torch.nn.Linear)])
+        self.n_mlp = len([m for m in model.enc.mlp if isinstance(m, torch.nn.Linear)]) if self.has_enc else 0
         self.pad_rid, self.pad_eid = cfg.get("pad_rid"), cfg.get("pad_eid")
         self.tied = model.dec.out.weight is model.dec.tok_emb.weight
         self.p_drop = float(cfg.get("dec_dropout", 0.1)) if self.nl > 1 else 0.0
         if self.d % 8:
             raise ValueError("d_model must be a multiple of 8")
-        self.flat = FlatParams(sail_param_order(model), dev)
+        self.flat = FlatParams(sail_param_order(model) if self.has_enc else ark_param_order(model), dev)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.step_count = 0
         self.backend = gemm_backend
@@ -131,7 +133,7 @@ class SailEngine:
         (overwritten, never accumulated).  Returns a device tensor [ce, kl] (already globally normalised when
         the *_global normalisers are given; the caller sums them over ranks)."""
         f, dev, d, dz, V, ldv, nl = self.flat, self.device, self.d, self.dz, self.V, self.ldv, self.nl
-        B = triples.shape[0]
+        B = seq.shape[0]
         N, L = lay.n_tok, lay.L
         d3 = 3 * d
         bf, f32 = torch.bfloat16, torch.float32
@@ -143,32 +145,39 @@ class SailEngine:
         new = lambda *s, dtype=f32: torch.empty(*s, device=dev, dtype=dtype)  # noqa: E731
 
         # ---------------- encoder forward (models.py:46-64)
-        g_b, inv_cnt = new(B, d3, dtype=bf), new(B)
-        with self._timed("gather_pool_fwd", nbytes=3.0 * lay.n_triples * d * 4 + 3.0 * lay.n_triples * 8 + B * d3 * 2):
-            ops.gather_pool_fwd(triples, lay.perm_dev, f.p("enc.e_emb.weight"), f.p("enc.r_emb.weight"), self.pad_rid,
-                                None, g_b, inv_cnt)
-        acts, pres = [g_b], []
-        for k in range(self.n_mlp):
-            a_next, pre = new(B, d3, dtype=bf), new(B, d3)
-            self._gemm(acts[-1], K, self._w(f"enc.mlp.{2 * k}.weight"), K, a_next, B, d3, d3, tag="enc_mlp",
-                       bias=f.p(f"enc.mlp.{2 * k}.bias"), epilogue=ops.EPI_GELU, aux=pre)
-            acts.append(a_next)
-            pres.append(pre)
-        w_heads = f.fused(f.shadow, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
-        b_heads = f.fused(f.param, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
-        heads = new(B, 2 * dz)
-        self._gemm(acts[-1], K, w_heads, K, heads, B, 2 * dz, d3, tag="enc_heads", bias=b_heads)
-        z, z_b = new(B, dz), new(B, dz, dtype=bf)
-        ops.reparam_kl_fwd(heads, eps, lay.perm_dev, dz, True, 1.0 / (b_g * dz), z, z_b, out[1:2])
-        h0 = new(B, d)
-        self._gemm(z_b, K, self._w("dec.z_proj.weight"), K, h0, B, d, dz, tag="z_proj", bias=f.p("dec.z_proj.bias"),
-                   epilogue=ops.EPI_TANH)
+        if self.has_enc:
+            g_b, inv_cnt = new(B, d3, dtype=bf), new(B)
+            with self._timed("gather_pool_fwd", nbytes=3.0 * lay.n_triples * d * 4 + 3.0 * lay.n_triples * 8 + B * d3 * 2):
+                ops.gather_pool_fwd(triples, lay.perm_dev, f.p("enc.e_emb.weight"), f.p("enc.r_emb.weight"), self.pad_rid,
+                                    None, g_b, inv_cnt)
+            acts, pres = [g_b], []
+            for k in range(self.n_mlp):
+                a_next, pre = new(B, d3, dtype=bf), new(B, d3)
+                self._gemm(acts[-1], K, self._w(f"enc.mlp.{2 * k}.weight"), K, a_next, B, d3, d3, tag="enc_mlp",
+                           bias=f.p(f"enc.mlp.{2 * k}.bias"), epilogue=ops.EPI_GELU, aux=pre)
+                acts.append(a_next)
+                pres.append(pre)
+            w_heads = f.fused(f.shadow, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
+            b_heads = f.fused(f.param, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
+            heads = new(B, 2 * dz)
+            self._gemm(acts[-1], K, w_heads, K, heads, B, 2 * dz, d3, tag="enc_heads", bias=b_heads)
+            z, z_b = new(B, dz), new(B, dz, dtype=bf)
+            ops.reparam_kl_fwd(heads, eps, lay.perm_dev, dz, True, 1.0 / (b_g * dz), z, z_b, out[1:2])
+            h0 = new(B, d)
+            self._gemm(z_b, K, self._w("dec.z_proj.weight"), K, h0, B, d, dz, tag="z_proj", bias=f.p("dec.z_proj.bias"),
+                       epilogue=ops.EPI_TANH)
+        else:
+            h0 = torch.zeros(B, d, device=dev)          # decoder-only ARK: nn.GRU's default initial state
 
         # ---------------- decoder forward (models.py:136-142) over packed rows
         tok, tgt = new(N, dtype=torch.int32), new(N, dtype=torch.int32)
-        ops.pack_tokens(seq, lay.perm_dev, lay.bt_dev, lay.off_dev, L, tok, tgt)
+        row_t = None if self.has_enc else new(N, dtype=torch.int32)
+        ops.pack_tokens(seq, lay.perm_dev, lay.bt_dev, lay.off_dev, L, tok, tgt, row_t)
         x_b = new(N, d, dtype=bf)
-        ops.tok_gather_fwd(self._w("dec.tok_emb.weight"), tok, None, x_b)
+        if self.has_enc:
+            ops.tok_gather_fwd(self._w("dec.tok_emb.weight"), tok, None, x_b)
+        else:   # token + position embedding (reference models.py:340-342)
+            ops.tok_pos_gather_fwd(self._w("dec.tok_emb.weight"), self._w("dec.pos_emb.weight"), tok, row_t, x_b)
         b0 = int(lay.bt[0])
         saved = []
         u_b = x_b
@@ -261,6 +270,13 @@ class SailEngine:
         with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
             ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
         self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+
+        if not self.has_enc:
+            g_pos = f.g("dec.pos_emb.weight")
+            g_pos.zero_()
+            ops.tok_scatter_add(dy, row_t, g_pos)      # d pos_emb[t] = sum of dX over the rows of step t
+            self._grad_ready("dec.pos_emb.weight", "dec.pos_emb.weight")
+            return out
 
         # ---------------- h0 = tanh(W_z z + b_z), reparameterisation, KL
         dpre, dpre_b = new(B, d), new(B, d, dtype=bf)
@@ -356,7 +372,8 @@ class SailEngine:
         next to the cooperative GRU kernels hung at 2 ranks (round-1 finding), so DP steps stay eager."""
         if self.world > 1:
             return self.train_step(triples, seq, lay, eps, beta, lr, n_tok_global, batch_global)
-        key = (tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(), float(beta), n_tok_global, batch_global)
+        key = (None if triples is None else tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(), float(beta),
+               n_tok_global, batch_global)
         ent = self._graphs.get(key)
         self.step_count += 1
         lr = self.lr if lr is None else float(lr)
@@ -367,7 +384,8 @@ class SailEngine:
         self.dyn_i.copy_(torch.tensor([self.philox_offset], dtype=torch.int64))
         if ent is None:
             dev = self.device
-            st = {"triples": triples.to(dev, copy=True), "seq": seq.to(dev, copy=True), "eps": eps.to(dev, copy=True),
+            st = {"triples": None if triples is None else triples.to(dev, copy=True), "seq": seq.to(dev, copy=True),
+                  "eps": None if eps is None else eps.to(dev, copy=True),
                   "lay": PackedLayout(perm=lay.perm, lens=lay.lens, bt=lay.bt, off=lay.off, n_tok=lay.n_tok,
                                       n_triples=lay.n_triples, L=lay.L, perm_dev=lay.perm_dev.clone(),
                                       bt_dev=lay.bt_dev.clone(), off_dev=lay.off_dev.clone())}
@@ -397,9 +415,10 @@ class SailEngine:
             st["n_launch"] = _C.lib().launch_count() - n0
             self._graphs[key] = ent = st
         else:
-            ent["triples"].copy_(triples, non_blocking=True)
+            if triples is not None:
+                ent["triples"].copy_(triples, non_blocking=True)
+                ent["eps"].copy_(eps, non_blocking=True)
             ent["seq"].copy_(seq, non_blocking=True)
-            ent["eps"].copy_(eps, non_blocking=True)
             ent["lay"].perm_dev.copy_(lay.perm_dev, non_blocking=True)
         ent["graph"].replay()
         self.launches_replayed += ent["n_launch"]

@@ -45,6 +45,24 @@ def sail_param_order(model):
     return groups
 
 
+def ark_param_order(model):
+    """Gradient-readiness order for the decoder-only ARK model (reference models.py:323-405)."""
+    named = dict(model.named_parameters())
+    nl = model.dec.gru.num_layers
+    groups = [[("dec.out.bias", named["dec.out.bias"])]]
+    if "dec.out.weight" in named:
+        groups.append([("dec.out.weight", named["dec.out.weight"])])
+    for k in range(nl - 1, -1, -1):
+        for nm in (f"weight_ih_l{k}", f"weight_hh_l{k}", f"bias_ih_l{k}", f"bias_hh_l{k}"):
+            groups.append([(f"dec.gru.{nm}", named[f"dec.gru.{nm}"])])
+    groups.append([("dec.tok_emb.weight", named["dec.tok_emb.weight"])])
+    groups.append([("dec.pos_emb.weight", named["dec.pos_emb.weight"])])
+    missing = set(named) - {n for g in groups for n, _ in g}
+    if missing:
+        raise RuntimeError(f"parameters without a slot in the flat layout: {sorted(missing)}")
+    return groups
+
+
 class FlatParams:
     def __init__(self, groups, device):
         self.slots = {}  # name -> (offset, numel, shape)

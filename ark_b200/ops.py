@@ -62,11 +62,18 @@ def gather_pool_bwd(dg, triples, perm, inv_cnt, pad_rid, pad_eid, dE, dR):
                   -1 if pad_eid is None else int(pad_eid), _ptr(dE, torch.float32), _ptr(dR, torch.float32), _stream())
 
 
-def pack_tokens(seq, perm, bt, off, L, tok_in, tgt):
+def pack_tokens(seq, perm, bt, off, L, tok_in, tgt, row_t=None):
     B, seq_len = seq.shape
-    _contig(seq, perm, bt, off, tok_in, tgt)
+    _contig(seq, perm, bt, off, tok_in, tgt, row_t)
     _C.lib().call("ark_pack_tokens", _ptr(seq, torch.int64), _ptr(perm, torch.int32), _ptr(bt, torch.int32),
-                  _ptr(off, torch.int32), B, seq_len, L, _ptr(tok_in, torch.int32), _ptr(tgt, torch.int32), _stream())
+                  _ptr(off, torch.int32), B, seq_len, L, _ptr(tok_in, torch.int32), _ptr(tgt, torch.int32),
+                  _ptr(row_t, torch.int32), _stream())
+
+
+def tok_pos_gather_fwd(W, P, tok, pos, X_bf16):
+    _contig(W, P, tok, pos, X_bf16)
+    _C.lib().call("ark_tok_pos_gather_fwd", _ptr(W, torch.bfloat16), _ptr(P, torch.bfloat16), _ptr(tok, torch.int32),
+                  _ptr(pos, torch.int32), tok.numel(), W.shape[1], _ptr(X_bf16, torch.bfloat16), _stream())
 
 
 def tok_gather_fwd(W, tok, X_f32=None, X_bf16=None):

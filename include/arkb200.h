@@ -68,14 +68,18 @@ int ark_gather_pool_bwd(const float* dg, const int64_t* triples, const int32_t* 
 
 /* ---- a1: packed token ids (utils.py:102-108 layout; PAD-skip) ----
  * seq int64 [B, seq_len]; for t in [0,L), b in [0,bt[t]): row = off[t]+b,
- * tok_in[row] = seq[perm[b], t], tgt[row] = seq[perm[b], t+1]. */
+ * tok_in[row] = seq[perm[b], t], tgt[row] = seq[perm[b], t+1]; row_t[row] = t (optional, may be NULL). */
 int ark_pack_tokens(const int64_t* seq, const int32_t* perm, const int32_t* bt, const int32_t* off,
-                    int64_t B, int64_t seq_len, int64_t L, int32_t* tok_in, int32_t* tgt, void* stream);
+                    int64_t B, int64_t seq_len, int64_t L, int32_t* tok_in, int32_t* tgt, int32_t* row_t,
+                    void* stream);
 
 /* ---- K5: token-embedding gather (models.py:138) and scatter-add backward ----
  * W is f32 or bf16 [V,d] (w_dtype); X f32 and/or bf16 [N,d] (either may be NULL). d % 8 == 0. */
 int ark_tok_gather_fwd(const void* W, int w_dtype, const int32_t* tok, int64_t N, int64_t d, int64_t V,
                        float* X_f32, uint16_t* X_bf16, void* stream);
+/* Decoder-only ARK input: X[i] = W[tok[i]] + P[pos[i]] in bf16 (tok_emb + pos_emb, models.py:340-342). */
+int ark_tok_pos_gather_fwd(const uint16_t* W, const uint16_t* P, const int32_t* tok, const int32_t* pos,
+                           int64_t N, int64_t d, uint16_t* X_bf16, void* stream);
 /* dW[tok[i], :] += dX[i, :]  (red.global.add.v4.f32); dW is NOT zeroed here (tied weight: it already
  * holds dLogits^T Y, models.py:130-132). */
 int ark_tok_scatter_add(const float* dX, const int32_t* tok, int64_t N, int64_t d, int64_t V,

@@ -28,7 +28,7 @@ import yaml
 from ark_b200.layout import pack_layout
 from ark_b200.optim import FusedAdam
 from ark_b200.synthetic import DATASET_SHAPES
-from kgvae.model.models import SAIL
+from kgvae.model.models import ARK, SAIL
 from kgvae.model.utils import GraphSeqDataset, build_batch, canonical_graph_string, ints_to_labels, seq_to_triples
 
 SPECIAL = {"PAD": 0, "BOS": 1, "EOS": 2}
@@ -140,8 +140,9 @@ class BatchLoader:
 def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None):
     """One epoch of ELBO steps (reference: ablation_study.py:31-88, SAIL branch :59-81).
     Returns (avg_loss, avg_recon, avg_kl, avg_entity_loss) like the reference."""
-    if config.get("model_type", "ARK") not in ("SAIL",):
-        raise NotImplementedError("only model_type 'SAIL' runs on the fused path (see DESIGN.md)")
+    mt = config.get("model_type", "ARK")
+    if mt not in ("SAIL", "ARK"):
+        raise NotImplementedError("model_type 'SAIL' and 'ARK' run on the fused path (see DESIGN.md)")
     model.train()
     eng = model.engine()
     eng.stats.zero_()
@@ -150,8 +151,11 @@ def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None
         ntg = batch[2] if len(batch) > 2 else None
         bg = batch[3] if len(batch) > 3 else None
         optimizer.zero_grad()
-        model.elbo_backward(triples, seq, b, eps=None if eps_fn is None else eps_fn(i), n_tok_global=ntg,
-                            batch_global=bg)
+        if mt == "ARK":       # decoder-only: loss = CE, KL = 0 (reference train.py:42-58)
+            model.ce_backward(seq, n_tok_global=ntg)
+        else:
+            model.elbo_backward(triples, seq, b, eps=None if eps_fn is None else eps_fn(i), n_tok_global=ntg,
+                                batch_global=bg)
         optimizer.step()
     loss, ce, kl = eng.read_stats(b)            # one device->host read for the whole epoch
     return loss, ce, kl, 0.0
@@ -166,7 +170,7 @@ def validate(model, dataloader, config, device, b=1.0):
     for batch in dataloader:
         triples, seq = batch[0].to(eng.device), batch[1].to(eng.device)
         lay = pack_layout(batch[1]).to(eng.device)
-        eps = torch.randn(triples.shape[0], config["d_latent"], device=eng.device)
+        eps = torch.randn(triples.shape[0], config["d_latent"], device=eng.device) if eng.has_enc else None
         acc += eng.eval_step(triples.contiguous(), seq.contiguous(), lay, eps, b)
         n += 1
     ce, kl = (acc / max(n, 1)).tolist()
@@ -213,10 +217,10 @@ def main(argv=None):
                       UserWarning, stacklevel=2)
 
     model_type = config.get("model_type", "ARK")
-    if model_type != "SAIL":
+    if model_type not in ("SAIL", "ARK"):
         raise NotImplementedError(
-            f"model_type '{model_type}': this build accelerates the KG-VAE ELBO path (model_type: SAIL). "
-            "ARK / t-ARK / t-SAIL are the next rows of the scope table (DESIGN.md).")
+            f"model_type '{model_type}': this build accelerates the GRU models (SAIL: the KG-VAE ELBO path; ARK: its "
+            "decoder-only sibling).  t-ARK / t-SAIL are the next rows of the scope table (DESIGN.md).")
 
     train_g, val_g, test_g, (e2i, i2e), (r2i, i2r), (min_edges, max_edges) = load_graphs(config)
     n_ent, n_rel = len(e2i), len(r2i)
@@ -242,7 +246,7 @@ def main(argv=None):
         print(f"Train batches: {len(train_loader)}, Val batches: {len(val_loader)}  world={world}")
 
     torch.manual_seed(0)
-    model = SAIL(config).to(device)
+    model = (SAIL if model_type == "SAIL" else ARK)(config).to(device)
     optimizer = FusedAdam(model, lr=config["learning_rate"], dist_group=group,
                           bucket_mb=float(config.get("ddp_bucket_mb", 32)))
     scheduler = None

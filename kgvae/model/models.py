@@ -90,6 +90,28 @@ class AutoRegEncoderMLP(nn.Module):
         return z, mu, logv
 
 
+def _gru_stack_f32(gru, x, h0, B, Lp):
+    """fp32 multi-layer GRU over time-major rows (t, b) on the library's kernels (eval semantics)."""
+    dev = x.device
+    d = x.shape[1]
+    N = B * Lp
+    bt = np.full(Lp, B, dtype=np.int32)
+    off = (np.arange(Lp + 1, dtype=np.int32) * B).astype(np.int32)
+    gh_ws = torch.empty(B, 3 * d, device=dev)
+    u = x
+    for k in range(gru.num_layers):
+        w_ih, w_hh = getattr(gru, f"weight_ih_l{k}").detach(), getattr(gru, f"weight_hh_l{k}").detach()
+        b_ih, b_hh = getattr(gru, f"bias_ih_l{k}").detach(), getattr(gru, f"bias_hh_l{k}").detach()
+        gi = torch.empty(N, 3 * d, device=dev)
+        ops.gemm(u, K, w_ih, K, gi, N, 3 * d, d, bias=b_ih, backend="simt")
+        hp = torch.empty(N, d, device=dev)
+        hp[:B].copy_(h0)
+        y = torch.empty(N, d, device=dev)
+        ops.gru_layer_fwd(None, hp, w_hh, gi, b_hh, bt, off, Lp, d, y, None, None, gh_ws, 0)
+        u = y
+    return u
+
+
 class AutoRegDecoderGRU(nn.Module):
     """Token embedding + h0 = tanh(z_proj z) + n-layer GRU + tied vocabulary projection
     (reference: models.py:116-142)."""
@@ -111,32 +133,38 @@ class AutoRegDecoderGRU(nn.Module):
         if self.training and self.gru.dropout > 0:
             raise RuntimeError("dec() is the fp32 inference path; train with SAIL.elbo_step (dropout lives there)")
         B, Lp = tgt.shape
-        dev = tgt.device
         d = self.tok_emb.weight.shape[1]
-        N = B * Lp
-        bt = np.full(Lp, B, dtype=np.int32)
-        off = (np.arange(Lp + 1, dtype=np.int32) * B).astype(np.int32)
         tok = tgt.t().contiguous().view(-1).to(torch.int32)           # time-major rows (t, b)
-        x = torch.empty(N, d, device=dev)
+        x = torch.empty(B * Lp, d, device=tgt.device)
         ops.tok_gather_fwd(self.tok_emb.weight.detach(), tok, x, None)
         h0 = _linear_f32(z.to(torch.float32).contiguous(), self.z_proj, ops.EPI_TANH)
-        gh_ws = torch.empty(B, 3 * d, device=dev)
-        u = x
-        for k in range(self.gru.num_layers):
-            w_ih, w_hh = getattr(self.gru, f"weight_ih_l{k}").detach(), getattr(self.gru, f"weight_hh_l{k}").detach()
-            b_ih, b_hh = getattr(self.gru, f"bias_ih_l{k}").detach(), getattr(self.gru, f"bias_hh_l{k}").detach()
-            gi = torch.empty(N, 3 * d, device=dev)
-            ops.gemm(u, K, w_ih, K, gi, N, 3 * d, d, bias=b_ih, backend="simt")
-            hp = torch.empty(N, d, device=dev)
-            hp[:B].copy_(h0)
-            y = torch.empty(N, d, device=dev)
-            ops.gru_layer_fwd(None, hp, w_hh, gi, b_hh, bt, off, Lp, d, y, None, None, gh_ws, 0)
-            u = y
+        u = _gru_stack_f32(self.gru, x, h0, B, Lp)
         logits = _linear_f32(u, self.out)
         return logits.view(Lp, B, -1).transpose(0, 1).contiguous()
 
 
-class SAIL(nn.Module):
+class _EngineMixin:
+    """Plumbing between an nn.Module with the reference's parameters and its fused ark_b200 training engine."""
+
+    def _init_engine_slot(self):
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._weights_changed())
+
+    def _attach_engine(self, engine):
+        object.__setattr__(self, "_engine", engine)
+
+    def _weights_changed(self):
+        if self._engine is not None:
+            self._engine.refresh_shadow()
+
+    def engine(self, **kw) -> SailEngine:
+        """The fused training engine bound to this module (created on first use; the module must be on CUDA)."""
+        if self._engine is None:
+            SailEngine(self, **kw)          # attaches itself
+        return self._engine
+
+
+class SAIL(_EngineMixin, nn.Module):
     """The KG-VAE.  Reference: models.py:144-320."""
 
     def __init__(self, config):
@@ -158,22 +186,7 @@ class SAIL(nn.Module):
                 "SURVEY.md §8 priority 2.  Use model_type 'SAIL'.")
         else:
             raise NotImplementedError(f"Unknown model_type: {mt}")
-        self._engine = None
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module._weights_changed())
-
-    # ---- engine plumbing -------------------------------------------------------------------------
-    def _attach_engine(self, engine):
-        object.__setattr__(self, "_engine", engine)
-
-    def _weights_changed(self):
-        if self._engine is not None:
-            self._engine.refresh_shadow()
-
-    def engine(self, **kw) -> SailEngine:
-        """The fused training engine bound to this module (created on first use; the module must be on CUDA)."""
-        if self._engine is None:
-            SailEngine(self, **kw)          # attaches itself
-        return self._engine
+        self._init_engine_slot()
 
     def elbo_backward(self, triples, seq, beta, eps=None, layout: PackedLayout = None,
                       n_tok_global=None, batch_global=None):
@@ -292,3 +305,128 @@ class SAIL(nn.Module):
             if len(graphs) >= num_generated_test_graphs:
                 return graphs[:num_generated_test_graphs]
         return graphs
+
+
+class DecoderOnlyGRU(nn.Module):
+    """tok_emb + pos_emb -> n-layer GRU (h0 = 0) -> tied vocabulary projection (reference: models.py:323-346)."""
+
+    def __init__(self, d_model, num_layers, seq_len, vocab_size, dropout=0.1, tie_weights=True):
+        super().__init__()
+        self.tok_emb = nn.Embedding(vocab_size, d_model)
+        self.pos_emb = nn.Embedding(seq_len, d_model)
+        self.gru = nn.GRU(input_size=d_model, hidden_size=d_model, num_layers=num_layers, batch_first=True,
+                          dropout=dropout if num_layers > 1 else 0.0)
+        self.out = nn.Linear(d_model, vocab_size)
+        if tie_weights and self.out.weight.shape == self.tok_emb.weight.shape:
+            self.out.weight = self.tok_emb.weight
+
+    @torch.no_grad()
+    def forward(self, seq_in):
+        _need_cuda(seq_in, "dec")
+        if self.training and self.gru.dropout > 0:
+            raise RuntimeError("dec() is the fp32 inference path; train with ARK.ce_backward (dropout lives there)")
+        B, Lp = seq_in.shape
+        d = self.tok_emb.weight.shape[1]
+        tok = seq_in.t().contiguous().view(-1).to(torch.int32)
+        x = torch.empty(B * Lp, d, device=seq_in.device)
+        ops.tok_gather_fwd(self.tok_emb.weight.detach(), tok, x, None)
+        x = (x.view(Lp, B, d) + self.pos_emb.weight.detach()[:Lp, None, :]).view(B * Lp, d).contiguous()
+        u = _gru_stack_f32(self.gru, x, torch.zeros(B, d, device=seq_in.device), B, Lp)
+        logits = _linear_f32(u, self.out)
+        return logits.view(Lp, B, -1).transpose(0, 1).contiguous()
+
+
+class ARK(_EngineMixin, nn.Module):
+    """Decoder-only autoregressive model — the reference's default ``model_type`` (models.py:368-520).
+    Training (``ce_backward`` / ``ce_step``) runs on the same fused engine as SAIL minus the encoder and KL."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        if config["model_type"] == "ARK":
+            self.dec = DecoderOnlyGRU(d_model=config["d_model"], num_layers=config["n_layers"], seq_len=config["seq_len"],
+                                      vocab_size=config["vocab_size"], dropout=config.get("dec_dropout", 0.1),
+                                      tie_weights=config.get("tie_weights", True))
+        elif config["model_type"] == "t-ARK":
+            raise NotImplementedError("model_type 't-ARK' (Transformer decoder, reference models.py:349-366) is not "
+                                      "built yet; use 'ARK' or 'SAIL'")
+        else:
+            raise NotImplementedError(f"Unknown model_type: {config['model_type']}")
+        self._init_engine_slot()
+
+    def forward(self, triples_or_seq, seq_in=None):
+        """forward(seq) or forward(triples, seq) — triples are ignored (reference models.py:395-405)."""
+        return self.dec(triples_or_seq if seq_in is None else seq_in)
+
+    def ce_backward(self, seq, layout: PackedLayout = None, n_tok_global=None):
+        """Fused CE forward + backward over packed rows (reference train step: train.py:42-58)."""
+        eng = self.engine()
+        if layout is None:
+            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+        seq = seq.to(eng.device, non_blocking=True).contiguous()
+        out = eng.forward_backward(None, seq, layout, None, 0.0, n_tok_global, None)
+        eng.stats[0:2] += out
+        eng.stats[2] += 1
+        return out
+
+    def ce_step(self, seq, layout: PackedLayout = None, lr=None, n_tok_global=None):
+        out = self.ce_backward(seq, layout, n_tok_global)
+        self._engine.adam_step(lr)
+        return out
+
+    @torch.no_grad()
+    def generate(self, seq_len, special_tokens, device=None, batch_size=1, beam=1, sample=False, temperature=1.0,
+                 top_p=0.0, top_k=0):
+        """Greedy or sampled generation, full prefix re-decoded per step (reference: models.py:408-471)."""
+        device = device or next(self.parameters()).device
+        eos = special_tokens["EOS"]
+        seq = torch.full((batch_size, 1), special_tokens["BOS"], dtype=torch.long, device=device)
+        for _ in range(seq_len - 1):
+            logits = self.dec(seq)[:, -1]
+            if not sample:
+                nxt = logits.argmax(dim=-1, keepdim=True)
+            else:
+                if temperature and temperature != 1.0:
+                    logits = logits / float(temperature)
+                probs = F.softmax(logits, dim=-1)
+                if top_k and top_k > 0:
+                    _, keep = probs.topk(top_k, dim=-1)
+                    probs = probs * torch.zeros_like(probs).scatter_(-1, keep, 1.0)
+                    probs = probs / probs.sum(dim=-1, keepdim=True).clamp_min(1e-12)
+                if top_p and 0.0 < top_p < 1.0:
+                    sp, si = probs.sort(dim=-1, descending=True)
+                    drop = sp.cumsum(dim=-1) > top_p
+                    drop[..., 1:] = drop[..., :-1].clone()
+                    drop[..., 0] = False
+                    sp = sp.masked_fill(drop, 0.0)
+                    sp = sp / sp.sum(dim=-1, keepdim=True).clamp_min(1e-12)
+                    nxt = si.gather(-1, torch.multinomial(sp, 1))
+                else:
+                    nxt = torch.multinomial(probs, 1)
+            seq = torch.cat([seq, nxt], dim=1)
+            if bool((seq[:, -1] == eos).all()):
+                break
+        if seq.size(1) < seq_len:
+            seq = torch.cat([seq, torch.full((batch_size, seq_len - seq.size(1)), eos, dtype=torch.long, device=device)], 1)
+        return seq[:, :seq_len]
+
+    def bits_per_sequence(self, seq, pad_id=0):
+        """AR bits under teacher forcing (reference: models.py:473-486); one causal pass instead of O(L^2)."""
+        seq = seq.unsqueeze(0)
+        n = int((seq[0, 1:] != pad_id).long().cumprod(0).sum().item())
+        if n == 0:
+            return 0.0
+        logp = F.log_softmax(self(seq[:, :n]), dim=-1)[0]
+        return float(-(logp[torch.arange(n, device=seq.device), seq[0, 1:n + 1]]).sum().item() / math.log(2))
+
+    @torch.no_grad()
+    def posterior_bits(self, dataset, device, pad_id=0, sample_frac=0.1, desc="Posterior compression"):
+        """Reference: models.py:488-520 (decoder-only: KL = 0, total = AR)."""
+        n = max(1, int(sample_frac * len(dataset)))
+        records = []
+        for i in range(n):
+            ar = self.bits_per_sequence(dataset[i][1].to(device), pad_id=pad_id)
+            records.append({"ar_bits": ar, "kl_bits": 0.0, "total_bits": ar})
+        tot = np.array([r["total_bits"] for r in records])
+        return {"avg_total_bits": float(tot.mean()), "avg_ar_bits": float(tot.mean()), "avg_kl_bits": 0.0,
+                "min_total_bits": float(tot.min()), "max_total_bits": float(tot.max()), "records": records}

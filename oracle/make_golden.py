@@ -202,7 +202,57 @@ def train_epoch_golden():
     print(f"[golden] train_epoch: {res[:3]}")
 
 
+def ark_case(name, *, n_ent, n_rel, lo, hi, use_padding, d, nl, B, seed, tie=True):
+    """Decoder-only ARK (models.py:323-405) with the CE-only step of train.py:42-58."""
+    rng = np.random.default_rng(seed)
+    lay = layout_from_reference_rules(n_ent, n_rel, hi, use_padding)
+    graphs = random_graphs(rng, B, n_ent, n_rel, lo, hi)
+    triples, seq = dataset_batch(graphs, lay, use_padding)
+    cfg = dict(lay, model_type="ARK", d_model=d, d_latent=4, n_heads=2, n_layers=nl, dec_dropout=0.0, tie_weights=tie)
+    torch.manual_seed(seed)
+    model = ref_models.ARK(cfg)
+    model.train()
+    logits = model(seq[:, :-1])
+    ce = F.cross_entropy(logits.reshape(-1, logits.size(-1)), seq[:, 1:].reshape(-1), ignore_index=0)
+    ce.backward()
+    arrays = {"triples": triples.numpy(), "seq": seq.numpy(), "logits": logits.detach().numpy(),
+              "ce": np.float64(ce.item())}
+    for k, v in model.state_dict().items():
+        arrays["param::" + k] = v.detach().numpy().copy()
+    for k, p in model.named_parameters():
+        arrays["grad::" + k] = p.grad.detach().numpy().copy()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    losses = []
+    for s in range(2):
+        opt.zero_grad()
+        lg = model(triples, seq[:, :-1])                      # the (triples, seq) call form, models.py:395-405
+        c_ = F.cross_entropy(lg.reshape(-1, lg.size(-1)), seq[:, 1:].reshape(-1), ignore_index=0)
+        c_.backward()
+        opt.step()
+        losses.append(c_.item())
+    arrays["adam_losses"] = np.asarray(losses)
+    for k, v in model.state_dict().items():
+        arrays["adam_param::" + k] = v.detach().numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        gen = model.generate(lay["seq_len"], lay["special_tokens"], batch_size=3, sample=False)   # greedy
+        arrays["greedy"] = gen.numpy()
+        arrays["eval_logits_prefix5"] = model(seq[:2, :5]).numpy()
+    np.savez_compressed(os.path.join(OUT, f"ark_{name}.npz"), **arrays)
+    with open(os.path.join(OUT, f"ark_{name}.json"), "w") as f:
+        json.dump({"cfg": cfg, "adam_lr": 1e-2}, f)
+    print(f"[golden] ark_{name}: ce={ce.item():.6f} V={lay['vocab_size']} L={lay['seq_len'] - 1}")
+
+
+def ark_golden():
+    ark_case("syn", n_ent=11, n_rel=3, lo=3, hi=3, use_padding=False, d=16, nl=3, B=5, seed=11)
+    ark_case("wd", n_ent=23, n_rel=4, lo=1, hi=6, use_padding=True, d=16, nl=2, B=6, seed=12)
+
+
 if __name__ == "__main__":
+    if "--ark-only" in sys.argv:
+        ark_golden()
+        sys.exit(0)
     utils_golden()
     sail_case("syn", n_ent=11, n_rel=3, lo=3, hi=3, use_padding=False, d=16, dz=6, nl=3, B=5, seed=1, beta=0.5)
     sail_case("wd", n_ent=23, n_rel=4, lo=1, hi=6, use_padding=True, d=16, dz=8, nl=2, B=6, seed=2,
@@ -212,3 +262,4 @@ if __name__ == "__main__":
     sail_case("untied", n_ent=9, n_rel=2, lo=2, hi=2, use_padding=False, d=8, dz=4, nl=2, B=3, seed=4,
               beta=0.1, tie=False)
     train_epoch_golden()
+    ark_golden()

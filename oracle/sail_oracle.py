@@ -151,7 +151,7 @@ def encoder_forward(params, triples, eps, pad_rid):
             "logv_raw": logv_raw, "logv": logv, "sigma": sigma, "z": z}
 
 
-def gru_decoder_forward(params, z, seq_in, drop_masks=None, tied=True):
+def gru_decoder_forward(params, z, seq_in, drop_masks=None, tied=True, decoder_only=False):
     """AutoRegDecoderGRU.forward — kgvae/model/models.py:136-142.
 
     GRU equations are torch.nn.GRU's (gate order r,z,n).
@@ -162,8 +162,12 @@ def gru_decoder_forward(params, z, seq_in, drop_masks=None, tied=True):
     B, L = seq_in.shape
     d = Wt.shape[1]
     nl = n_gru_layers(params)
-    x = Wt[seq_in]                                                        # :138
-    h0 = np.tanh(z @ params["dec.z_proj.weight"].T + params["dec.z_proj.bias"])  # :139
+    if decoder_only:   # DecoderOnlyGRU.forward — models.py:340-343: tok_emb + pos_emb, nn.GRU default h0 = 0
+        x = Wt[seq_in] + params["dec.pos_emb.weight"][np.arange(L)][None]
+        h0 = np.zeros((B, d), dtype=Wt.dtype)
+    else:
+        x = Wt[seq_in]                                                    # :138
+        h0 = np.tanh(z @ params["dec.z_proj.weight"].T + params["dec.z_proj.bias"])  # :139
     layers = []
     u = x
     for k in range(nl):                                                   # :141
@@ -219,34 +223,15 @@ def elbo_forward(params, cfg, triples, seq, eps, beta, drop_masks=None):
             "lse": lse, "valid": valid, "n_tok": n_tok}
 
 
-def elbo_step(params, cfg, triples, seq, eps, beta, drop_masks=None,
-              n_tok_global=None, batch_global=None):
-    """Forward + hand-written backward of ``loss = CE + beta*KL`` (ablation_study.py:59-75).
-
-    ``n_tok_global`` / ``batch_global`` replace the local CE / KL normalisers; the data-parallel
-    path uses them so that SUMMED rank gradients equal the single-process gradient on the
-    concatenated batch (SURVEY.md §8e).  Returns (losses dict, grads dict keyed like params).
-    """
-    tied = cfg.get("tie_weights", True)
-    pad_rid, pad_eid = cfg.get("pad_rid"), cfg.get("pad_eid")
-    fw = elbo_forward(params, cfg, triples, seq, eps, beta, drop_masks)
-    enc, dec = fw["enc"], fw["dec"]
-    seq_in, tgt = seq[:, :-1], seq[:, 1:]
+def _decoder_backward(params, fw, seq_in, tgt, n_tok, tied, drop_masks, grads):
+    """CE + vocabulary projection + GRU stack + token-embedding backward, shared by the SAIL and ARK steps.
+    Fills ``grads`` in place; returns (gradient w.r.t. the layer-0 input rows [B,L,d], summed dh0 [B,d])."""
+    dec = fw["dec"]
     B, L = seq_in.shape
     Wt = params["dec.tok_emb.weight"]
     V, d = Wt.shape
-    dz_dim = enc["mu"].shape[1]
     nl = n_gru_layers(params)
     dt = Wt.dtype
-    grads = {k: np.zeros_like(v) for k, v in params.items()}
-
-    n_tok = fw["n_tok"] if n_tok_global is None else float(n_tok_global)
-    b_glob = B if batch_global is None else int(batch_global)
-    if n_tok_global is not None or batch_global is not None:
-        ce_local = fw["ce"] * fw["n_tok"] / n_tok
-        kl_local = fw["kl"] * B / b_glob
-        fw = dict(fw, ce=ce_local, kl=kl_local, loss=ce_local + beta * kl_local)
-
     # ---- CE backward: (softmax - onehot)/N_tok on non-PAD rows ----
     lg = dec["logits"].reshape(-1, V)
     p = np.exp(lg - fw["lse"][:, None])
@@ -294,6 +279,39 @@ def elbo_step(params, cfg, triples, seq, eps, beta, drop_masks=None,
     # token-embedding gather backward (scatter-add; tok_emb has no padding_idx)
     np.add.at(grads["dec.tok_emb.weight"], seq_in.reshape(-1), dy.reshape(-1, d))
 
+    return dy, dh0_total
+
+
+def elbo_step(params, cfg, triples, seq, eps, beta, drop_masks=None,
+              n_tok_global=None, batch_global=None):
+    """Forward + hand-written backward of ``loss = CE + beta*KL`` (ablation_study.py:59-75).
+
+    ``n_tok_global`` / ``batch_global`` replace the local CE / KL normalisers; the data-parallel
+    path uses them so that SUMMED rank gradients equal the single-process gradient on the
+    concatenated batch (SURVEY.md §8e).  Returns (losses dict, grads dict keyed like params).
+    """
+    tied = cfg.get("tie_weights", True)
+    pad_rid, pad_eid = cfg.get("pad_rid"), cfg.get("pad_eid")
+    fw = elbo_forward(params, cfg, triples, seq, eps, beta, drop_masks)
+    enc, dec = fw["enc"], fw["dec"]
+    seq_in, tgt = seq[:, :-1], seq[:, 1:]
+    B, L = seq_in.shape
+    Wt = params["dec.tok_emb.weight"]
+    V, d = Wt.shape
+    dz_dim = enc["mu"].shape[1]
+    nl = n_gru_layers(params)
+    dt = Wt.dtype
+    grads = {k: np.zeros_like(v) for k, v in params.items()}
+
+    n_tok = fw["n_tok"] if n_tok_global is None else float(n_tok_global)
+    b_glob = B if batch_global is None else int(batch_global)
+    if n_tok_global is not None or batch_global is not None:
+        ce_local = fw["ce"] * fw["n_tok"] / n_tok
+        kl_local = fw["kl"] * B / b_glob
+        fw = dict(fw, ce=ce_local, kl=kl_local, loss=ce_local + beta * kl_local)
+
+    dy, dh0_total = _decoder_backward(params, fw, seq_in, tgt, n_tok, tied, drop_masks, grads)
+
     # ---- h0 = tanh(W_z z + b_z) shared by all layers ----
     dpre = dh0_total * (1.0 - dec["h0"] ** 2)
     grads["dec.z_proj.weight"] = dpre.T @ enc["z"]
@@ -334,6 +352,33 @@ def elbo_step(params, cfg, triples, seq, eps, beta, drop_masks=None,
         grads["dec.out.weight"] = grads["dec.tok_emb.weight"]
     losses = {"loss": float(fw["loss"]), "ce": float(fw["ce"]), "kl": float(fw["kl"]), "n_tok": n_tok}
     return losses, grads, fw
+
+
+def ark_forward(params, cfg, seq):
+    """ARK.forward + CE — kgvae/model/models.py:340-346,395-405; kgvae/experiments/train.py:44-52."""
+    tied = cfg.get("tie_weights", True)
+    dec = gru_decoder_forward(params, None, seq[:, :-1], None, tied, decoder_only=True)
+    ce, lse, valid, n_tok = cross_entropy_ignore_pad(dec["logits"], seq[:, 1:])
+    return {"dec": dec, "ce": ce, "kl": 0.0, "loss": ce, "lse": lse, "valid": valid, "n_tok": n_tok}
+
+
+def ark_step(params, cfg, seq, n_tok_global=None):
+    """Decoder-only CE step (train.py:42-58): forward + hand-written backward.  Returns (losses, grads, fw)."""
+    tied = cfg.get("tie_weights", True)
+    fw = ark_forward(params, cfg, seq)
+    seq_in, tgt = seq[:, :-1], seq[:, 1:]
+    B, L = seq_in.shape
+    d = params["dec.tok_emb.weight"].shape[1]
+    grads = {k: np.zeros_like(v) for k, v in params.items()}
+    n_tok = fw["n_tok"] if n_tok_global is None else float(n_tok_global)
+    if n_tok_global is not None:
+        fw = dict(fw, ce=fw["ce"] * fw["n_tok"] / n_tok)
+        fw["loss"] = fw["ce"]
+    dy, _ = _decoder_backward(params, fw, seq_in, tgt, n_tok, tied, None, grads)
+    grads["dec.pos_emb.weight"][:L] = dy.sum(0)          # pos_emb(arange(L)) broadcast over the batch
+    if tied and "dec.out.weight" in grads:
+        grads["dec.out.weight"] = grads["dec.tok_emb.weight"]
+    return {"loss": float(fw["loss"]), "ce": float(fw["ce"]), "kl": 0.0, "n_tok": n_tok}, grads, fw
 
 
 def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):

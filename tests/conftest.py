@@ -31,3 +31,16 @@ SAIL_CASES = ["syn", "wd", "wd_clamp", "untied"]
 @pytest.fixture(params=SAIL_CASES)
 def sail_golden(request):
     return (request.param,) + load_sail_golden(request.param)
+
+
+def load_ark_golden(name):
+    """Decoder-only ARK fixture (oracle/make_golden.py::ark_case) from the unmodified reference."""
+    arr = dict(np.load(os.path.join(GOLDEN, f"ark_{name}.npz")))
+    with open(os.path.join(GOLDEN, f"ark_{name}.json")) as f:
+        meta = json.load(f)
+    params = {k[len("param::"):]: v for k, v in arr.items() if k.startswith("param::")}
+    grads = {k[len("grad::"):]: v for k, v in arr.items() if k.startswith("grad::")}
+    return arr, meta, params, grads
+
+
+ARK_CASES = ["syn", "wd"]

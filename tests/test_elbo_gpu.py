@@ -280,3 +280,70 @@ def test_cuda_graph_step_matches_eager_step():
     torch.testing.assert_close(res[0][0], res[1][0], rtol=5e-3, atol=1e-5)
     bad = (res[0][1] - res[1][1]).abs() > 0.25 * 3e-3
     assert bad.float().mean().item() < 0.02
+
+
+# ------------------------------------------------------------------ decoder-only ARK
+from conftest import ARK_CASES, load_ark_golden  # noqa: E402
+
+from kgvae.model.models import ARK  # noqa: E402
+
+
+def _ark_from(params, cfg):
+    torch.manual_seed(0)
+    m = ARK(dict(cfg)).to(DEV)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in params.items()}, strict=True)
+    return m
+
+
+@pytest.mark.parametrize("case", ARK_CASES)
+def test_ark_ce_step_matches_reference_golden(case):
+    """CE-only step of the reference trainer (train.py:42-58) on the fused engine without encoder / KL."""
+    arr, meta, params, grads = load_ark_golden(case)
+    model = _ark_from(params, meta["cfg"])
+    seq = torch.from_numpy(arr["seq"])
+    out = model.ce_backward(seq)
+    ce, kl = out.tolist()
+    assert kl == 0.0
+    assert abs(ce - float(arr["ce"])) <= LOSS_RTOL * abs(float(arr["ce"]))
+    _check_grads(model.engine(), grads)
+
+
+@pytest.mark.parametrize("case", ARK_CASES)
+def test_ark_fp32_inference_and_greedy_generation_match_reference(case):
+    arr, meta, _, _ = load_ark_golden(case)
+    cfg = meta["cfg"]
+    params = {k[len("adam_param::"):]: v for k, v in arr.items() if k.startswith("adam_param::")}
+    model = _ark_from(params, cfg).eval()
+    seq = torch.from_numpy(arr["seq"]).to(DEV)
+    np.testing.assert_allclose(model(seq[:2, :5]).cpu().numpy(), arr["eval_logits_prefix5"], rtol=1e-4, atol=2e-4)
+    # the (triples, seq) call form ignores triples (models.py:395-405)
+    assert torch.equal(model(torch.from_numpy(arr["triples"]).to(DEV)[:2], seq[:2, :5]), model(seq[:2, :5]))
+    gen = model.generate(cfg["seq_len"], cfg["special_tokens"], batch_size=3, sample=False)
+    assert gen.cpu().tolist() == arr["greedy"].tolist()          # integer outputs: bit-exact
+
+
+def test_ark_two_adam_steps_match_reference_golden():
+    arr, meta, params, _ = load_ark_golden("syn")
+    model = _ark_from(params, meta["cfg"])
+    model.engine(lr=meta["adam_lr"])
+    seq = torch.from_numpy(arr["seq"])
+    for s in range(2):
+        ce = model.ce_step(seq)[0].item()
+        np.testing.assert_allclose(ce, arr["adam_losses"][s], rtol=2e-2)
+    sd = model.state_dict()
+    for k, ref in arr.items():
+        if k.startswith("adam_param::"):
+            bad = np.abs(sd[k[len("adam_param::"):]].cpu().numpy() - ref) > 0.25 * meta["adam_lr"]
+            assert bad.mean() < 0.05, (k, bad.mean())
+
+
+def test_ark_step_matches_numpy_oracle_ragged():
+    cfg, tri, seq, rng = _random_case(23, nE=300, nR=6, lo=1, hi=12, pad=True, d=64, dz=16, nl=3, B=32)
+    cfg["model_type"] = "ARK"
+    torch.manual_seed(1)
+    model = ARK(dict(cfg)).to(DEV)
+    params = {k: v.detach().double().cpu().numpy() for k, v in model.state_dict().items()}
+    losses, g_ref, _ = O.ark_step(params, cfg, seq)
+    ce = model.ce_backward(torch.from_numpy(seq))[0].item()
+    assert abs(ce - losses["ce"]) <= LOSS_RTOL * abs(losses["ce"])
+    _check_grads(model.engine(), g_ref)

@@ -109,3 +109,52 @@ def test_train_epoch_matches_reference():
         for k in p:
             p[k], m[k], v[k] = O.adam_step(p[k], g[k], m[k], v[k], i + 1, meta["lr"])
     np.testing.assert_allclose(tot / 3, arr["result"], rtol=5e-5)
+
+
+# ---------------------------------------------------------------- decoder-only ARK (reference models.py:323-405)
+import pytest  # noqa: E402
+
+from conftest import ARK_CASES, load_ark_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ARK_CASES)
+def test_ark_forward_and_gradients_match_reference(case):
+    arr, meta, params, grads = load_ark_golden(case)
+    losses, g, fw = O.ark_step(_f64(params), meta["cfg"], arr["seq"])
+    np.testing.assert_allclose(fw["dec"]["logits"], arr["logits"], rtol=1e-4, atol=2e-5)
+    assert abs(losses["ce"] - float(arr["ce"])) <= 1e-5 * abs(float(arr["ce"]))
+    for k, ref in grads.items():
+        num, den = np.linalg.norm(g[k] - ref), max(np.linalg.norm(ref), 1e-6)
+        assert num / den < 1e-4, (k, num / den)
+
+
+@pytest.mark.parametrize("case", ARK_CASES)
+def test_ark_two_adam_steps_and_greedy_match_reference(case):
+    arr, meta, params, _ = load_ark_golden(case)
+    cfg = meta["cfg"]
+    p = _f64(params)
+    p.pop("dec.out.weight")
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(x) for k, x in p.items()}
+    for s in range(2):
+        losses, g, _ = O.ark_step(p, cfg, arr["seq"])
+        np.testing.assert_allclose(losses["ce"], arr["adam_losses"][s], rtol=3e-5)
+        for k in p:
+            p[k], m[k], v[k] = O.adam_step(p[k], g[k], m[k], v[k], s + 1, meta["adam_lr"])
+    for k in p:
+        ref = arr["adam_param::" + k]
+        bad = np.abs(p[k] - ref) > 1e-4 + 1e-4 * np.abs(ref)
+        assert bad.mean() < 0.02, (k, bad.mean())
+    # greedy generation (ARK.generate, models.py:408-471 with sample=False) on the post-Adam weights
+    pa = {k[len("adam_param::"):]: x.astype(np.float64) for k, x in arr.items() if k.startswith("adam_param::")}
+    np.testing.assert_allclose(O.gru_decoder_forward(pa, None, arr["seq"][:2, :5], None, True, decoder_only=True)["logits"],
+                               arr["eval_logits_prefix5"], rtol=1e-4, atol=2e-5)
+    seq = np.full((3, 1), O.BOS, dtype=np.int64)
+    for _ in range(cfg["seq_len"] - 1):
+        lg = O.gru_decoder_forward(pa, None, seq, None, True, decoder_only=True)["logits"][:, -1]
+        seq = np.concatenate([seq, lg.argmax(-1)[:, None]], axis=1)
+        if (seq[:, -1] == O.EOS).all():
+            break
+    if seq.shape[1] < cfg["seq_len"]:
+        seq = np.concatenate([seq, np.full((3, cfg["seq_len"] - seq.shape[1]), O.EOS, dtype=np.int64)], axis=1)
+    assert seq[:, :cfg["seq_len"]].tolist() == arr["greedy"].tolist()
