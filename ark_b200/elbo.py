@@ -71,6 +71,7 @@ class SailEngine:
         self._pending = []
         self.prof = None
         self._capturing = False
+        self._segment_break = None
         self._graphs = {}
         self.dyn_f = torch.zeros(2, device=dev)                      # [lr/(1-b1^t), 1/sqrt(1-b2^t)] for graph replay
         self.dyn_i = torch.zeros(1, device=dev, dtype=torch.int64)   # running Philox offset for graph replay
@@ -331,12 +332,14 @@ class SailEngine:
     def _flush_bucket(self):
         if not self._pending:
             return
-        ev = torch.cuda.Event()
-        ev.record()
-        self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
-            for (s, e) in self._pending:
-                torch.distributed.all_reduce(self.flat.grad[s:e], group=self.group)
+        if self._capturing:
+            # graph mode under data parallelism: end the graph segment here; the replay loop all-reduces the
+            # finished gradient slices eagerly on the side stream while the NEXT segment runs (NCCL kernels are
+            # never captured: capturing them next to the cooperative GRU kernels hung at 2 ranks)
+            self._segment_break(self._pending)
+            self._pending = []
+            return
+        self._all_reduce_async(self._pending)
         self._pending = []
 
     def _sync_grads(self):
@@ -364,14 +367,24 @@ class SailEngine:
         return out
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def _all_reduce_async(self, spans):
+        """Sum gradient slices over ranks on the side stream, ordered after everything queued on this stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            for (s, e) in spans:
+                torch.distributed.all_reduce(self.flat.grad[s:e], group=self.group)
+
     def train_step_graphed(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
         """Same as train_step, but the ~190 launches of the step are captured ONCE per batch layout
-        (B, T, per-step row counts, normalisers, beta) into a CUDA graph and replayed: the host cost of a step
-        drops to a few small input copies + one graph launch.  Layouts that never repeat (ragged real data)
-        should use train_step.  NOT used under data parallelism: capturing the side-stream NCCL all-reduces
-        next to the cooperative GRU kernels hung at 2 ranks (round-1 finding), so DP steps stay eager."""
-        if self.world > 1:
-            return self.train_step(triples, seq, lay, eps, beta, lr, n_tok_global, batch_global)
+        (B, T, per-step row counts, normalisers, beta) into CUDA graphs and replayed: the host cost of a step
+        drops to a few small input copies + a handful of graph launches.  Layouts that never repeat (ragged real
+        data) should use train_step.
+        Under data parallelism the step is captured as a CHAIN of graph segments cut at the gradient-bucket
+        boundaries; between two segments the replay loop issues that bucket's NCCL all-reduce eagerly on the
+        side stream, so it overlaps the following segment of backward exactly as in the eager step, and Adam
+        (last segment) waits for the side stream."""
         key = (None if triples is None else tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(), float(beta),
                n_tok_global, batch_global)
         ent = self._graphs.get(key)
@@ -389,29 +402,44 @@ class SailEngine:
                   "lay": PackedLayout(perm=lay.perm, lens=lay.lens, bt=lay.bt, off=lay.off, n_tok=lay.n_tok,
                                       n_triples=lay.n_triples, L=lay.L, perm_dev=lay.perm_dev.clone(),
                                       bt_dev=lay.bt_dev.clone(), off_dev=lay.off_dev.clone())}
+            from . import _C
+            segs = []                     # [(CUDAGraph, [(s, e) gradient spans to all-reduce after it])]
+            pool = torch.cuda.graph_pool_handle()
+            cur = {"g": None}
 
-            def body():
-                out = self.forward_backward(st["triples"], st["seq"], st["lay"], st["eps"], beta, n_tok_global,
-                                            batch_global, train=True)
-                f = self.flat
-                self._sync_grads()
-                ops.adam_flat_dyn(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.dyn_f, b1, b2, self.eps)
-                self.stats[0:2] += out
-                self.stats[2] += 1
-                return out
+            def begin():
+                cur["g"] = torch.cuda.CUDAGraph()
+                cur["g"].capture_begin(pool=pool)
+
+            def brk(spans):
+                cur["g"].capture_end()
+                segs.append((cur["g"], list(spans)))
+                begin()
 
             # warm-up outside capture is NOT wanted (it would apply an extra optimiser step): capture directly
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            from . import _C
             n0 = _C.lib().launch_count()
-            self._capturing = True
+            cap = torch.cuda.Stream(device=dev)
+            cap.wait_stream(torch.cuda.current_stream())
+            self._capturing, self._segment_break = True, brk
             try:
-                with torch.cuda.graph(g):
-                    st["out"] = body()
+                with torch.cuda.stream(cap):
+                    begin()
+                    out = self.forward_backward(st["triples"], st["seq"], st["lay"], st["eps"], beta, n_tok_global,
+                                                batch_global, train=True)
+                    if self.world > 1:
+                        self._flush_bucket()          # the last gradient slices: cut, then Adam in its own segment
+                    f = self.flat
+                    ops.adam_flat_dyn(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.dyn_f, b1, b2, self.eps)
+                    self.stats[0:2] += out
+                    self.stats[2] += 1
+                    cur["g"].capture_end()
+                    segs.append((cur["g"], []))
             finally:
                 self._capturing = False
-            st["graph"], st["philox_per_step"] = g, self._drop_calls * ((lay.n_tok * self.d + 3) // 4)
+            torch.cuda.current_stream().wait_stream(cap)
+            st["out"], st["segs"] = out, segs
+            st["philox_per_step"] = self._drop_calls * ((lay.n_tok * self.d + 3) // 4)
             st["n_launch"] = _C.lib().launch_count() - n0
             self._graphs[key] = ent = st
         else:
@@ -420,7 +448,13 @@ class SailEngine:
                 ent["eps"].copy_(eps, non_blocking=True)
             ent["seq"].copy_(seq, non_blocking=True)
             ent["lay"].perm_dev.copy_(lay.perm_dev, non_blocking=True)
-        ent["graph"].replay()
+        segs = ent["segs"]
+        for i, (g, spans) in enumerate(segs):
+            if i == len(segs) - 1 and self.world > 1:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)     # Adam needs the summed gradients
+            g.replay()
+            if spans:
+                self._all_reduce_async(spans)
         self.launches_replayed += ent["n_launch"]
         self.philox_offset += ent["philox_per_step"]
         return ent["out"]

@@ -192,7 +192,7 @@ def main():
     bg = batch * world
     beta = 0.5
 
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph      # N>1: graph segments cut at the gradient buckets, NCCL eager in between
 
     def step(i, graph=use_graph):
         j = i % NB
