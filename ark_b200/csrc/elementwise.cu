@@ -2,6 +2,7 @@
 // residual add, casts, inter-layer dropout, and K10 dense Adam over the flat parameter buffer
 // (torch.optim.Adam defaults, kgvae/experiments/ablation_study.py:571).  All HBM-bound, 128-bit accesses.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace ark {
 
@@ -127,19 +128,6 @@ __global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, c
   if (yb) yb[i] = f32_to_bf16_bits(v);
 }
 
-// Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = seed
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
 
 __global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restrict__ x, int64_t n, float p,
                                                           uint64_t seed, uint64_t offset, float* __restrict__ y,

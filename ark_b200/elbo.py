@@ -77,6 +77,8 @@ class SailEngine:
         self.dyn_i = torch.zeros(1, device=dev, dtype=torch.int64)   # running Philox offset for graph replay
         self.launches_replayed = 0       # kernels of libarkb200 executed through graph replays
         self.force_unfused_gru = False   # tests: compare the persistent GRU kernel with the per-step path
+        self.gru_mode = "auto"           # "auto": wavefront stack kernel when it fits, else per-layer persistent;
+                                         # "layer": never the wavefront kernel (tests / A-B timing)
         self.stats = torch.zeros(4, device=dev)  # [ce, kl, steps, unused] accumulated on device
         self.refresh_shadow()
         if hasattr(model, "_attach_engine"):
@@ -182,10 +184,38 @@ class SailEngine:
         b0 = int(lay.bt[0])
         saved = []
         u_b = x_b
-        persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru
-        gh_ws = None if persist else new(b0, d3)
-        sync_ws = new((b0 + 127) // 128, dtype=torch.int32) if persist else None
-        for k in range(nl):
+        wave = (use_tc and self.gru_mode in ("auto", "wave") and not self.force_unfused_gru
+                and ops.gru_wave_supported(d, b0, nl) > 0)
+        persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru and not wave
+        gh_ws = None if (persist or wave) else new(b0, d3)
+        sync_ws = new(nl * ((b0 + 127) // 128), dtype=torch.int32) if (persist or wave) else None
+        if wave:
+            # the whole stack in ONE cooperative launch: layers run as a diagonal wavefront (L+nl-1 dependent
+            # steps instead of nl*L), W_ih u_t inside the recurrence (no gi buffer), dropout in the epilogue
+            hp_all, out_all = new(nl, N, d, dtype=bf), new(nl, N, d, dtype=bf)
+            h0_b = new(b0, d, dtype=bf)
+            ops.cast_bf16(h0[:b0], h0_b)
+            hp_all[:, :b0].copy_(h0_b)
+            wave_gates = tuple(new(nl, N, d, dtype=bf) for _ in range(4))
+            dropping = train and self.p_drop > 0 and nl > 1
+            wave_mask = new(nl - 1, N, d, dtype=torch.uint8) if dropping else None
+            stride = (N * d + 3) // 4
+            with self._timed("gru_wave_fwd", flops=4.0 * N * d * d3 * nl):
+                ops.gru_wave_fwd(x_b, hp_all, out_all, h0 if self.has_enc else None,
+                                 [self._w(f"dec.gru.weight_ih_l{k}") for k in range(nl)],
+                                 [self._w(f"dec.gru.weight_hh_l{k}") for k in range(nl)],
+                                 [f.p(f"dec.gru.bias_ih_l{k}") for k in range(nl)],
+                                 [f.p(f"dec.gru.bias_hh_l{k}") for k in range(nl)],
+                                 lay.bt_dev, lay.off_dev, L, b0, d, wave_gates, wave_mask,
+                                 self.p_drop if dropping else 0.0, self.seed,
+                                 self._drop_calls * stride if self._capturing else self.philox_offset,
+                                 self.dyn_i if (self._capturing and dropping) else None, sync_ws)
+            if dropping:
+                if not self._capturing:
+                    self.philox_offset += (nl - 1) * stride
+                self._drop_calls += nl - 1
+            u_b = out_all[nl - 1]
+        for k in range(0 if not wave else nl, nl):
             gi = new(N, d3)
             self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, tag="gru_gi",
                        bias=f.p(f"dec.gru.bias_ih_l{k}"))
@@ -238,12 +268,33 @@ class SailEngine:
         del logits
         self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
         dh0 = new(b0, d)
-        dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
-        if persist:
-            whh_t = new(d, d3, dtype=bf)
+        if wave:
+            w_t = new(2 * nl, d, d3, dtype=bf)
+            for k in range(nl):
+                ops.transpose_bf16(self._w(f"dec.gru.weight_hh_l{k}"), w_t[k])
+                if k > 0:
+                    ops.transpose_bf16(self._w(f"dec.gru.weight_ih_l{k}"), w_t[nl + k])
+            dgi_all, dgh_all = new(nl, N, d3, dtype=bf), new(nl, N, d3, dtype=bf)
+            with self._timed("gru_wave_bwd", flops=4.0 * N * d * d3 * nl - 2.0 * N * d * d3):
+                ops.gru_wave_bwd(dy, wave_gates, hp_all, wave_mask, self.p_drop if wave_mask is not None else 0.0,
+                                 [w_t[k] for k in range(nl)], [None] + [w_t[nl + k] for k in range(1, nl)],
+                                 lay.bt_dev, lay.off_dev, L, b0, d, dgi_all, dgh_all, dh0 if self.has_enc else None,
+                                 sync_ws)
+            for k in range(nl - 1, -1, -1):
+                u_in = x_b if k == 0 else out_all[k - 1]
+                self._gemm(dgi_all[k], MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
+                self._gemm(dgh_all[k], MN, hp_all[k], MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
+                ops.colsum(dgi_all[k], N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
+                ops.colsum(dgh_all[k], N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
+                self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+            self._gemm(dgi_all[0], K, self._w("dec.gru.weight_ih_l0"), MN, dy, N, d, d3, tag="gru_dX")
         else:
-            dh_a, dh_b = new(b0, d), new(b0, d)
-        for k in range(nl - 1, -1, -1):
+            dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
+            if persist:
+                whh_t = new(d, d3, dtype=bf)
+            else:
+                dh_a, dh_b = new(b0, d), new(b0, d)
+        for k in range(nl - 1, -1 if not wave else nl - 1, -1):
             u_in, hp_f, hp_b, gates, mask = saved[k]
             if mask is not None:
                 ops.dropout_bwd(dy, mask, self.p_drop, dy)

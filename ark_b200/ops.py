@@ -259,3 +259,42 @@ def adam_flat_dyn(p, g, m, v, shadow, hyper, beta1, beta2, eps, grad_scale=1.0):
     _C.lib().call("ark_adam_flat_dyn", _ptr(p, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32),
                   _ptr(v, torch.float32), _ptr(shadow, torch.bfloat16), p.numel(), _ptr(hyper, torch.float32),
                   float(beta1), float(beta2), float(eps), float(grad_scale), _stream())
+
+
+def gru_wave_supported(d, bt0, nl) -> int:
+    return int(_C.lib().raw("ark_gru_wave_supported")(int(d), int(bt0), int(nl)))
+
+
+def _ptr_array(tensors, dtype):
+    """HOST array of device pointers (const T* const*)."""
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = _ptr(t, dtype) if t is not None else None
+    return arr
+
+
+def gru_wave_fwd(x_b, hp_b, out_b, h0, Wih, Whh, b_ih, b_hh, bt_dev, off_dev, L, bt0, d, gates, mask, p_drop, seed,
+                 offset, offset_dev, sync_ws):
+    """All layers x all steps of the GRU stack in one cooperative launch (csrc/gru_wave.cu)."""
+    nl, N = hp_b.shape[0], hp_b.shape[1]
+    r, z, n, ghn = gates if gates is not None else (None, None, None, None)
+    _contig(x_b, hp_b, out_b, h0, r, z, n, ghn, mask, *Wih, *Whh)
+    a_ih, a_hh = _ptr_array(Wih, torch.bfloat16), _ptr_array(Whh, torch.bfloat16)
+    a_bi, a_bh = _ptr_array(b_ih, torch.float32), _ptr_array(b_hh, torch.float32)
+    _C.lib().call("ark_gru_wave_fwd", _ptr(x_b, torch.bfloat16), _ptr(hp_b, torch.bfloat16), _ptr(out_b, torch.bfloat16),
+                  _ptr(h0, torch.float32), a_ih, a_hh, a_bi, a_bh, _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32),
+                  L, bt0, N, d, nl, _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16), _ptr(n, torch.bfloat16),
+                  _ptr(ghn, torch.bfloat16), _ptr(mask, torch.uint8), float(p_drop), int(seed), int(offset),
+                  _ptr(offset_dev, torch.int64), _ptr(sync_ws, torch.int32), _stream())
+
+
+def gru_wave_bwd(dy_top, gates, hp_b, mask, p_drop, WhhT, WihT, bt_dev, off_dev, L, bt0, d, dgi_b, dgh_b, dh0, sync_ws):
+    nl, N = hp_b.shape[0], hp_b.shape[1]
+    r, z, n, ghn = gates
+    _contig(dy_top, r, z, n, ghn, hp_b, mask, dgi_b, dgh_b, dh0, *WhhT, *[w for w in WihT if w is not None])
+    a_hh, a_ih = _ptr_array(WhhT, torch.bfloat16), _ptr_array(WihT, torch.bfloat16)
+    _C.lib().call("ark_gru_wave_bwd", _ptr(dy_top, torch.float32), _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16),
+                  _ptr(n, torch.bfloat16), _ptr(ghn, torch.bfloat16), _ptr(hp_b, torch.bfloat16), _ptr(mask, torch.uint8),
+                  float(p_drop), a_hh, a_ih, _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32), L, bt0, N, d, nl,
+                  _ptr(dgi_b, torch.bfloat16), _ptr(dgh_b, torch.bfloat16), _ptr(dh0, torch.float32),
+                  _ptr(sync_ws, torch.int32), _stream())

@@ -175,6 +175,30 @@ int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uint16_t* z, c
                         const uint16_t* hp_b, const uint16_t* WhhT_b, const int32_t* bt_dev, const int32_t* off_dev,
                         int64_t L, int64_t bt0, int64_t N, int64_t d, uint16_t* dgi_b, uint16_t* dgh_b,
                         float* dh0, int dh0_accumulate, int32_t* sync_ws, void* stream);
+/* Wavefront GRU STACK (ark_b200/csrc/gru_wave.cu): all nl layers x L steps of nn.GRU (models.py:121-127,141;
+ * decoder-only :329-343) in ONE cooperative launch per direction; layer k step t runs as soon as layer k-1 step t
+ * and layer k step t-1 are done (L+nl-1 dependent steps instead of nl*L).  The input projections W_ih u_t run
+ * inside the recurrence, so there is no gi buffer.  Per-layer tensors are stacked: hp_b / out_b / r / z / n / ghn
+ * bf16 [nl,N,d]; mask u8 [nl-1,N,d] (NULL when p_drop == 0); dgi_b / dgh_b bf16 [nl,N,3d].  x_b bf16 [N,d] are the
+ * layer-0 input rows; out_b[k] is layer k's output AFTER the inter-layer dropout (k < nl-1; Philox stream of
+ * ark_dropout_bf16 with offset + k*ceil(N*d/4)), hp_b[k] holds the undropped h_{t-1} rows (block 0 of every
+ * layer pre-filled with bf16(h0)).  h0 f32 [bt0,d] is shared by all layers (NULL = zeros).  Wih_b / Whh_b /
+ * b_ih / b_hh (and WhhT_b / WihT_b = transposed [d,3d] bf16 weights; WihT_b[0] unused) are HOST arrays of nl
+ * device pointers.  dh0 (optional) receives the SUM over layers of d loss / d h0.  sync_ws int32 [nl*ceil(bt0/128)].
+ * ark_gru_wave_supported returns the hidden-slice width (16/32) or 0 when the stack does not fit (resident
+ * weights 12*slice*d bytes per CTA, (d/slice)*ceil(bt0/128)*nl CTAs <= 148, nl <= 4, d % 64 == 0). */
+int ark_gru_wave_supported(int64_t d, int64_t bt0, int64_t nl);
+int ark_gru_wave_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t* out_b, const float* h0,
+                     const uint16_t* const* Wih_b, const uint16_t* const* Whh_b, const float* const* b_ih,
+                     const float* const* b_hh, const int32_t* bt_dev, const int32_t* off_dev, int64_t L, int64_t bt0,
+                     int64_t N, int64_t d, int64_t nl, uint16_t* r, uint16_t* z, uint16_t* n, uint16_t* ghn,
+                     uint8_t* mask, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                     int32_t* sync_ws, void* stream);
+int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const uint16_t* z, const uint16_t* n, const uint16_t* ghn,
+                     const uint16_t* hp_b, const uint8_t* mask, float p_drop, const uint16_t* const* WhhT_b,
+                     const uint16_t* const* WihT_b, const int32_t* bt_dev, const int32_t* off_dev, int64_t L,
+                     int64_t bt0, int64_t N, int64_t d, int64_t nl, uint16_t* dgi_b, uint16_t* dgh_b, float* dh0,
+                     int32_t* sync_ws, void* stream);
 /* out[C,R] = in[R,C]^T (bf16) */
 int ark_transpose_bf16(const uint16_t* in, int64_t R, int64_t C, uint16_t* out, void* stream);
 
