@@ -50,6 +50,25 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+int make_tmap_kchunked_bf16(CUtensorMap* out, const void* base, uint64_t K, uint64_t rows, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_chunks) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(ARK_E_NODRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
+  if (K % 64 != 0 || box_rows == 0 || box_rows > 256 || box_chunks == 0 || box_chunks > 256)
+    return fail(ARK_E_SHAPE, "k-chunked tensor map: K=%llu rows-box=%u chunk-box=%u", (unsigned long long)K, box_rows, box_chunks);
+  const cuuint64_t gdim[3] = {64, rows, K / 64};
+  const cuuint64_t gstride[2] = {ld * 2, 128};
+  const cuuint32_t box[3] = {64, box_rows, box_chunks};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ARK_E_SHAPE, "cuTensorMapEncodeTiled (k-chunked) failed (CUresult %d) K=%llu rows=%llu ld=%llu box=(%u,%u)",
+                (int)r, (unsigned long long)K, (unsigned long long)rows, (unsigned long long)ld, box_rows, box_chunks);
+  return 0;
+}
+
 }  // namespace ark
 
 extern "C" int ark_abi_version(void) { return ARK_ABI_VERSION; }

@@ -33,8 +33,8 @@ constexpr int GW_MAXL = 4;
 constexpr int GW_BK = 64;
 
 struct GruWaveFwdParams {
-  CUtensorMap tmU[GW_MAXL];    // layer input rows u^k [N,d] bf16 (u^0 = token embeddings), box {64, R}
-  CUtensorMap tmH[GW_MAXL];    // h_prev rows hp^k [N,d] bf16, box {64, R}
+  CUtensorMap tmU[GW_MAXL];    // layer input rows u^k [N,d] bf16 (u^0 = token embeddings), box {64, R, C}
+  CUtensorMap tmH[GW_MAXL];    // h_prev rows hp^k [N,d] bf16, box {64, R, C}
   CUtensorMap tmWih[GW_MAXL];  // W_ih^k [3d,d] bf16, box {64, DJ}
   CUtensorMap tmWhh[GW_MAXL];  // W_hh^k [3d,d] bf16, box {64, DJ}
   const float* b_ih[GW_MAXL];
@@ -51,12 +51,12 @@ struct GruWaveFwdParams {
   uint64_t seed, offset, drop_stride;
   int64_t layer_stride;        // N * d
   float p_drop;
-  int L, d, nl, R, n_slots;
+  int L, d, nl, R, n_groups, C;   // ring of n_groups groups, one TMA op loads C k-chunks
 };
 
 struct GruWaveBwdParams {
-  CUtensorMap tmDgi[GW_MAXL];   // dgi^k [N,3d] bf16, box {64, R}   (read by layer k-1)
-  CUtensorMap tmDgh[GW_MAXL];   // dgh^k [N,3d] bf16, box {64, R}   (read by layer k)
+  CUtensorMap tmDgi[GW_MAXL];   // dgi^k [N,3d] bf16, box {64, R, C}   (read by layer k-1)
+  CUtensorMap tmDgh[GW_MAXL];   // dgh^k [N,3d] bf16, box {64, R, C}   (read by layer k)
   CUtensorMap tmWhhT[GW_MAXL];  // W_hh^k^T [d,3d] bf16, box {64, DJ}
   CUtensorMap tmWihT[GW_MAXL];  // W_ih^k^T [d,3d] bf16, box {64, DJ} (read by layer k-1)
   const int32_t* bt;
@@ -69,7 +69,7 @@ struct GruWaveBwdParams {
   float* dh0;                   // [bt[0], d] fp32, zeroed before launch; every layer adds its share; may be null
   int64_t layer_stride;         // N * d
   float p_drop;
-  int L, d, nl, R, n_slots;
+  int L, d, nl, R, n_groups, C;   // ring of n_groups groups, one TMA op loads C k-chunks
 };
 
 __device__ __forceinline__ void st_mask4(uint8_t* p, const bool* keep) {
@@ -82,14 +82,14 @@ __device__ __forceinline__ void st_mask4(uint8_t* p, const bool* keep) {
 // =====================================================================================================
 template <int DJ>
 __global__ void __launch_bounds__(192, 1) gru_wave_fwd_kernel(const __grid_constant__ GruWaveFwdParams p) {
-  constexpr int NC = 4 * DJ;  // accumulator columns: r | z | n_i | n_h
-  constexpr uint32_t TMEM_COLS = 2 * NC <= 128 ? 128 : 256;
-  constexpr int ACC_LD = NC + 1;
+  constexpr int NC = 6 * DJ;  // accumulator columns: input side r|z|n, recurrent side r|z|n (summed in the epilogue)
+  constexpr uint32_t TMEM_COLS = 2 * NC <= 256 ? 256 : 512;
+  constexpr int ACC_LD = 4 * DJ + 1;   // staged: r | z | n_i | n_h
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int d = p.d, L = p.L, R = p.R, n_slots = p.n_slots;
-  const int nkc = d / GW_BK;
-  const int slot_bytes = R * 128;
+  const int d = p.d, L = p.L, R = p.R, n_slots = p.n_groups, C = p.C;
+  const int nkc = d / GW_BK, gpp = nkc / C;   // groups per phase
+  const int chunk_bytes = R * 128, slot_bytes = C * chunk_bytes;
   const int w_bytes = 3 * DJ * d * 2;
   uint8_t* wih_sm = smem;
   uint8_t* whh_sm = smem + w_bytes;
@@ -157,59 +157,61 @@ __global__ void __launch_bounds__(192, 1) gru_wave_fwd_kernel(const __grid_const
           wait_counter(below_sync, (t + 1) * ns);
           asm volatile("fence.proxy.async;" ::: "memory");
         }
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
+        for (int g = 0; g < gpp; ++g, ++it) {
           const int s = it % n_slots;
           ptx::mbar_wait(&empty_bar[s], ((it / n_slots) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)slot_bytes);
-          ptx::tma_load_2d(a_sm + s * slot_bytes, tmU, &full_bar[s], kc * GW_BK, row0);
+          ptx::tma_load_3d(a_sm + s * slot_bytes, tmU, &full_bar[s], 0, row0, g * C);
         }
         // recurrent side: h^k_{t-1}
         if (t > 0) {
           wait_counter(my_sync, t * ns);
           asm volatile("fence.proxy.async;" ::: "memory");
         }
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
+        for (int g = 0; g < gpp; ++g, ++it) {
           const int s = it % n_slots;
           ptx::mbar_wait(&empty_bar[s], ((it / n_slots) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)slot_bytes);
-          ptx::tma_load_2d(a_sm + s * slot_bytes, tmH, &full_bar[s], kc * GW_BK, row0);
+          ptx::tma_load_3d(a_sm + s * slot_bytes, tmH, &full_bar[s], 0, row0, g * C);
         }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc3 = ptx::make_idesc_bf16(128, 3 * DJ, 0, 0);
-      constexpr uint32_t idesc2 = ptx::make_idesc_bf16(128, 2 * DJ, 0, 0);
-      constexpr uint32_t idesc1 = ptx::make_idesc_bf16(128, DJ, 0, 0);
       ptx::mbar_wait(w_bar, 0);
       const uint32_t wih_addr = ptx::smem_u32(wih_sm), whh_addr = ptx::smem_u32(whh_sm), a_addr0 = ptx::smem_u32(a_sm);
       int it = 0;
       for (int t = 0; t < L; ++t) {
         if (m0 >= p.bt[t]) break;
         const uint32_t acc = tmem_base + (uint32_t)((t & 1) * NC);
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
+        for (int g = 0; g < gpp; ++g, ++it) {
           const int s = it % n_slots;
           ptx::mbar_wait(&full_bar[s], (it / n_slots) & 1);
           ptx::tc_fence_after();
+          for (int c = 0; c < C; ++c) {
+            const int kc = g * C + c;
 #pragma unroll
-          for (int kk = 0; kk < GW_BK / 16; ++kk) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + kk * 32, 16, 1024);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(wih_addr + kc * (3 * DJ * 128) + kk * 32, 16, 1024);
-            ptx::umma_f16(acc, adesc, bdesc, idesc3, (kc | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < GW_BK / 16; ++kk) {
+              const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + c * chunk_bytes + kk * 32, 16, 1024);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(wih_addr + kc * (3 * DJ * 128) + kk * 32, 16, 1024);
+              ptx::umma_f16(acc, adesc, bdesc, idesc3, (kc | kk) != 0 ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty_bar[s]);
         }
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
+        for (int g = 0; g < gpp; ++g, ++it) {
           const int s = it % n_slots;
           ptx::mbar_wait(&full_bar[s], (it / n_slots) & 1);
           ptx::tc_fence_after();
+          for (int c = 0; c < C; ++c) {
+            const int kc = g * C + c;
 #pragma unroll
-          for (int kk = 0; kk < GW_BK / 16; ++kk) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + kk * 32, 16, 1024);
-            const uint32_t wb = whh_addr + kc * (3 * DJ * 128) + kk * 32;
-            ptx::umma_f16(acc, adesc, ptx::make_smem_desc_sw128(wb, 16, 1024), idesc2, 1u);
-            ptx::umma_f16(acc + 3 * DJ, adesc, ptx::make_smem_desc_sw128(wb + 2 * DJ * 128, 16, 1024), idesc1,
-                          (kc | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < GW_BK / 16; ++kk) {
+              const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + c * chunk_bytes + kk * 32, 16, 1024);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(whh_addr + kc * (3 * DJ * 128) + kk * 32, 16, 1024);
+              ptx::umma_f16(acc + 3 * DJ, adesc, bdesc, idesc3, (kc | kk) != 0 ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty_bar[s]);
         }
@@ -255,14 +257,27 @@ __global__ void __launch_bounds__(192, 1) gru_wave_fwd_kernel(const __grid_const
       if (m0 + q * 32 < Bt) {
         const int row = q * 32 + lane;
         float* dst = acc_sm + row * ACC_LD;
+        // one gate per pass (input-side and recurrent-side columns in flight together, one wait per pass)
 #pragma unroll
-        for (int c = 0; c < NC; c += 16) {
-          uint32_t v[16];
-          ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
+        for (int g = 0; g < 3; ++g) {
+          uint32_t vi[DJ], vh[DJ];
+#pragma unroll
+          for (int c = 0; c < DJ; c += 16) {
+            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(g * DJ + c), vi + c);
+            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(3 * DJ + g * DJ + c), vh + c);
+          }
           ptx::tmem_ld_wait();
           if (row < R) {
+            if (g < 2) {   // r, z: input + recurrent parts summed here
 #pragma unroll
-            for (int kx = 0; kx < 16; ++kx) dst[c + kx] = __uint_as_float(v[kx]);
+              for (int c = 0; c < DJ; ++c) dst[g * DJ + c] = __uint_as_float(vi[c]) + __uint_as_float(vh[c]);
+            } else {       // n keeps them apart: n = tanh(i_n + r * h_n)
+#pragma unroll
+              for (int c = 0; c < DJ; ++c) {
+                dst[2 * DJ + c] = __uint_as_float(vi[c]);
+                dst[3 * DJ + c] = __uint_as_float(vh[c]);
+              }
+            }
           }
         }
       }
@@ -325,9 +340,9 @@ __global__ void __launch_bounds__(192, 1) gru_wave_bwd_kernel(const __grid_const
   constexpr int ACC_LD = NC + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int d = p.d, L = p.L, R = p.R, n_slots = p.n_slots, nl = p.nl;
-  const int nkc = 3 * d / GW_BK;
-  const int slot_bytes = R * 128;
+  const int d = p.d, L = p.L, R = p.R, n_slots = p.n_groups, C = p.C, nl = p.nl;
+  const int nkc = 3 * d / GW_BK, gpp = nkc / C;
+  const int chunk_bytes = R * 128, slot_bytes = C * chunk_bytes;
   const int w_bytes = 3 * DJ * d * 2;
   uint8_t* whh_sm = smem;               // rows j0.. of W_hh^k^T     [DJ x 3d]
   uint8_t* wih_sm = smem + w_bytes;     // rows j0.. of W_ih^{k+1}^T [DJ x 3d]
@@ -389,22 +404,22 @@ __global__ void __launch_bounds__(192, 1) gru_wave_bwd_kernel(const __grid_const
           wait_counter(above_sync, (done + 1) * ns);     // every slice of dgi^{k+1}_t is in global memory
           asm volatile("fence.proxy.async;" ::: "memory");
           const int row0 = p.off[t] + m0;
-          for (int kc = 0; kc < nkc; ++kc, ++it) {
+          for (int g = 0; g < gpp; ++g, ++it) {
             const int s = it % n_slots;
             ptx::mbar_wait(&empty_bar[s], ((it / n_slots) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)slot_bytes);
-            ptx::tma_load_2d(a_sm + s * slot_bytes, tmA1, &full_bar[s], kc * GW_BK, row0);
+            ptx::tma_load_3d(a_sm + s * slot_bytes, tmA1, &full_bar[s], 0, row0, g * C);
           }
         }
         if (has_rec(t)) {
           wait_counter(my_sync, done * ns);              // every slice of dgh^k_{t+1} is in global memory
           asm volatile("fence.proxy.async;" ::: "memory");
           const int row0 = p.off[t + 1] + m0;
-          for (int kc = 0; kc < nkc; ++kc, ++it) {
+          for (int g = 0; g < gpp; ++g, ++it) {
             const int s = it % n_slots;
             ptx::mbar_wait(&empty_bar[s], ((it / n_slots) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)slot_bytes);
-            ptx::tma_load_2d(a_sm + s * slot_bytes, tmA2, &full_bar[s], kc * GW_BK, row0);
+            ptx::tma_load_3d(a_sm + s * slot_bytes, tmA2, &full_bar[s], 0, row0, g * C);
           }
         }
         ++done;
@@ -422,29 +437,35 @@ __global__ void __launch_bounds__(192, 1) gru_wave_bwd_kernel(const __grid_const
         if (!dx && !rec) continue;
         const uint32_t acc = tmem_base + (uint32_t)((n_mma & 1) * NC);
         if (dx) {
-          for (int kc = 0; kc < nkc; ++kc, ++it) {
+          for (int g = 0; g < gpp; ++g, ++it) {
             const int s = it % n_slots;
             ptx::mbar_wait(&full_bar[s], (it / n_slots) & 1);
             ptx::tc_fence_after();
+            for (int c = 0; c < C; ++c) {
+              const int kc = g * C + c;
 #pragma unroll
-            for (int kk = 0; kk < GW_BK / 16; ++kk) {
-              const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + kk * 32, 16, 1024);
-              const uint64_t bdesc = ptx::make_smem_desc_sw128(wih_addr + kc * (DJ * 128) + kk * 32, 16, 1024);
-              ptx::umma_f16(acc + DJ, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < GW_BK / 16; ++kk) {
+                const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + c * chunk_bytes + kk * 32, 16, 1024);
+                const uint64_t bdesc = ptx::make_smem_desc_sw128(wih_addr + kc * (DJ * 128) + kk * 32, 16, 1024);
+                ptx::umma_f16(acc + DJ, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+              }
             }
             ptx::umma_commit(&empty_bar[s]);
           }
         }
         if (rec) {
-          for (int kc = 0; kc < nkc; ++kc, ++it) {
+          for (int g = 0; g < gpp; ++g, ++it) {
             const int s = it % n_slots;
             ptx::mbar_wait(&full_bar[s], (it / n_slots) & 1);
             ptx::tc_fence_after();
+            for (int c = 0; c < C; ++c) {
+              const int kc = g * C + c;
 #pragma unroll
-            for (int kk = 0; kk < GW_BK / 16; ++kk) {
-              const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + kk * 32, 16, 1024);
-              const uint64_t bdesc = ptx::make_smem_desc_sw128(whh_addr + kc * (DJ * 128) + kk * 32, 16, 1024);
-              ptx::umma_f16(acc, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < GW_BK / 16; ++kk) {
+                const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * slot_bytes + c * chunk_bytes + kk * 32, 16, 1024);
+                const uint64_t bdesc = ptx::make_smem_desc_sw128(whh_addr + kc * (DJ * 128) + kk * 32, 16, 1024);
+                ptx::umma_f16(acc, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+              }
             }
             ptx::umma_commit(&empty_bar[s]);
           }
@@ -511,15 +532,13 @@ __global__ void __launch_bounds__(192, 1) gru_wave_bwd_kernel(const __grid_const
         if (m0 + q * 32 < Bt) {
           const int row = q * 32 + lane;
           float* dst = acc_sm + row * ACC_LD;
+          uint32_t v[NC];
 #pragma unroll
-          for (int c = 0; c < NC; c += 16) {
-            uint32_t v[16];
-            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
-            ptx::tmem_ld_wait();
-            if (row < R) {
+          for (int c = 0; c < NC; c += 16) ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v + c);
+          ptx::tmem_ld_wait();
+          if (row < R) {
 #pragma unroll
-              for (int kx = 0; kx < 16; ++kx) dst[c + kx] = __uint_as_float(v[kx]);
-            }
+            for (int c = 0; c < NC; ++c) dst[c] = __uint_as_float(v[c]);
           }
         }
         ptx::tc_fence_before();
@@ -586,7 +605,7 @@ __global__ void __launch_bounds__(192, 1) gru_wave_bwd_kernel(const __grid_const
 
 // ---------------------------------------------------------------------------------------------- host
 struct WavePlan {
-  int dj, R, n_slots, smem;
+  int dj, R, n_groups, C, smem;
 };
 
 static int round_rows(int64_t bt0) {
@@ -596,7 +615,9 @@ static int round_rows(int64_t bt0) {
   return r;
 }
 
-// chunks one step streams through the ring (both phases): forward 2*d/64, backward 2*3d/64
+// One phase of a step streams nkc k-chunks of [R x 64] through the ring (forward nkc = d/64, backward 3d/64; two
+// phases per step).  A ring group = C chunks loaded by ONE TMA op; pick the largest C (a divisor of nkc) that still
+// leaves >= 2 groups in shared memory.
 static bool plan_wave(int64_t d, int64_t bt0, int64_t nl, bool bwd, WavePlan* out) {
   if (d % 64 != 0 || d < 64 || bt0 <= 0 || nl < 1 || nl > GW_MAXL) return false;
   const int64_t nbt = (bt0 + 127) / 128;
@@ -609,23 +630,23 @@ static bool plan_wave(int64_t d, int64_t bt0, int64_t nl, bool bwd, WavePlan* ou
     const int64_t w = 2LL * 3 * dj * d * 2;
     const int nc = bwd ? 2 * dj : 4 * dj;
     const int64_t fixed = w + (int64_t)R * (nc + 1) * 4 + 4 * dj * 4 + 2048 + 1024;   // weights, acc, bias, barriers, align
-    const int64_t tail = (int64_t)(128 - R) * 128;
-    const int64_t per_step = (bwd ? 6 : 2) * (d / 64);
-    int64_t slots = per_step + per_step / 2;                 // 1.5 steps in flight when it fits
-    if (slots > 48) slots = 48;
-    if (slots < 4) slots = 4;
-    while (slots >= 4) {
-      const int64_t ring = slots * R * 128;
-      // the overshoot of the last slot's UMMA lands in acc/bias/barriers: make sure the ALLOCATION covers it
-      int64_t total = fixed + ring;
-      const int64_t need_end = w + ring + tail + 1024;
+    const int64_t tail = (int64_t)(128 - R) * 128;     // the last chunk's UMMA reads 128 rows
+    const int nkc = (int)((bwd ? 3 : 1) * (d / 64));
+    for (int C = nkc; C >= 1; --C) {
+      if (nkc % C || C > 256) continue;
+      const int64_t group = (int64_t)C * R * 128;
+      int64_t n = (227 * 1024 - fixed - tail - 1024) / group;
+      const int64_t want = 3 * (nkc / C);              // 1.5 steps in flight is plenty
+      if (n > want) n = want;
+      if (n > 32) n = 32;
+      if (n < 2) continue;
+      int64_t total = fixed + n * group;
+      const int64_t need_end = w + n * group + tail + 1024;   // allocation must cover the overshoot
       if (total < need_end) total = need_end;
-      total += (int64_t)slots * 16;
-      if (total <= 227 * 1024) {
-        out->dj = dj; out->R = R; out->n_slots = (int)slots; out->smem = (int)total;
-        return true;
-      }
-      --slots;
+      total += n * 16;
+      if (total > 227 * 1024) continue;
+      out->dj = dj; out->R = R; out->n_groups = (int)n; out->C = C; out->smem = (int)total;
+      return true;
     }
   }
   return false;
@@ -683,8 +704,8 @@ extern "C" int ark_gru_wave_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t* o
   const int64_t LS = N * d;
   for (int k = 0; k < nl; ++k) {
     const uint16_t* u = k == 0 ? x_b : out_b + (int64_t)(k - 1) * LS;
-    if ((rc = make_tmap_2d_bf16(&prm.tmU[k], u, (uint64_t)d, (uint64_t)N, (uint64_t)d, GW_BK, pl.R))) return rc;
-    if ((rc = make_tmap_2d_bf16(&prm.tmH[k], hp_b + (int64_t)k * LS, (uint64_t)d, (uint64_t)N, (uint64_t)d, GW_BK, pl.R)))
+    if ((rc = make_tmap_kchunked_bf16(&prm.tmU[k], u, (uint64_t)d, (uint64_t)N, (uint64_t)d, pl.R, pl.C))) return rc;
+    if ((rc = make_tmap_kchunked_bf16(&prm.tmH[k], hp_b + (int64_t)k * LS, (uint64_t)d, (uint64_t)N, (uint64_t)d, pl.R, pl.C)))
       return rc;
     ARK_REQUIRE(Wih_b[k] && Whh_b[k] && b_ih[k] && b_hh[k], ARK_E_BADARG, "gru_wave_fwd: null weight pointer (layer %d)", k);
     if ((rc = make_tmap_2d_bf16(&prm.tmWih[k], Wih_b[k], (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, GW_BK, pl.dj))) return rc;
@@ -695,7 +716,7 @@ extern "C" int ark_gru_wave_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t* o
   prm.bt = bt_dev; prm.off = off_dev; prm.sync = sync_ws; prm.h0 = h0; prm.hp_b = hp_b; prm.out_b = out_b;
   prm.r = r; prm.z = z; prm.n = n; prm.ghn = ghn; prm.mask = mask; prm.offset_dev = offset_dev;
   prm.seed = seed; prm.offset = offset; prm.drop_stride = (uint64_t)((N * d + 3) / 4); prm.layer_stride = LS;
-  prm.p_drop = p_drop; prm.L = (int)L; prm.d = (int)d; prm.nl = (int)nl; prm.R = pl.R; prm.n_slots = pl.n_slots;
+  prm.p_drop = p_drop; prm.L = (int)L; prm.d = (int)d; prm.nl = (int)nl; prm.R = pl.R; prm.n_groups = pl.n_groups; prm.C = pl.C;
   dim3 grid((unsigned)(d / pl.dj), (unsigned)nbt, (unsigned)nl);
   if (pl.dj == 16) return launch_wave(gru_wave_fwd_kernel<16>, prm, grid, pl.smem, s, "gru_wave_fwd");
   return launch_wave(gru_wave_fwd_kernel<32>, prm, grid, pl.smem, s, "gru_wave_fwd");
@@ -729,10 +750,10 @@ extern "C" int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const ui
   int rc;
   const int64_t LS = N * d;
   for (int k = 0; k < nl; ++k) {
-    if ((rc = make_tmap_2d_bf16(&prm.tmDgi[k], dgi_b + (int64_t)k * LS * 3, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d),
-                                GW_BK, pl.R))) return rc;
-    if ((rc = make_tmap_2d_bf16(&prm.tmDgh[k], dgh_b + (int64_t)k * LS * 3, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d),
-                                GW_BK, pl.R))) return rc;
+    if ((rc = make_tmap_kchunked_bf16(&prm.tmDgi[k], dgi_b + (int64_t)k * LS * 3, (uint64_t)(3 * d), (uint64_t)N,
+                                      (uint64_t)(3 * d), pl.R, pl.C))) return rc;
+    if ((rc = make_tmap_kchunked_bf16(&prm.tmDgh[k], dgh_b + (int64_t)k * LS * 3, (uint64_t)(3 * d), (uint64_t)N,
+                                      (uint64_t)(3 * d), pl.R, pl.C))) return rc;
     ARK_REQUIRE(WhhT_b[k] && (k == 0 || WihT_b[k]), ARK_E_BADARG, "gru_wave_bwd: null weight pointer (layer %d)", k);
     if ((rc = make_tmap_2d_bf16(&prm.tmWhhT[k], WhhT_b[k], (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), GW_BK, pl.dj)))
       return rc;
@@ -742,7 +763,7 @@ extern "C" int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const ui
   prm.bt = bt_dev; prm.off = off_dev; prm.sync = sync_ws; prm.dy_top = dy_top; prm.r = r; prm.z = z; prm.n = n;
   prm.ghn = ghn; prm.hp_b = hp_b; prm.mask = (p_drop > 0.f) ? mask : nullptr; prm.dgi_b = dgi_b; prm.dgh_b = dgh_b;
   prm.dh0 = dh0; prm.layer_stride = LS; prm.p_drop = p_drop; prm.L = (int)L; prm.d = (int)d; prm.nl = (int)nl;
-  prm.R = pl.R; prm.n_slots = pl.n_slots;
+  prm.R = pl.R; prm.n_groups = pl.n_groups; prm.C = pl.C;
   dim3 grid((unsigned)(d / pl.dj), (unsigned)nbt, (unsigned)nl);
   if (pl.dj == 16) return launch_wave(gru_wave_bwd_kernel<16>, prm, grid, pl.smem, s, "gru_wave_bwd");
   return launch_wave(gru_wave_bwd_kernel<32>, prm, grid, pl.smem, s, "gru_wave_bwd");

@@ -11,4 +11,10 @@ namespace ark {
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                       uint32_t box_inner, uint32_t box_outer);
 
+// The same [rows, K] bf16 matrix seen as K/64 chunks of 64 elements: dims {64, rows, K/64}; one TMA op with box
+// {64, box_rows, box_chunks} lands box_chunks consecutive 128B-swizzled [box_rows x 128 B] slabs in shared memory
+// (the K-major UMMA operand layout), so a whole K panel costs ONE bulk-tensor instruction and ONE mbarrier.
+int make_tmap_kchunked_bf16(CUtensorMap* out, const void* base, uint64_t K, uint64_t rows, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_chunks);
+
 }  // namespace ark
