@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libarkb200.so")
 # enums mirrored from the header
 F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
-EPI_NONE, EPI_GELU, EPI_TANH = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_TANH, EPI_RELU = 0, 1, 2, 3
 
 _SCALARS = {
     "int": ctypes.c_int, "int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "uint64_t": ctypes.c_uint64,

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
       if (aux) aux[m * ldc + n] = v;
       if (epilogue == ARK_EPI_GELU) v = gelu_erf(v);
       else if (epilogue == ARK_EPI_TANH) v = tanhf(v);
+      else if (epilogue == ARK_EPI_RELU) v = fmaxf(v, 0.f);
       if (c_bf16) {
         reinterpret_cast<uint16_t*>(C)[m * ldc + n] = f32_to_bf16_bits(v);
       } else {
@@ -125,7 +126,7 @@ extern "C" int ark_gemm_simt(const void* A, int a_major, int64_t lda, const void
               ARK_E_BADARG, "gemm_simt: leading dimension too small");
   ARK_REQUIRE(c_dtype == ARK_F32 || c_dtype == ARK_BF16, ARK_E_BADARG, "gemm_simt: bad c_dtype");
   ARK_REQUIRE(!(accumulate && c_dtype != ARK_F32), ARK_E_BADARG, "gemm_simt: accumulate needs f32 C");
-  ARK_REQUIRE(epilogue >= ARK_EPI_NONE && epilogue <= ARK_EPI_TANH, ARK_E_BADARG, "gemm_simt: bad epilogue");
+  ARK_REQUIRE(epilogue >= ARK_EPI_NONE && epilogue <= ARK_EPI_RELU, ARK_E_BADARG, "gemm_simt: bad epilogue");
   if (M == 0 || N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (ab_dtype == ARK_F32)

@@ -42,6 +42,7 @@ struct TcSmem {
 __device__ __forceinline__ float apply_act(float v, int epilogue) {
   if (epilogue == ARK_EPI_GELU) return gelu_erf(v);
   if (epilogue == ARK_EPI_TANH) return tanhf(v);
+  if (epilogue == ARK_EPI_RELU) return fmaxf(v, 0.f);
   return v;
 }
 
@@ -394,7 +395,7 @@ extern "C" int ark_gemm_bf16_tc(const uint16_t* A, int a_major, int64_t lda, con
   ARK_REQUIRE(C && ldc >= N, ARK_E_BADARG, "gemm_bf16_tc: bad C / ldc");
   ARK_REQUIRE(c_dtype == ARK_F32 || c_dtype == ARK_BF16, ARK_E_BADARG, "gemm_bf16_tc: bad c_dtype");
   ARK_REQUIRE(!(accumulate && c_dtype != ARK_F32), ARK_E_BADARG, "gemm_bf16_tc: accumulate needs f32 C");
-  ARK_REQUIRE(epilogue >= ARK_EPI_NONE && epilogue <= ARK_EPI_TANH, ARK_E_BADARG, "gemm_bf16_tc: bad epilogue");
+  ARK_REQUIRE(epilogue >= ARK_EPI_NONE && epilogue <= ARK_EPI_RELU, ARK_E_BADARG, "gemm_bf16_tc: bad epilogue");
   if (M == 0 || N == 0) return 0;
   const int BN = tc_pick_bn(M, N);
   CUtensorMap tmA, tmB;

@@ -65,3 +65,82 @@ def unpack_rows(packed: torch.Tensor, lay: PackedLayout, B: int, L_full: int, fi
         n, o = int(lay.bt[t]), int(lay.off[t])
         out[perm[:n], t] = packed[o:o + n]
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# t-SAIL: graph-major ragged rows (a graph's rows are contiguous: attention needs all of them together)
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class Segments:
+    lens: np.ndarray        # int32 [B] rows per graph
+    cu: np.ndarray          # int32 [B+1] row offsets
+    sq_off: np.ndarray      # int64 [B+1] prefix sums of lens^2 (offset of the graph's score blocks / H)
+    graph: np.ndarray       # int32 [n_rows] graph of every row
+    n_rows: int
+    n_graphs: int
+    n_max: int
+    sq_total: int
+    cu_dev: torch.Tensor = None
+    sq_dev: torch.Tensor = None
+    graph_dev: torch.Tensor = None
+
+    def to(self, device):
+        self.cu_dev = torch.from_numpy(self.cu).to(device, non_blocking=True)
+        self.sq_dev = torch.from_numpy(self.sq_off).to(device, non_blocking=True)
+        self.graph_dev = torch.from_numpy(self.graph).to(device, non_blocking=True)
+        return self
+
+
+def segments_from_lens(lens) -> Segments:
+    lens = np.asarray(lens, dtype=np.int32)
+    cu = np.zeros(len(lens) + 1, dtype=np.int32)
+    np.cumsum(lens, out=cu[1:])
+    sq = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens.astype(np.int64) ** 2, out=sq[1:])
+    graph = np.repeat(np.arange(len(lens), dtype=np.int32), lens)
+    return Segments(lens=lens, cu=cu, sq_off=sq, graph=graph, n_rows=int(cu[-1]), n_graphs=len(lens),
+                    n_max=int(lens.max()) if len(lens) else 0, sq_total=int(sq[-1]))
+
+
+@dataclass
+class TLayout:
+    """PAD-free batch of the Transformer KG-VAE: encoder rows = real triples, decoder rows = real positions.
+    Exact for loss and gradients: PAD triples are masked keys whose own outputs the masked mean-pool drops
+    (models.py:85-89); PAD decoder positions sit behind the causal mask of every real position and are ignored
+    by the loss (models.py:112, ablation_study.py:65-69)."""
+    enc: Segments
+    dec: Segments
+    idx: np.ndarray         # int32 [N_e, 3] (h, r, t) of the real triples
+    tok: np.ndarray         # int32 [N]  decoder input token
+    pos: np.ndarray         # int32 [N]  position
+    tgt: np.ndarray         # int32 [N]  target token (never PAD)
+    n_tok: int
+    n_triples: int
+    L_pad: int              # seq_len - 1: the reference's (padded) memory length
+    idx_dev: torch.Tensor = None
+    tok_dev: torch.Tensor = None
+    pos_dev: torch.Tensor = None
+    tgt_dev: torch.Tensor = None
+
+    def to(self, device):
+        self.enc.to(device)
+        self.dec.to(device)
+        for k in ("idx", "tok", "pos", "tgt"):
+            setattr(self, k + "_dev", torch.from_numpy(getattr(self, k)).to(device, non_blocking=True))
+        return self
+
+
+def pack_tlayout(triples_cpu: torch.Tensor, seq_cpu: torch.Tensor, pad_rid) -> TLayout:
+    tri, s = triples_cpu.numpy(), seq_cpu.numpy()
+    B, T, _ = tri.shape
+    live = (tri[:, :, 1] != pad_rid) if pad_rid is not None else np.ones((B, T), dtype=bool)
+    idx = np.ascontiguousarray(tri[live].astype(np.int32))
+    enc = segments_from_lens(live.sum(1))
+    L = s.shape[1] - 1
+    lens = (s[:, 1:] != PAD).sum(1).astype(np.int32)
+    m = np.arange(L)[None, :] < lens[:, None]
+    tok = np.ascontiguousarray(s[:, :-1][m].astype(np.int32))
+    tgt = np.ascontiguousarray(s[:, 1:][m].astype(np.int32))
+    pos = np.ascontiguousarray(np.broadcast_to(np.arange(L, dtype=np.int32)[None, :], (B, L))[m])
+    dec = segments_from_lens(lens)
+    return TLayout(enc=enc, dec=dec, idx=idx, tok=tok, pos=pos, tgt=tgt, n_tok=dec.n_rows, n_triples=enc.n_rows, L_pad=L)

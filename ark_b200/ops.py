@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _C
-from ._C import BF16, EPI_GELU, EPI_NONE, EPI_TANH, F32, MAJOR_K, MAJOR_MN  # noqa: F401
+from ._C import BF16, EPI_GELU, EPI_NONE, EPI_RELU, EPI_TANH, F32, MAJOR_K, MAJOR_MN  # noqa: F401
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -298,3 +298,97 @@ def gru_wave_bwd(dy_top, gates, hp_b, mask, p_drop, WhhT, WihT, bt_dev, off_dev,
                   float(p_drop), a_hh, a_ih, _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32), L, bt0, N, d, nl,
                   _ptr(dgi_b, torch.bfloat16), _ptr(dgh_b, torch.bfloat16), _ptr(dh0, torch.float32),
                   _ptr(sync_ws, torch.int32), _stream())
+
+
+# ------------------------------------------------------------------ t-SAIL (Transformer) blocks: csrc/attn_ops.cu
+TOK, SQ = 0, 1
+
+
+def _opnd(t, kind):
+    """(ptr, is_f32, ld) of a bgemm operand; SQ buffers are flat."""
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        raise _C.ArkError("attention operands must be f32 or bf16")
+    return _ptr(t), int(t.dtype == torch.float32), (t.stride(0) if kind == TOK else 0)
+
+
+def attn_bgemm(A, a_kind, a_trans, a_col0, B, b_kind, b_trans, b_col0, C, c_kind, c_col0, seg, H, hd, mode, causal, alpha):
+    """C_p = alpha * A_p . B_p for every (graph, head); `seg` is a layout.Segments (cu, sq_off, n_max)."""
+    ap, af, ald = _opnd(A, a_kind)
+    bp, bfl, bld = _opnd(B, b_kind)
+    cp, cf, cld = _opnd(C, c_kind)
+    _C.lib().call("ark_attn_bgemm", ap, a_kind, int(a_trans), af, ald, a_col0, bp, b_kind, int(b_trans), bfl, bld, b_col0,
+                  cp, c_kind, cf, cld, c_col0, _ptr(seg.cu_dev, torch.int32), _ptr(seg.sq_dev, torch.int64), seg.n_graphs,
+                  seg.n_max, H, hd, mode, int(causal), float(alpha), _stream())
+
+
+def attn_softmax_fwd(S, seg, H, causal, p_drop, seed, offset, offset_dev, P, P_drop):
+    _C.lib().call("ark_attn_softmax_fwd", _ptr(S, torch.float32), _ptr(seg.cu_dev, torch.int32), _ptr(seg.sq_dev, torch.int64),
+                  _ptr(seg.graph_dev, torch.int32), seg.n_rows, H, int(causal), float(p_drop), int(seed), int(offset),
+                  _ptr(offset_dev, torch.int64), _ptr(P, torch.bfloat16), _ptr(P_drop, torch.bfloat16), _stream())
+
+
+def attn_softmax_bwd(P, P_drop, dP, seg, H, causal, p_drop, alpha, dS):
+    _C.lib().call("ark_attn_softmax_bwd", _ptr(P, torch.bfloat16), _ptr(P_drop, torch.bfloat16), _ptr(dP, torch.float32),
+                  _ptr(seg.cu_dev, torch.int32), _ptr(seg.sq_dev, torch.int64), _ptr(seg.graph_dev, torch.int32),
+                  seg.n_rows, H, int(causal), float(p_drop), float(alpha), _ptr(dS, torch.bfloat16), _stream())
+
+
+def add_layernorm_fwd(branch, res, gamma, beta, eps, p_drop, seed, offset, offset_dev, mask, y, y_bf16, mean, rstd):
+    n, D = branch.shape
+    _contig(branch, res, gamma, beta, mask, y, y_bf16, mean, rstd)
+    _C.lib().call("ark_add_layernorm_fwd", _ptr(branch, torch.float32), _ptr(res, torch.float32), _ptr(gamma, torch.float32),
+                  _ptr(beta, torch.float32), n, D, float(eps), float(p_drop), int(seed), int(offset),
+                  _ptr(offset_dev, torch.int64), _ptr(mask, torch.uint8), _ptr(y, torch.float32),
+                  _ptr(y_bf16, torch.bfloat16), _ptr(mean, torch.float32), _ptr(rstd, torch.float32), _stream())
+
+
+def add_layernorm_bwd(dy, s, mean, rstd, gamma, p_drop, mask, d_res, d_branch_f32, d_branch_bf16, dgamma, dbeta):
+    n, D = dy.shape
+    _contig(dy, s, mean, rstd, gamma, mask, d_res, d_branch_f32, d_branch_bf16, dgamma, dbeta)
+    _C.lib().call("ark_add_layernorm_bwd", _ptr(dy, torch.float32), _ptr(s, torch.float32), _ptr(mean, torch.float32),
+                  _ptr(rstd, torch.float32), _ptr(gamma, torch.float32), n, D, float(p_drop), _ptr(mask, torch.uint8),
+                  _ptr(d_res, torch.float32), _ptr(d_branch_f32, torch.float32), _ptr(d_branch_bf16, torch.bfloat16),
+                  _ptr(dgamma, torch.float32), _ptr(dbeta, torch.float32), _stream())
+
+
+def triple_embed_fwd(idx, E, R, X, X_bf16):
+    _contig(idx, E, R, X, X_bf16)
+    _C.lib().call("ark_triple_embed_fwd", _ptr(idx, torch.int32), _ptr(E, torch.float32), _ptr(R, torch.float32),
+                  idx.shape[0], E.shape[1], _ptr(X, torch.float32), _ptr(X_bf16, torch.bfloat16), _stream())
+
+
+def triple_embed_bwd(idx, dX, dE, dR):
+    _contig(idx, dX, dE, dR)
+    _C.lib().call("ark_triple_embed_bwd", _ptr(idx, torch.int32), _ptr(dX, torch.float32), idx.shape[0], dE.shape[1],
+                  _ptr(dE, torch.float32), _ptr(dR, torch.float32), _stream())
+
+
+def embed_sum_fwd(W, P, tok, pos, X, X_bf16):
+    _contig(W, P, tok, pos, X, X_bf16)
+    _C.lib().call("ark_embed_sum_fwd", _ptr(W, torch.float32), _ptr(P, torch.float32), _ptr(tok, torch.int32),
+                  _ptr(pos, torch.int32), tok.numel(), W.shape[1], _ptr(X, torch.float32), _ptr(X_bf16, torch.bfloat16),
+                  _stream())
+
+
+def seg_reduce(X, seg, mean, wts, H, out, out_bf16):
+    _contig(X, wts, out, out_bf16)
+    _C.lib().call("ark_seg_reduce", _ptr(X, torch.float32), _ptr(seg.cu_dev, torch.int32), seg.n_graphs, X.shape[1], int(mean),
+                  _ptr(wts, torch.float32), H, _ptr(out, torch.float32), _ptr(out_bf16, torch.bfloat16), _stream())
+
+
+def seg_broadcast(src, seg, mean, wts, H, out, out_bf16):
+    _contig(src, wts, out, out_bf16)
+    _C.lib().call("ark_seg_broadcast", _ptr(src, torch.float32), _ptr(seg.cu_dev, torch.int32), _ptr(seg.graph_dev, torch.int32),
+                  seg.n_rows, src.shape[1], int(mean), _ptr(wts, torch.float32), H, _ptr(out, torch.float32),
+                  _ptr(out_bf16, torch.bfloat16), _stream())
+
+
+def xattn_weights(n_items, n_keys, p_drop, seed, offset, offset_dev, wts):
+    _C.lib().call("ark_xattn_weights", n_items, n_keys, float(p_drop), int(seed), int(offset), _ptr(offset_dev, torch.int64),
+                  _ptr(wts, torch.float32), _stream())
+
+
+def relu_bwd(d, out, scale, dpre):
+    _contig(d, out, dpre)
+    _C.lib().call("ark_relu_bwd", _ptr(d, torch.float32), _ptr(out, torch.bfloat16), d.numel(), float(scale),
+                  _ptr(dpre, torch.bfloat16), _stream())

@@ -44,7 +44,7 @@ enum { ARK_F32 = 0, ARK_BF16 = 1 };
  * [M,K]); MN-major = the M (or N) index is contiguous, i.e. the operand is stored as [K, M|N]. */
 enum { ARK_MAJOR_K = 0, ARK_MAJOR_MN = 1 };
 /* GEMM epilogues (applied to acc + bias) */
-enum { ARK_EPI_NONE = 0, ARK_EPI_GELU = 1, ARK_EPI_TANH = 2 };
+enum { ARK_EPI_NONE = 0, ARK_EPI_GELU = 1, ARK_EPI_TANH = 2, ARK_EPI_RELU = 3 };
 
 int ark_abi_version(void);
 const char* ark_last_error(void);
@@ -201,6 +201,61 @@ int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const uint16_t* z, 
                      int32_t* sync_ws, void* stream);
 /* out[C,R] = in[R,C]^T (bf16) */
 int ark_transpose_bf16(const uint16_t* in, int64_t R, int64_t C, uint16_t* out, void* stream);
+
+/* ---- K8/K9 + glue: t-SAIL (Transformer encoder/decoder, models.py:66-114) over ragged, PAD-free, graph-major
+ * packed rows: graph b owns rows cu[b]..cu[b+1] (cu int32 [n_graphs+1]); sq_off int64 [n_graphs+1] = prefix sums
+ * of n_b^2; the per-(graph, head) [n_b x n_b] score blocks live at sq_off[b]*H + h*n_b^2 of a packed buffer;
+ * tok_graph int32 [n_tok] = graph of every row.  See ark_b200/csrc/attn_ops.cu.
+ *
+ * ark_attn_bgemm: C_p = alpha * A_p . B_p for every (graph, head) p.  Operand kind 0 (TOK) = the graph's rows of a
+ * token matrix [n_tok, ld], columns col0 + h*hd .. +hd; kind 1 (SQ) = the score block; *_trans views the operand
+ * transposed; *_f32 selects f32 (else bf16).  mode 0: [n x hd].[hd x n] -> SQ (Q.K^T, dO.V^T); mode 1:
+ * [n x n].[n x hd] -> TOK (P.V, P^T.dO, dS.K, dS^T.Q).  causal != 0 skips the never-read upper triangle. */
+int ark_attn_bgemm(const void* A, int a_kind, int a_trans, int a_f32, int64_t a_ld, int64_t a_col0,
+                   const void* B, int b_kind, int b_trans, int b_f32, int64_t b_ld, int64_t b_col0,
+                   void* C, int c_kind, int c_f32, int64_t c_ld, int64_t c_col0, const int32_t* cu,
+                   const int64_t* sq_off, int64_t n_graphs, int64_t n_max, int64_t H, int64_t hd, int mode,
+                   int causal, float alpha, void* stream);
+/* P = softmax over keys (j <= i when causal) of the f32 scores; P_drop = dropout(P) (Philox counter = element
+ * index / 4) when p_drop > 0, else NULL.  Both bf16, zeros above the diagonal. */
+int ark_attn_softmax_fwd(const float* S, const int32_t* cu, const int64_t* sq_off, const int32_t* tok_graph,
+                         int64_t n_tok, int64_t H, int causal, float p_drop, uint64_t seed, uint64_t offset,
+                         const uint64_t* offset_dev, uint16_t* P, uint16_t* P_drop, void* stream);
+/* dS = alpha * P * (dP - sum_j P dP) with dP = dP_drop * keep/(1-p) (keep <=> P_drop != 0) */
+int ark_attn_softmax_bwd(const uint16_t* P, const uint16_t* P_drop, const float* dP, const int32_t* cu,
+                         const int64_t* sq_off, const int32_t* tok_graph, int64_t n_tok, int64_t H, int causal,
+                         float p_drop, float alpha, uint16_t* dS, void* stream);
+/* Post-LN residual block (nn.TransformerEncoderLayer/DecoderLayer, norm_first=False): s = res + dropout(branch),
+ * y = LayerNorm(s)*gamma+beta.  `branch` f32 [n,D] is OVERWRITTEN with s (kept for the backward); mask u8 [n,D]
+ * when p_drop > 0; mean/rstd f32 [n]. */
+int ark_add_layernorm_fwd(float* branch, const float* res, const float* gamma, const float* beta, int64_t n,
+                          int64_t D, float eps, float p_drop, uint64_t seed, uint64_t offset,
+                          const uint64_t* offset_dev, uint8_t* mask, float* y, uint16_t* y_bf16, float* mean,
+                          float* rstd, void* stream);
+/* d_res = ds (f32); d_branch = ds*keep/(1-p) as f32 and/or bf16; dgamma/dbeta are zeroed then accumulated. */
+int ark_add_layernorm_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
+                          const float* gamma, int64_t n, int64_t D, float p_drop, const uint8_t* mask,
+                          float* d_res, float* d_branch_f32, uint16_t* d_branch_bf16, float* dgamma,
+                          float* dbeta, void* stream);
+/* X[r, slot*d..] = (slot==1 ? R : E)[idx[r,slot]] for real triples (idx int32 [n,3]); models.py:80-83 */
+int ark_triple_embed_fwd(const int32_t* idx, const float* E, const float* R, int64_t n, int64_t d, float* X,
+                         uint16_t* X_bf16, void* stream);
+int ark_triple_embed_bwd(const int32_t* idx, const float* dX, int64_t n, int64_t d, float* dE, float* dR,
+                         void* stream);
+/* X[r] = W[tok[r]] + P[pos[r]] (f32 masters; f32 + bf16 outputs); models.py:109-110 */
+int ark_embed_sum_fwd(const float* W, const float* P, const int32_t* tok, const int32_t* pos, int64_t n,
+                      int64_t d, float* X, uint16_t* X_bf16, void* stream);
+/* out[b] = (mean ? 1/n_b : 1) * sum_{r in graph b} w[r, head(col)] * X[r]   (wts f32 [n_tok,H] or NULL) */
+int ark_seg_reduce(const float* X, const int32_t* cu, int64_t n_graphs, int64_t D, int mean, const float* wts,
+                   int64_t H, float* out, uint16_t* out_bf16, void* stream);
+/* out[r] = (mean ? 1/n_b : 1) * w[r, head(col)] * src[graph(r)] */
+int ark_seg_broadcast(const float* src, const int32_t* cu, const int32_t* tok_graph, int64_t n, int64_t D,
+                      int mean, const float* wts, int64_t H, float* out, uint16_t* out_bf16, void* stream);
+/* wts[i] = Binomial(n_keys, 1-p) / ((1-p) n_keys): attention dropout of the collapsed cross-attention */
+int ark_xattn_weights(int64_t n_items, int64_t n_keys, float p_drop, uint64_t seed, uint64_t offset,
+                      const uint64_t* offset_dev, float* wts, void* stream);
+/* dpre = (out > 0) ? d*scale : 0  (ReLU backward; folds the in-place FFN dropout backward) */
+int ark_relu_bwd(const float* d, const uint16_t* out, int64_t n, float scale, uint16_t* dpre, void* stream);
 
 /* ---- elementwise helpers ----
  * dpre = dact * gelu'(pre) (erf form, models.py:37) -> f32 and/or bf16 */

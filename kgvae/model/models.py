@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from ark_b200 import ops
 from ark_b200.elbo import SailEngine
-from ark_b200.layout import PackedLayout, pack_layout
+from ark_b200.layout import PackedLayout, pack_layout, pack_tlayout
 from kgvae.model.utils import canonical_graph_string
 
 K, MN = ops.MAJOR_K, ops.MAJOR_MN
@@ -143,6 +143,42 @@ class AutoRegDecoderGRU(nn.Module):
         return logits.view(Lp, B, -1).transpose(0, 1).contiguous()
 
 
+class AutoRegEncoder(nn.Module):
+    """t-SAIL encoder PARAMETERS (reference: models.py:66-76): same modules, names, shapes and initialisation as
+    the reference so state_dicts interchange; the forward pass lives in ark_b200.tsail (fused ELBO step)."""
+
+    def __init__(self, num_entities, num_relations, d_model, nhead, latent_dim, pad_eid=None, pad_rid=None, n_layers=2):
+        super().__init__()
+        self.pad_rid = pad_rid
+        self.e_emb = nn.Embedding(num_entities, d_model, padding_idx=pad_eid)
+        self.r_emb = nn.Embedding(num_relations, d_model, padding_idx=pad_rid)
+        layer = nn.TransformerEncoderLayer(d_model * 3, nhead, batch_first=True)
+        self.txf = nn.TransformerEncoder(layer, n_layers)
+        self.mu = nn.Linear(d_model * 3, latent_dim)
+        self.logv = nn.Linear(d_model * 3, latent_dim)
+
+    def forward(self, triples):
+        raise NotImplementedError("t-SAIL runs through SAIL.elbo_step / engine().eval_step (fused training and "
+                                  "validation loss); the stand-alone fp32 enc()/dec() inference path is built for the "
+                                  "GRU models only so far")
+
+
+class AutoRegDecoder(nn.Module):
+    """t-SAIL decoder PARAMETERS (reference: models.py:98-106)."""
+
+    def __init__(self, d_model, nhead, num_layers, seq_len, vocab_size, latent_dim):
+        super().__init__()
+        self.tok_emb = nn.Embedding(vocab_size, d_model)
+        self.pos_emb = nn.Embedding(seq_len, d_model)
+        self.z_proj = nn.Linear(latent_dim, d_model)
+        layer = nn.TransformerDecoderLayer(d_model, nhead, batch_first=True)
+        self.txf = nn.TransformerDecoder(layer, num_layers)
+        self.out = nn.Linear(d_model, vocab_size)
+
+    def forward(self, z, tgt):
+        raise NotImplementedError("t-SAIL runs through SAIL.elbo_step / engine().eval_step; see AutoRegEncoder.forward")
+
+
 class _EngineMixin:
     """Plumbing between an nn.Module with the reference's parameters and its fused ark_b200 training engine."""
 
@@ -160,8 +196,21 @@ class _EngineMixin:
     def engine(self, **kw) -> SailEngine:
         """The fused training engine bound to this module (created on first use; the module must be on CUDA)."""
         if self._engine is None:
-            SailEngine(self, **kw)          # attaches itself
+            if self.config["model_type"] == "t-SAIL":
+                from ark_b200.tsail import TSailEngine
+                TSailEngine(self, **kw)     # attaches itself
+            else:
+                SailEngine(self, **kw)      # attaches itself
         return self._engine
+
+    def _make_layout(self, triples, seq):
+        """Host-side PAD-skipping layout of one batch (time-major packed rows for the GRU models, graph-major
+        ragged rows for the Transformer models)."""
+        seq_cpu = seq if not seq.is_cuda else seq.cpu()
+        if self.config["model_type"] == "t-SAIL":
+            tri_cpu = triples if not triples.is_cuda else triples.cpu()
+            return pack_tlayout(tri_cpu, seq_cpu, self.config.get("pad_rid")).to(self.engine().device)
+        return pack_layout(seq_cpu).to(self.engine().device)
 
 
 class SAIL(_EngineMixin, nn.Module):
@@ -181,9 +230,13 @@ class SAIL(_EngineMixin, nn.Module):
                 vocab_size=config["vocab_size"], latent_dim=config["d_latent"],
                 dropout=config.get("dec_dropout", 0.1), tie_weights=config.get("tie_weights", True))
         elif mt == "t-SAIL":
-            raise NotImplementedError(
-                "model_type 't-SAIL' (Transformer encoder/decoder, reference models.py:66-114) is not built yet: "
-                "SURVEY.md §8 priority 2.  Use model_type 'SAIL'.")
+            self.enc = AutoRegEncoder(
+                num_entities=config["n_entities"], num_relations=config["n_relations"], d_model=config["d_model"],
+                nhead=config["n_heads"], latent_dim=config["d_latent"], pad_eid=config.get("pad_eid"),
+                pad_rid=config.get("pad_rid"), n_layers=config.get("n_layers", 2))
+            self.dec = AutoRegDecoder(
+                d_model=config["d_model"], nhead=config["n_heads"], num_layers=config["n_layers"],
+                seq_len=config["seq_len"], vocab_size=config["vocab_size"], latent_dim=config["d_latent"])
         else:
             raise NotImplementedError(f"Unknown model_type: {mt}")
         self._init_engine_slot()
@@ -197,7 +250,7 @@ class SAIL(_EngineMixin, nn.Module):
         models.py:63.  Returns a device tensor [ce, kl] (no host sync)."""
         eng = self.engine()
         if layout is None:
-            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+            layout = self._make_layout(triples, seq)
         triples = triples.to(eng.device, non_blocking=True).contiguous()
         seq = seq.to(eng.device, non_blocking=True).contiguous()
         if eps is None:
@@ -217,7 +270,7 @@ class SAIL(_EngineMixin, nn.Module):
             return out
         eng = self.engine()
         if layout is None:
-            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+            layout = self._make_layout(triples, seq)
         if eps is None:
             eps = torch.randn(triples.shape[0], self.config["d_latent"], device=eng.device)
         return eng.train_step_graphed(triples, seq, layout, eps, float(beta), lr, n_tok_global, batch_global)

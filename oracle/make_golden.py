@@ -244,6 +244,61 @@ def ark_case(name, *, n_ent, n_rel, lo, hi, use_padding, d, nl, B, seed, tie=Tru
     print(f"[golden] ark_{name}: ce={ce.item():.6f} V={lay['vocab_size']} L={lay['seq_len'] - 1}")
 
 
+def tsail_case(name, *, n_ent, n_rel, lo, hi, use_padding, d, dz, heads, nl, B, seed, beta, lengths=None):
+    """Transformer KG-VAE (models.py:66-114) with the ELBO step of ablation_study.py:59-75.  The reference's
+    layers hard-code torch's default dropout 0.1; for an exact fixture every dropout probability of the
+    instantiated reference modules is set to 0 (hyper-parameter change on the live modules, no code change)."""
+    rng = np.random.default_rng(seed)
+    lay = layout_from_reference_rules(n_ent, n_rel, hi, use_padding)
+    graphs = random_graphs(rng, B, n_ent, n_rel, lo, hi)
+    if lengths is not None:
+        graphs = [g[:n] + random_graphs(rng, 1, n_ent, n_rel, max(n - len(g), 0), max(n - len(g), 0))[0]
+                  for g, n in zip(graphs, lengths)]
+    triples, seq = dataset_batch(graphs, lay, use_padding)
+    cfg = dict(lay, model_type="t-SAIL", d_model=d, d_latent=dz, n_heads=heads, n_layers=nl, txf_dropout=0.0)
+    torch.manual_seed(seed)
+    model = ref_models.SAIL(cfg)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    with torch.no_grad():      # LayerNorm affine / biases away from their (1, 0) init so their gradients are exercised
+        for n_, p_ in model.named_parameters():
+            if "norm" in n_ or n_.endswith("bias"):
+                p_.add_(0.1 * torch.randn_like(p_))
+    model.train()
+    torch.manual_seed(1000 + seed)
+    eps = torch.randn(B, dz)
+    torch.manual_seed(1000 + seed)
+    logits, mu, logv = model(triples, seq[:, :-1])
+    ce = F.cross_entropy(logits.reshape(-1, logits.size(-1)), seq[:, 1:].reshape(-1), ignore_index=0)
+    kl = model.kl_mean(mu, logv)
+    loss = ce + beta * kl
+    loss.backward()
+    torch.manual_seed(1000 + seed)
+    z_ref, mu2, logv2 = model.enc(triples)
+    assert torch.equal(z_ref, mu2 + eps * torch.exp(0.5 * logv2)), "eps replay mismatch (dropout consumed RNG?)"
+    arrays = {"triples": triples.numpy(), "seq": seq.numpy(), "eps": eps.numpy(), "beta": np.float64(beta),
+              "mu": mu.detach().numpy(), "logv": logv.detach().numpy(), "logits": logits.detach().numpy(),
+              "ce": np.float64(ce.item()), "kl": np.float64(kl.item()), "loss": np.float64(loss.item())}
+    for k, v in model.state_dict().items():
+        arrays["param::" + k] = v.detach().numpy().copy()
+    for k, p_ in model.named_parameters():
+        arrays["grad::" + k] = p_.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, f"tsail_{name}.npz"), **arrays)
+    with open(os.path.join(OUT, f"tsail_{name}.json"), "w") as f:
+        json.dump({"cfg": cfg}, f)
+    print(f"[golden] tsail_{name}: loss={loss.item():.6f} ce={ce.item():.6f} kl={kl.item():.6f} "
+          f"V={lay['vocab_size']} L={lay['seq_len'] - 1} params={sum(p_.numel() for p_ in model.parameters())}")
+
+
+def tsail_golden():
+    tsail_case("syn", n_ent=11, n_rel=3, lo=3, hi=3, use_padding=False, d=8, dz=6, heads=2, nl=2, B=5, seed=21, beta=0.5)
+    tsail_case("wd", n_ent=23, n_rel=4, lo=1, hi=6, use_padding=True, d=8, dz=8, heads=2, nl=2, B=6, seed=22,
+               beta=0.25, lengths=[6, 1, 3, 4, 2, 6])
+
+
 def ark_golden():
     ark_case("syn", n_ent=11, n_rel=3, lo=3, hi=3, use_padding=False, d=16, nl=3, B=5, seed=11)
     ark_case("wd", n_ent=23, n_rel=4, lo=1, hi=6, use_padding=True, d=16, nl=2, B=6, seed=12)
@@ -252,6 +307,9 @@ def ark_golden():
 if __name__ == "__main__":
     if "--ark-only" in sys.argv:
         ark_golden()
+        sys.exit(0)
+    if "--tsail-only" in sys.argv:
+        tsail_golden()
         sys.exit(0)
     utils_golden()
     sail_case("syn", n_ent=11, n_rel=3, lo=3, hi=3, use_padding=False, d=16, dz=6, nl=3, B=5, seed=1, beta=0.5)
@@ -263,3 +321,4 @@ if __name__ == "__main__":
               beta=0.1, tie=False)
     train_epoch_golden()
     ark_golden()
+    tsail_golden()

@@ -44,3 +44,16 @@ def load_ark_golden(name):
 
 
 ARK_CASES = ["syn", "wd"]
+
+
+def load_tsail_golden(name):
+    """Transformer KG-VAE fixture (oracle/make_golden.py::tsail_case) from the unmodified reference, dropout 0."""
+    arr = dict(np.load(os.path.join(GOLDEN, f"tsail_{name}.npz")))
+    with open(os.path.join(GOLDEN, f"tsail_{name}.json")) as f:
+        meta = json.load(f)
+    params = {k[len("param::"):]: v for k, v in arr.items() if k.startswith("param::")}
+    grads = {k[len("grad::"):]: v for k, v in arr.items() if k.startswith("grad::")}
+    return arr, meta, params, grads
+
+
+TSAIL_CASES = ["syn", "wd"]

@@ -158,3 +158,26 @@ def test_ark_two_adam_steps_and_greedy_match_reference(case):
     if seq.shape[1] < cfg["seq_len"]:
         seq = np.concatenate([seq, np.full((3, cfg["seq_len"] - seq.shape[1]), O.EOS, dtype=np.int64)], axis=1)
     assert seq[:, :cfg["seq_len"]].tolist() == arr["greedy"].tolist()
+
+
+# ---------------------------------------------------------------- Transformer KG-VAE (reference models.py:66-114)
+from conftest import TSAIL_CASES, load_tsail_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("case", TSAIL_CASES)
+def test_tsail_port_matches_reference(case):
+    from oracle import tsail_torch_port as T
+    arr, meta, params, grads = load_tsail_golden(case)
+    losses, g, ex = T.elbo_step(params, meta["cfg"], arr["triples"], arr["seq"], arr["eps"], float(arr["beta"]))
+    np.testing.assert_allclose(ex["mu"], arr["mu"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(ex["logv"], arr["logv"], rtol=2e-4, atol=2e-5)
+    valid = arr["seq"][:, 1:] != 0            # PAD positions of the reference see -inf rows only through fp noise
+    np.testing.assert_allclose(ex["logits"][valid], arr["logits"][valid], rtol=2e-4, atol=5e-5)
+    for k in ("ce", "kl", "loss"):
+        assert abs(losses[k] - float(arr[k])) <= 2e-5 * max(1.0, abs(float(arr[k]))), k
+    for k, ref in grads.items():
+        nr = np.linalg.norm(ref)
+        if nr < 1e-7:           # cross-attention q/k projections: uniform softmax, zero gradient up to round-off
+            assert np.linalg.norm(g[k]) < 1e-6, k
+            continue
+        assert np.linalg.norm(g[k] - ref) / nr < 2e-4, (k, np.linalg.norm(g[k] - ref) / nr)
