@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--impl", default="ark", choices=["ark", "reference"])
     ap.add_argument("--workload", default="syn-types",
                     choices=["syn-paths", "syn-types", "syn-tipr", "wd-movies", "wd-articles"])
+    ap.add_argument("--model", default="SAIL", choices=["SAIL", "t-SAIL", "ARK"],
+                    help="SAIL = the KG-VAE ELBO path (headline); t-SAIL = Transformer KG-VAE; ARK = decoder-only GRU")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the YAML batch_size)")
     ap.add_argument("--dense", action="store_true", help="every graph at max_edges (what the reference pays for)")
     ap.add_argument("--backend", default="tc", choices=["tc", "simt"])
@@ -167,21 +169,25 @@ def main():
         group = torch.distributed.group.WORLD
 
     from ark_b200 import _C
-    from ark_b200.layout import pack_layout
+    from ark_b200.layout import pack_tlayout
     from ark_b200.synthetic import DeviceBatch, model_config
-    from kgvae.model.models import SAIL
+    from kgvae.model.models import ARK, SAIL
 
-    cfg = model_config(args.workload)
+    cfg = model_config(args.workload, model_type=args.model)
+    mt = args.model
     batch = args.batch or cfg["batch_size"]
     torch.manual_seed(0)                       # identical initial weights on every rank
-    model = SAIL(cfg).to(dev)
+    model = (ARK if mt == "ARK" else SAIL)(cfg).to(dev)
     eng = model.engine(lr=1e-3, gemm_backend=args.backend, dist_group=group)
     n_params = sum(p.numel() for p in model.parameters())
 
     NB = 4
     host = make_host_batches(cfg, batch, rank, NB, args.dense)
     dbs = [DeviceBatch(t, s, n, dev, 1234 + 1000 * rank + i) for i, (t, s, n) in enumerate(host)]
-    eps = [b.eps(cfg["d_latent"], dev) for b in dbs]
+    if mt == "t-SAIL":                          # graph-major ragged rows instead of time-major packed rows
+        for b_, (t, s, _) in zip(dbs, host):
+            b_.layout = pack_tlayout(t, s, cfg.get("pad_rid")).to(dev)
+    eps = [b.eps(cfg["d_latent"], dev) if mt != "ARK" else None for b in dbs]
     # global normalisers: the sampler knows every rank's lengths, so no per-step collective
     ntok = torch.tensor([b.layout.n_tok for b in dbs], device=dev, dtype=torch.float64)
     ntri = torch.tensor([b.n_triples for b in dbs], device=dev, dtype=torch.float64)
@@ -197,7 +203,8 @@ def main():
     def step(i, graph=use_graph):
         j = i % NB
         fn = eng.train_step_graphed if graph else eng.train_step
-        return fn(dbs[j].triples, dbs[j].seq, dbs[j].layout, eps[j], beta, n_tok_global=ntok_g[j], batch_global=bg)
+        return fn(dbs[j].triples if mt != "ARK" else None, dbs[j].seq, dbs[j].layout, eps[j], beta if mt != "ARK" else 0.0,
+                  n_tok_global=ntok_g[j], batch_global=bg if mt != "ARK" else None)
 
     def barrier():
         if world > 1:
@@ -233,18 +240,25 @@ def main():
     e2e = None
     if not args.no_e2e:
         pinned = [b.host for b in dbs]
-        h2d = pinned[0][0].numel() * 8 + pinned[0][1].numel() * 8 + (batch + 2 * dbs[0].layout.L) * 4
+        lay0 = dbs[0].layout
+        meta_bytes = (batch + 2 * lay0.L) * 4 if hasattr(lay0, "L") else \
+            (lay0.idx.nbytes + lay0.tok.nbytes * 3 + lay0.enc.cu.nbytes * 2 + lay0.enc.sq_off.nbytes * 2 + lay0.enc.graph.nbytes
+             + lay0.dec.graph.nbytes)
+        h2d = pinned[0][0].numel() * 8 + pinned[0][1].numel() * 8 + meta_bytes
+        def api_step(j):
+            if mt == "ARK":
+                return model.ce_step(pinned[j][1], n_tok_global=ntok_g[j])
+            return model.elbo_step(pinned[j][0], pinned[j][1], beta, n_tok_global=ntok_g[j], batch_global=bg, graph=use_graph)
+
         for i in range(2):
-            model.elbo_step(pinned[i % NB][0], pinned[i % NB][1], beta, n_tok_global=ntok_g[i % NB], batch_global=bg,
-                            graph=use_graph).tolist()
+            api_step(i % NB).tolist()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
         for i in range(args.steps):
             j = i % NB
-            out = model.elbo_step(pinned[j][0], pinned[j][1], beta, n_tok_global=ntok_g[j], batch_global=bg,
-                                  graph=use_graph)
+            out = api_step(j)
             out.tolist()                                    # device->host read of the step's (ce, kl)
         f1.record()
         barrier()
@@ -254,7 +268,8 @@ def main():
             torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
         e2e = {"value": triples_done / (ems.item() / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 8, "ms_per_step": ems.item() / args.steps,
-               "api": "kgvae.model.models.SAIL.elbo_step(triples_cpu, seq_cpu, beta)"}
+               "api": "kgvae.model.models.ARK.ce_step(seq_cpu)" if mt == "ARK" else
+                      "kgvae.model.models.SAIL.elbo_step(triples_cpu, seq_cpu, beta)"}
 
     # ---------------- roofline pass: CUDA events around every op of the same steps (rank 0 reports)
     eng.prof = []
@@ -290,7 +305,7 @@ def main():
                  for t, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and mt == "SAIL":
         from oracle.torch_cpu_port import time_cpu_baseline   # the checker/baseline, never the product
         cpu = time_cpu_baseline(cfg, [(t, s) for t, s, _ in host], [n for _, _, n in host], beta=beta,
                                 budget_s=20.0, max_steps=8)
@@ -307,7 +322,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"autoreg_{args.workload} SAIL", "graphs_per_gpu": batch, "global_batch": bg,
+            "config": {"workload": f"autoreg_{args.workload} {mt}", "graphs_per_gpu": batch, "global_batch": bg,
                        "d_model": cfg["d_model"], "d_latent": cfg["d_latent"], "n_layers": cfg["n_layers"],
                        "vocab_size": cfg["vocab_size"], "seq_len": cfg["seq_len"], "params": n_params,
                        "triples_per_step": triples_done / args.steps, "tokens_per_step_rank0": dbs[0].layout.n_tok,

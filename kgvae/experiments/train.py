@@ -25,7 +25,6 @@ import numpy as np
 import torch
 import yaml
 
-from ark_b200.layout import pack_layout
 from ark_b200.optim import FusedAdam
 from ark_b200.synthetic import DATASET_SHAPES
 from kgvae.model.models import ARK, SAIL
@@ -141,8 +140,8 @@ def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None
     """One epoch of ELBO steps (reference: ablation_study.py:31-88, SAIL branch :59-81).
     Returns (avg_loss, avg_recon, avg_kl, avg_entity_loss) like the reference."""
     mt = config.get("model_type", "ARK")
-    if mt not in ("SAIL", "ARK"):
-        raise NotImplementedError("model_type 'SAIL' and 'ARK' run on the fused path (see DESIGN.md)")
+    if mt not in ("SAIL", "ARK", "t-SAIL"):
+        raise NotImplementedError("model_type 'SAIL', 't-SAIL' and 'ARK' run on the fused path (see DESIGN.md)")
     model.train()
     eng = model.engine()
     eng.stats.zero_()
@@ -168,8 +167,8 @@ def validate(model, dataloader, config, device, b=1.0):
     eng = model.engine()
     acc, n = torch.zeros(2, device=eng.device), 0
     for batch in dataloader:
+        lay = model._make_layout(batch[0], batch[1])
         triples, seq = batch[0].to(eng.device), batch[1].to(eng.device)
-        lay = pack_layout(batch[1]).to(eng.device)
         eps = torch.randn(triples.shape[0], config["d_latent"], device=eng.device) if eng.has_enc else None
         acc += eng.eval_step(triples.contiguous(), seq.contiguous(), lay, eps, b)
         n += 1
@@ -217,10 +216,10 @@ def main(argv=None):
                       UserWarning, stacklevel=2)
 
     model_type = config.get("model_type", "ARK")
-    if model_type not in ("SAIL", "ARK"):
+    if model_type not in ("SAIL", "ARK", "t-SAIL"):
         raise NotImplementedError(
-            f"model_type '{model_type}': this build accelerates the GRU models (SAIL: the KG-VAE ELBO path; ARK: its "
-            "decoder-only sibling).  t-ARK / t-SAIL are the next rows of the scope table (DESIGN.md).")
+            f"model_type '{model_type}': this build accelerates SAIL / t-SAIL (the KG-VAE ELBO path, GRU and "
+            "Transformer variants) and the decoder-only GRU model ARK; t-ARK is not built yet (DESIGN.md).")
 
     train_g, val_g, test_g, (e2i, i2e), (r2i, i2r), (min_edges, max_edges) = load_graphs(config)
     n_ent, n_rel = len(e2i), len(r2i)
@@ -246,7 +245,7 @@ def main(argv=None):
         print(f"Train batches: {len(train_loader)}, Val batches: {len(val_loader)}  world={world}")
 
     torch.manual_seed(0)
-    model = (SAIL if model_type == "SAIL" else ARK)(config).to(device)
+    model = (ARK if model_type == "ARK" else SAIL)(config).to(device)
     optimizer = FusedAdam(model, lr=config["learning_rate"], dist_group=group,
                           bucket_mb=float(config.get("ddp_bucket_mb", 32)))
     scheduler = None
