@@ -22,6 +22,7 @@
 #include "gru_math.cuh"
 #include "gru_dev.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace ark {
 
@@ -63,7 +64,7 @@ struct GpSmem {
 // =====================================================================================================
 // forward
 // =====================================================================================================
-template <int DJ, int STAGES>
+template <int DJ, int STAGES, int CS>
 __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmW,
                                                                  const GruPersistFwdParams p) {
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
     ptx::prefetch_tmap(&tmW);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CS);     // every CTA of the cluster releases the stage (multicast A tile)
     }
     ptx::mbar_init(w_bar, 1);
     ptx::mbar_init(tmem_full_bar, 1);
@@ -105,8 +106,12 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();       // peers' mbarriers exist before any multicast / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr int MC_ROWS = GP_BM / CS;        // rows of the A tile this CTA fetches (and multicasts to its cluster)
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1u);
+  const uint32_t crank = CS > 1 ? ptx::cluster_ctarank() : 0u;
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -125,7 +130,9 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
           const int s = it % STAGES;
           ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[s], GP_A_BYTES);
-          ptx::tma_load_2d(a_sm + s * GP_A_BYTES, &tmA, &full_bar[s], kc * GP_BK, row0);
+          if (CS == 1) ptx::tma_load_2d(a_sm + s * GP_A_BYTES, &tmA, &full_bar[s], kc * GP_BK, row0);
+          else ptx::tma_load_2d_mc(a_sm + s * GP_A_BYTES + crank * (MC_ROWS * 128), &tmA, &full_bar[s], kc * GP_BK,
+                                   row0 + (int)crank * MC_ROWS, MC_MASK);
         }
       }
     }
@@ -147,7 +154,8 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
             const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128) + kk * 32, 16, 1024);
             ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[s]);
+          if (CS == 1) ptx::umma_commit(&empty_bar[s]);
+          else ptx::umma_commit_mc(&empty_bar[s], MC_MASK);
         }
         ptx::umma_commit(tmem_full_bar);
       }
@@ -250,13 +258,14 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();       // no CTA leaves while a peer may still multicast into it
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // =====================================================================================================
 // backward through time
 // =====================================================================================================
-template <int DJ, int STAGES>
+template <int DJ, int STAGES, int CS>
 __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmW,
                                                                  const GruPersistBwdParams p) {
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
     ptx::prefetch_tmap(&tmW);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CS);     // every CTA of the cluster releases the stage (multicast A tile)
     }
     ptx::mbar_init(w_bar, 1);
     ptx::mbar_init(tmem_full_bar, 1);
@@ -298,8 +307,12 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();       // peers' mbarriers exist before any multicast / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr int MC_ROWS = GP_BM / CS;        // rows of the A tile this CTA fetches (and multicasts to its cluster)
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1u);
+  const uint32_t crank = CS > 1 ? ptx::cluster_ctarank() : 0u;
 
   // Iterations t = L-1 .. 0 (cell backward of step t) and t = -1 (gradient of the initial state).
   // Iteration t consumes dgh_{t+1} (if step t+1 had rows in this tile) through the tensor cores.
@@ -322,7 +335,9 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
             const int s = it % STAGES;
             ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[s], GP_A_BYTES);
-            ptx::tma_load_2d(a_sm + s * GP_A_BYTES, &tmA, &full_bar[s], kc * GP_BK, row0);
+            if (CS == 1) ptx::tma_load_2d(a_sm + s * GP_A_BYTES, &tmA, &full_bar[s], kc * GP_BK, row0);
+            else ptx::tma_load_2d_mc(a_sm + s * GP_A_BYTES + crank * (MC_ROWS * 128), &tmA, &full_bar[s], kc * GP_BK,
+                                     row0 + (int)crank * MC_ROWS, MC_MASK);
           }
         }
         ++done;
@@ -346,7 +361,8 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
             const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128) + kk * 32, 16, 1024);
             ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[s]);
+          if (CS == 1) ptx::umma_commit(&empty_bar[s]);
+          else ptx::umma_commit_mc(&empty_bar[s], MC_MASK);
         }
         ptx::umma_commit(tmem_full_bar);
       }
@@ -462,6 +478,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();       // no CTA leaves while a peer may still multicast into it
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -500,14 +517,83 @@ static int pick_dj(int64_t d, int64_t bt0, int* stages_out) {
 
 template <typename Params, typename Kern>
 static int launch_coop(Kern kern, const CUtensorMap& tmA, const CUtensorMap& tmW, const Params& prm, dim3 grid,
-                       int smem, cudaStream_t s, const char* who) {
+                       int smem, cudaStream_t s, const char* who, int cluster) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return fail((int)e, "%s: smem attribute (%d B): %s", who, smem, cudaGetErrorString(e));
-  void* args[] = {(void*)&tmA, (void*)&tmW, (void*)&prm};
-  e = cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(192), args, (size_t)smem, s);
-  if (e != cudaSuccess) return fail((int)e, "%s: cooperative launch grid=(%u,%u): %s", who, grid.x, grid.y, cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = (unsigned)cluster;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = cluster > 1 ? 2 : 1;
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmW, prm);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail((int)e, "%s: cooperative launch grid=(%u,%u) cluster=%d: %s", who, grid.x, grid.y, cluster, cudaGetErrorString(e));
+  }
   count_launch();
   return 0;
+}
+
+// Largest cluster width (4, 2, 1) along the hidden-slice dimension for which ALL clusters of the grid are co-resident
+// (the kernel spins on flags written by other CTAs, so co-residency is a correctness requirement).
+template <typename Kern>
+static int pick_cluster(Kern k4, Kern k2, dim3 grid, int smem) {
+  static int forced = -1;
+  if (forced < 0) {
+    // Default 1 (no clusters): measured on B200 (syn-types, d=1024) the 4-CTA multicast cuts the L2 reads of the A
+    // tile 4x but not the step time — the chain is bound by the latency of the 4-stage ring, not by L2 bandwidth.
+    const char* env = getenv("ARK_GRU_CLUSTER");
+    forced = env ? atoi(env) : 1;
+  }
+  // the answer depends only on (kernel, grid, smem): remember it (the occupancy query costs host time every step)
+  static thread_local struct { const void* k; unsigned gx, gy; int smem, cs; } memo[16];
+  static thread_local int n_memo = 0;
+  for (int i = 0; i < n_memo; ++i)
+    if (memo[i].k == (const void*)k4 && memo[i].gx == grid.x && memo[i].gy == grid.y && memo[i].smem == smem) return memo[i].cs;
+  auto remember = [&](int cs) {
+    if (n_memo < 16) { memo[n_memo].k = (const void*)k4; memo[n_memo].gx = grid.x; memo[n_memo].gy = grid.y; memo[n_memo].smem = smem; memo[n_memo].cs = cs; ++n_memo; }
+    return cs;
+  };
+  const int cand[2] = {4, 2};
+  for (int i = 0; i < 2; ++i) {
+    const int cs = cand[i];
+    if (cs > forced) continue;
+    if (grid.x % cs) continue;
+    Kern k = cs == 4 ? k4 : k2;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) continue;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, k, &cfg);
+    if (qe != cudaSuccess) {
+      if (getenv("ARK_GRU_DEBUG")) fprintf(stderr, "[arkb200] cudaOccupancyMaxActiveClusters(cluster=%d): %s\n", cs, cudaGetErrorString(qe));
+      (void)cudaGetLastError();
+      continue;
+    }
+    if (getenv("ARK_GRU_DEBUG"))
+      fprintf(stderr, "[arkb200] gru_persist grid=(%u,%u) smem=%d cluster=%d: max active clusters %d (need %u)\n", grid.x,
+              grid.y, smem, cs, n, grid.x * grid.y / cs);
+    if ((long long)n * cs >= (long long)grid.x * grid.y) return remember(cs);
+  }
+  return remember(1);
 }
 
 }  // namespace ark
@@ -547,15 +633,20 @@ extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16
   if (e != cudaSuccess) return fail((int)e, "gru_persist_fwd: memset: %s", cudaGetErrorString(e));
   CUtensorMap tmA, tmW;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&tmA, hp_b, (uint64_t)d, (uint64_t)N, (uint64_t)d, GP_BK, GP_BM))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW, Whh_b, (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, GP_BK, dj))) return rc;
   GruPersistFwdParams prm;
   prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.gi = gi; prm.b_hh = b_hh;
   prm.h0 = h0; prm.hp_b = hp_b; prm.y_b = y_b; prm.r = r; prm.z = z; prm.n = n; prm.ghn = ghn;
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
   const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
-#define ARK_GP_FWD(DJ, ST) \
-  if (dj == DJ && stages == ST) return launch_coop(gru_persist_fwd_kernel<DJ, ST>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd")
+#define ARK_GP_FWD(DJ, ST)                                                                                              \
+  if (dj == DJ && stages == ST) {                                                                                       \
+    const int cs = (bt0 >= GP_BM) ? pick_cluster(gru_persist_fwd_kernel<DJ, ST, 4>, gru_persist_fwd_kernel<DJ, ST, 2>, grid, smem) : 1; \
+    if ((rc = make_tmap_2d_bf16(&tmA, hp_b, (uint64_t)d, (uint64_t)N, (uint64_t)d, GP_BK, GP_BM / cs))) return rc;       \
+    if (cs == 4) return launch_coop(gru_persist_fwd_kernel<DJ, ST, 4>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd", 4); \
+    if (cs == 2) return launch_coop(gru_persist_fwd_kernel<DJ, ST, 2>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd", 2); \
+    return launch_coop(gru_persist_fwd_kernel<DJ, ST, 1>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd", 1);          \
+  }
   ARK_GP_FWD(16, 4); ARK_GP_FWD(16, 3); ARK_GP_FWD(16, 2);
   ARK_GP_FWD(32, 4); ARK_GP_FWD(32, 3); ARK_GP_FWD(32, 2);
   ARK_GP_FWD(64, 4); ARK_GP_FWD(64, 3); ARK_GP_FWD(64, 2);
@@ -582,7 +673,6 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
   if (e != cudaSuccess) return fail((int)e, "gru_persist_bwd: memset: %s", cudaGetErrorString(e));
   CUtensorMap tmA, tmW;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&tmA, dgh_b, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d), GP_BK, GP_BM))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW, WhhT_b, (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), GP_BK, dj))) return rc;
   GruPersistBwdParams prm;
   prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.dy = dy; prm.r = r;
@@ -590,8 +680,14 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
   prm.dh0_accumulate = dh0_accumulate;
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
   const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
-#define ARK_GP_BWD(DJ, ST) \
-  if (dj == DJ && stages == ST) return launch_coop(gru_persist_bwd_kernel<DJ, ST>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd")
+#define ARK_GP_BWD(DJ, ST)                                                                                              \
+  if (dj == DJ && stages == ST) {                                                                                       \
+    const int cs = (bt0 >= GP_BM) ? pick_cluster(gru_persist_bwd_kernel<DJ, ST, 4>, gru_persist_bwd_kernel<DJ, ST, 2>, grid, smem) : 1; \
+    if ((rc = make_tmap_2d_bf16(&tmA, dgh_b, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d), GP_BK, GP_BM / cs))) return rc; \
+    if (cs == 4) return launch_coop(gru_persist_bwd_kernel<DJ, ST, 4>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd", 4); \
+    if (cs == 2) return launch_coop(gru_persist_bwd_kernel<DJ, ST, 2>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd", 2); \
+    return launch_coop(gru_persist_bwd_kernel<DJ, ST, 1>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd", 1);          \
+  }
   ARK_GP_BWD(16, 4); ARK_GP_BWD(16, 3); ARK_GP_BWD(16, 2);
   ARK_GP_BWD(32, 4); ARK_GP_BWD(32, 3); ARK_GP_BWD(32, 2);
   ARK_GP_BWD(64, 4); ARK_GP_BWD(64, 3); ARK_GP_BWD(64, 2);

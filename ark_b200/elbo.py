@@ -40,7 +40,7 @@ class SailEngine:
     """
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gemm_backend="tc", dist_group=None,
-                 bucket_mb=32.0, seed=0):
+                 bucket_mb=16.0, seed=0):
         cfg = model.config
         if cfg["model_type"] not in ("SAIL", "ARK"):
             raise NotImplementedError("SailEngine accelerates model_type 'SAIL' (MLP encoder + GRU decoder) and its "
@@ -67,7 +67,8 @@ class SailEngine:
         self.group = dist_group
         self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.comm_stream = torch.cuda.Stream(device=dev)   # gradient all-reduce + per-bucket Adam, overlapping backward
+        self._upd = None                 # (mode, lr) while a train step is in flight: buckets are updated as they finish
         self._pending = []
         self.prof = None
         self._capturing = False
@@ -286,8 +287,10 @@ class SailEngine:
                 self._gemm(dgh_all[k], MN, hp_all[k], MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
                 ops.colsum(dgi_all[k], N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
                 ops.colsum(dgh_all[k], N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
-                self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+                if k > 0:
+                    self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
             self._gemm(dgi_all[0], K, self._w("dec.gru.weight_ih_l0"), MN, dy, N, d, d3, tag="gru_dX")
+            self._grad_ready("dec.gru.weight_ih_l0", "dec.gru.bias_hh_l0")    # W_ih^0 was still read by the dX GEMM
         else:
             dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
             if persist:
@@ -366,42 +369,63 @@ class SailEngine:
         self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight")
         return out
 
-    # ------------------------------------------------------------------ data-parallel gradient exchange
+    # ------------------------------------------------------------------ gradient exchange + bucketed update
     def _grad_ready(self, first, last):
-        """Gradient slots first..last (contiguous in the flat layout) are final: under data parallelism,
-        sum them over ranks on the side stream while backward continues (bucketed NCCL all-reduce)."""
-        if self.world == 1:
+        """Gradient slots first..last (contiguous in the flat layout) are final AND their weights are no longer read
+        by the rest of this backward pass.  They are merged into buckets; a full bucket is handed to the side stream,
+        which (data parallel) sums it over ranks with NCCL and (inside a train step) applies Adam to exactly that
+        slice of the flat buffers — both overlap the remaining backward kernels on the main stream."""
+        if self.world == 1 and self._upd is None:
             return
         s, e = self.flat.span(first, last)
         if self._pending and self._pending[-1][1] >= s - 64:
             self._pending[-1] = (self._pending[-1][0], e)
         else:
             self._pending.append((s, e))
-        if self._pending[-1][1] - self._pending[-1][0] >= self.bucket_elems:
+        if sum(b - a for a, b in self._pending) >= self.bucket_elems:
             self._flush_bucket()
 
     def _flush_bucket(self):
         if not self._pending:
             return
-        if self._capturing:
-            # graph mode under data parallelism: end the graph segment here; the replay loop all-reduces the
-            # finished gradient slices eagerly on the side stream while the NEXT segment runs (NCCL kernels are
-            # never captured: capturing them next to the cooperative GRU kernels hung at 2 ranks)
-            self._segment_break(self._pending)
-            self._pending = []
+        spans, self._pending = self._pending, []
+        if self._capturing and self.world > 1:
+            # graph mode under data parallelism: end the graph segment here; the replay loop runs the bucket's NCCL
+            # all-reduce and Adam eagerly on the side stream while the NEXT segment runs (NCCL kernels are never
+            # captured: capturing them next to the cooperative GRU kernels hung at 2 ranks)
+            self._segment_break(spans)
             return
-        self._all_reduce_async(self._pending)
-        self._pending = []
+        self._bucket_async(spans)
+
+    def _bucket_async(self, spans, upd=None):
+        """On the side stream, ordered after everything queued on the current stream: all-reduce (world > 1) and,
+        inside a train step, Adam over the slices."""
+        upd = self._upd if upd is None else upd
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm_stream.wait_event(ev)
+        f = self.flat
+        with torch.cuda.stream(self.comm_stream):
+            for (s, e) in spans:
+                if self.world > 1:
+                    torch.distributed.all_reduce(f.grad[s:e], group=self.group)
+                if upd is not None:
+                    with self._timed("adam_flat", nbytes=30.0 * (e - s)):
+                        if upd[0] == "dyn":     # graph replay: lr / bias corrections live in device memory
+                            ops.adam_flat_dyn(f.param[s:e], f.grad[s:e], f.exp_avg[s:e], f.exp_avg_sq[s:e], f.shadow[s:e],
+                                              self.dyn_f, self.betas[0], self.betas[1], self.eps)
+                        else:
+                            ops.adam_flat(f.param[s:e], f.grad[s:e], f.exp_avg[s:e], f.exp_avg_sq[s:e], f.shadow[s:e],
+                                          upd[1], self.betas[0], self.betas[1], self.eps, self.step_count)
 
     def _sync_grads(self):
-        if self.world == 1:
-            return
         self._flush_bucket()
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, lr=None):
-        """Dense Adam over the whole flat buffer (torch.optim.Adam defaults, ablation_study.py:571)."""
+        """Dense Adam over the whole flat buffer (torch.optim.Adam defaults, ablation_study.py:571) — the separate
+        optimizer.step() of the reference's loop.  train_step() instead updates bucket by bucket during backward."""
         self._sync_grads()
         self.step_count += 1
         f = self.flat
@@ -410,32 +434,29 @@ class SailEngine:
                           self.betas[0], self.betas[1], self.eps, self.step_count)
 
     def train_step(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
-        """zero_grad + forward + backward (+ all-reduce) + Adam: ablation_study.py:43,59-76."""
-        out = self.forward_backward(triples, seq, lay, eps, beta, n_tok_global, batch_global, train=True)
-        self.adam_step(lr)
+        """zero_grad + forward + backward (+ all-reduce) + Adam: ablation_study.py:43,59-76.  Adam runs per gradient
+        bucket on the side stream as soon as the bucket is final, overlapping the rest of backward."""
+        self.step_count += 1
+        self._upd = ("host", self.lr if lr is None else float(lr))
+        try:
+            out = self.forward_backward(triples, seq, lay, eps, beta, n_tok_global, batch_global, train=True)
+            self._sync_grads()          # last bucket + join: the next forward must see every updated weight
+        finally:
+            self._upd = None
         self.stats[0:2] += out
         self.stats[2] += 1
         return out
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
-    def _all_reduce_async(self, spans):
-        """Sum gradient slices over ranks on the side stream, ordered after everything queued on this stream."""
-        ev = torch.cuda.Event()
-        ev.record()
-        self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
-            for (s, e) in spans:
-                torch.distributed.all_reduce(self.flat.grad[s:e], group=self.group)
-
     def train_step_graphed(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
         """Same as train_step, but the ~190 launches of the step are captured ONCE per batch layout
         (B, T, per-step row counts, normalisers, beta) into CUDA graphs and replayed: the host cost of a step
         drops to a few small input copies + a handful of graph launches.  Layouts that never repeat (ragged real
         data) should use train_step.
-        Under data parallelism the step is captured as a CHAIN of graph segments cut at the gradient-bucket
-        boundaries; between two segments the replay loop issues that bucket's NCCL all-reduce eagerly on the
-        side stream, so it overlaps the following segment of backward exactly as in the eager step, and Adam
-        (last segment) waits for the side stream."""
+        Single GPU: the per-bucket Adam launches are a parallel branch of the one captured graph.  Under data
+        parallelism the step is captured as a CHAIN of graph segments cut at the gradient-bucket boundaries; between
+        two segments the replay loop issues that bucket's NCCL all-reduce + Adam eagerly on the side stream, so they
+        overlap the following segment of backward exactly as in the eager step."""
         key = (None if triples is None else tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(), float(beta),
                n_tok_global, batch_global)
         ent = self._graphs.get(key)
@@ -472,22 +493,21 @@ class SailEngine:
             n0 = _C.lib().launch_count()
             cap = torch.cuda.Stream(device=dev)
             cap.wait_stream(torch.cuda.current_stream())
-            self._capturing, self._segment_break = True, brk
+            self._capturing, self._segment_break, self._upd = True, brk, ("dyn", None)
             try:
                 with torch.cuda.stream(cap):
                     begin()
                     out = self.forward_backward(st["triples"], st["seq"], st["lay"], st["eps"], beta, n_tok_global,
                                                 batch_global, train=True)
-                    if self.world > 1:
-                        self._flush_bucket()          # the last gradient slices: cut, then Adam in its own segment
-                    f = self.flat
-                    ops.adam_flat_dyn(f.param, f.grad, f.exp_avg, f.exp_avg_sq, f.shadow, self.dyn_f, b1, b2, self.eps)
+                    self._flush_bucket()              # the last gradient slices (world > 1: cuts a segment)
+                    if self.world == 1:
+                        torch.cuda.current_stream().wait_stream(self.comm_stream)    # join the Adam branch
                     self.stats[0:2] += out
                     self.stats[2] += 1
                     cur["g"].capture_end()
                     segs.append((cur["g"], []))
             finally:
-                self._capturing = False
+                self._capturing, self._upd = False, None
             torch.cuda.current_stream().wait_stream(cap)
             st["out"], st["segs"] = out, segs
             st["philox_per_step"] = self._drop_calls * ((lay.n_tok * self.d + 3) // 4)
@@ -500,12 +520,12 @@ class SailEngine:
             ent["seq"].copy_(seq, non_blocking=True)
             ent["lay"].perm_dev.copy_(lay.perm_dev, non_blocking=True)
         segs = ent["segs"]
-        for i, (g, spans) in enumerate(segs):
-            if i == len(segs) - 1 and self.world > 1:
-                torch.cuda.current_stream().wait_stream(self.comm_stream)     # Adam needs the summed gradients
+        for g, spans in segs:
             g.replay()
             if spans:
-                self._all_reduce_async(spans)
+                self._bucket_async(spans, ("dyn", None))
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)     # the next forward needs every updated weight
         self.launches_replayed += ent["n_launch"]
         self.philox_offset += ent["philox_per_step"]
         return ent["out"]

@@ -74,7 +74,7 @@ class TSailEngine(SailEngine):
     """Owns the flat parameters of one t-SAIL module and runs its ELBO step on one GPU (or one rank)."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gemm_backend="tc", dist_group=None,
-                 bucket_mb=32.0, seed=0):
+                 bucket_mb=16.0, seed=0):
         cfg = model.config
         if cfg["model_type"] != "t-SAIL":
             raise NotImplementedError("TSailEngine accelerates model_type 't-SAIL'")
@@ -105,7 +105,8 @@ class TSailEngine(SailEngine):
         self.group = dist_group
         self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self._upd = None
         self._pending = []
         self.prof = None
         self._capturing = False

@@ -264,16 +264,17 @@ class SAIL(_EngineMixin, nn.Module):
                   n_tok_global=None, batch_global=None, graph=False):
         """elbo_backward + the fused Adam update: one full optimisation step (ablation_study.py:43,59-76).
         ``graph=True`` replays a CUDA graph captured per batch layout (fixed-size datasets such as syn-*)."""
-        if not graph:
-            out = self.elbo_backward(triples, seq, beta, eps, layout, n_tok_global, batch_global)
-            self._engine.adam_step(lr)
-            return out
         eng = self.engine()
         if layout is None:
             layout = self._make_layout(triples, seq)
         if eps is None:
             eps = torch.randn(triples.shape[0], self.config["d_latent"], device=eng.device)
-        return eng.train_step_graphed(triples, seq, layout, eps, float(beta), lr, n_tok_global, batch_global)
+        if graph:
+            return eng.train_step_graphed(triples, seq, layout, eps, float(beta), lr, n_tok_global, batch_global)
+        triples = triples.to(eng.device, non_blocking=True).contiguous()
+        seq = seq.to(eng.device, non_blocking=True).contiguous()
+        # eager step: Adam runs bucket by bucket on a side stream while backward is still going
+        return eng.train_step(triples, seq, layout, eps.contiguous(), float(beta), lr, n_tok_global, batch_global)
 
     # ---- reference interface -----------------------------------------------------------------------
     def kl_mean(self, mu, logv):
@@ -423,9 +424,12 @@ class ARK(_EngineMixin, nn.Module):
         return out
 
     def ce_step(self, seq, layout: PackedLayout = None, lr=None, n_tok_global=None):
-        out = self.ce_backward(seq, layout, n_tok_global)
-        self._engine.adam_step(lr)
-        return out
+        """ce_backward + Adam (bucket by bucket, overlapped with backward): one optimisation step."""
+        eng = self.engine()
+        if layout is None:
+            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+        seq = seq.to(eng.device, non_blocking=True).contiguous()
+        return eng.train_step(None, seq, layout, None, 0.0, lr, n_tok_global, None)
 
     @torch.no_grad()
     def generate(self, seq_len, special_tokens, device=None, batch_size=1, beam=1, sample=False, temperature=1.0,
