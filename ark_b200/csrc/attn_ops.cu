@@ -21,7 +21,7 @@ namespace ark {
 // Operand kinds: TOK = rows of a token matrix [N_tok, ld] restricted to graph b and head h's hd columns;
 //                SQ  = the [n_b x n_b] block of (b, h) inside a packed buffer (offset sq_off[b]*H + h*n_b^2).
 // ------------------------------------------------------------------------------------------------
-constexpr int BG_T = 64, BG_K = 16;
+constexpr int BG_K = 16;   // k-step; the output tile BG_T x BG_T (64 / 32 / 16) follows the longest graph of the batch
 
 struct BgOperand {
   const void* ptr;   // bf16 or f32
@@ -49,7 +49,9 @@ __device__ __forceinline__ float bg_load(const void* p, int64_t off, int is_f32)
   return is_f32 ? reinterpret_cast<const float*>(p)[off] : bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(p)[off]);
 }
 
+template <int BG_T>
 __global__ void __launch_bounds__(256) bgemm_kernel(const BgParams p) {
+  constexpr int R = BG_T / 16;   // outputs per thread per dimension
   __shared__ float As[BG_K][BG_T + 1];
   __shared__ float Bs[BG_K][BG_T + 1];
   const int b = blockIdx.z / p.H, h = blockIdx.z % p.H;
@@ -73,38 +75,38 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgParams p) {
     else k_hi = min(K, m0 + BG_T);                     // A(i,j) = P[i,j]: zero for j > i
   }
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
+  float acc[R][R];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
   // loader mapping: the thread's fastest index follows the operand's unit-stride dimension
   const bool a_kfast = (a_cs == 1), b_nfast = (b_cs == 1);
   for (int k0 = k_lo; k0 < k_hi; k0 += BG_K) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = threadIdx.x + 256 * e;              // 0..1023
+    for (int e = 0; e < R; ++e) {
+      const int idx = threadIdx.x + 256 * e;              // 0 .. BG_T*16-1
       int mi, kk;
-      if (a_kfast) { mi = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; mi = idx & 63; }
+      if (a_kfast) { mi = idx >> 4; kk = idx & 15; } else { kk = idx / BG_T; mi = idx % BG_T; }
       const int gm = m0 + mi, gk = k0 + kk;
       As[kk][mi] = (gm < M && gk < k_hi) ? bg_load(p.A.ptr, a_base + gm * a_rs + gk * a_cs, p.A.is_f32) : 0.f;
       int ni, kb;
-      if (b_nfast) { kb = idx >> 6; ni = idx & 63; } else { ni = idx >> 4; kb = idx & 15; }
+      if (b_nfast) { kb = idx / BG_T; ni = idx % BG_T; } else { ni = idx >> 4; kb = idx & 15; }
       const int gn = n0 + ni, gk2 = k0 + kb;
       Bs[kb][ni] = (gn < N && gk2 < k_hi) ? bg_load(p.B.ptr, b_base + gk2 * b_rs + gn * b_cs, p.B.is_f32) : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < BG_K; ++k) {
-      float a[4], bb[4];
+      float a[R], bb[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty + 16 * i];
+      for (int i = 0; i < R; ++i) a[i] = As[k][ty + 16 * i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = Bs[k][tx + 16 * j];
+      for (int j = 0; j < R; ++j) bb[j] = Bs[k][tx + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -112,11 +114,11 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgParams p) {
   if (p.c_kind == 0) { c_base = (int64_t)r0 * p.c_ld + p.c_col0 + h * p.hd; c_rs = p.c_ld; }
   else { c_base = sq_base; c_rs = n; }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < R; ++i) {
     const int m = m0 + ty + 16 * i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < R; ++j) {
       const int nn = n0 + tx + 16 * j;
       if (nn >= N) continue;
       const float v = acc[i][j] * p.alpha;
@@ -502,8 +504,11 @@ extern "C" int ark_attn_bgemm(const void* A, int a_kind, int a_trans, int a_f32,
   p.C = C; p.c_ld = c_ld; p.c_col0 = (int)c_col0; p.c_kind = c_kind; p.c_f32 = c_f32; p.cu = cu; p.sq_off = sq_off;
   p.H = (int)H; p.hd = (int)hd; p.mode = mode; p.causal = causal; p.a_lower = (mode == 1 && a_trans) ? 1 : 0; p.alpha = alpha;
   const int64_t Mx = n_max, Nx = mode == 0 ? n_max : hd;
-  dim3 grid((unsigned)((Nx + BG_T - 1) / BG_T), (unsigned)((Mx + BG_T - 1) / BG_T), (unsigned)(n_graphs * H));
-  bgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  const int tt = n_max <= 16 ? 16 : (n_max <= 32 ? 32 : 64);     // short graphs (syn-*: 3..16 rows): small tiles
+  dim3 grid((unsigned)((Nx + tt - 1) / tt), (unsigned)((Mx + tt - 1) / tt), (unsigned)(n_graphs * H));
+  if (tt == 16) bgemm_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else if (tt == 32) bgemm_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else bgemm_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   return launched("attn_bgemm");
 }
 

@@ -7,66 +7,91 @@
 namespace ark {
 
 // grid (B, 3): CTA (b, slot) pools column block `slot` (head | relation | tail) of graph perm[b].
-// Each thread owns float4 columns c, c+blockDim, ...; triples are read through L1 (broadcast).
+// Threads form a [TY t-lanes] x [CX column lanes] grid: t-lane ty walks triples ty, ty+TY, ... (UNROLL independent
+// 16-byte row loads in flight), column lane tx owns float4 columns tx, tx+CX, ...; the TY partial sums meet in
+// shared memory.  With few graphs per GPU (wd-articles: B = 16, T = 212) the parallelism over triples is what
+// keeps enough loads in flight; triples are read through L1 (broadcast across the column lanes).
+constexpr int GP_MAX_THREADS = 1024;
+
 template <int UNROLL>
-__global__ void __launch_bounds__(256) gather_pool_fwd_kernel(
+__global__ void __launch_bounds__(GP_MAX_THREADS) gather_pool_fwd_kernel(
     const int64_t* __restrict__ triples, const int32_t* __restrict__ perm, const float* __restrict__ E,
-    const float* __restrict__ R, int T, int d, long long pad_rid, float* __restrict__ g,
+    const float* __restrict__ R, int T, int d, long long pad_rid, int CX, float* __restrict__ g,
     uint16_t* __restrict__ g_bf16, float* __restrict__ inv_cnt) {
+  extern __shared__ float4 gp_red[];   // [TY][CX]
+  __shared__ int cnt_s;
   const int b = blockIdx.x, slot = blockIdx.y;
   const int src = perm ? perm[b] : b;
   const int64_t* tri = triples + (int64_t)src * T * 3;
   const float* table = (slot == 1) ? R : E;
   const int d4 = d >> 2;
+  const int tx = threadIdx.x % CX, ty = threadIdx.x / CX, TY = blockDim.x / CX;
 
-  // number of valid triples (uniform over the CTA)
-  int cnt = 0;
-  if (pad_rid >= 0) {
-    for (int t = 0; t < T; ++t) cnt += (tri[t * 3 + 1] != pad_rid);
-  } else {
-    cnt = T;
+  if (threadIdx.x == 0) cnt_s = 0;
+  __syncthreads();
+  if (pad_rid >= 0) {   // number of valid triples: one warp-aggregated atomic per warp
+    int c = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) c += (tri[t * 3 + 1] != pad_rid);
+    c = (int)warp_sum((float)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt_s, c);
+  } else if (threadIdx.x == 0) {
+    cnt_s = T;
   }
+  __syncthreads();
+  const int cnt = cnt_s;
   const float inv = 1.f / (float)(cnt > 0 ? cnt : 1);
   if (slot == 0 && threadIdx.x == 0) inv_cnt[b] = inv;
 
-  for (int c = threadIdx.x; c < d4; c += blockDim.x) {
+  for (int c0 = 0; c0 < d4; c0 += CX) {
+    const int c = c0 + tx;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int t = 0;
-    for (; t + UNROLL <= T; t += UNROLL) {
-      float4 v[UNROLL];
+    if (c < d4) {
+      int t = ty;
+      for (; t + (UNROLL - 1) * TY < T; t += UNROLL * TY) {
+        float4 v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int64_t rel = tri[(t + u) * 3 + 1];
-        const bool ok = (pad_rid < 0) || (rel != pad_rid);
-        const int64_t idx = tri[(t + u) * 3 + slot];
-        v[u] = ok ? __ldg(reinterpret_cast<const float4*>(table + idx * d) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int u = 0; u < UNROLL; ++u) {
+          const int tt = t + u * TY;
+          const bool ok = (pad_rid < 0) || (tri[tt * 3 + 1] != pad_rid);
+          const int64_t idx = tri[tt * 3 + slot];
+          v[u] = ok ? __ldg(reinterpret_cast<const float4*>(table + idx * d) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        for (int u = 0; u < UNROLL; ++u) {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        }
+      }
+      for (; t < T; t += TY) {
+        if (pad_rid >= 0 && tri[t * 3 + 1] == pad_rid) continue;
+        const int64_t idx = tri[t * 3 + slot];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(table + idx * d) + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     }
-    for (; t < T; ++t) {
-      const int64_t rel = tri[t * 3 + 1];
-      if (pad_rid >= 0 && rel == pad_rid) continue;
-      const int64_t idx = tri[t * 3 + slot];
-      const float4 v = __ldg(reinterpret_cast<const float4*>(table + idx * d) + c);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    gp_red[ty * CX + tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < d4) {
+      for (int y = 1; y < TY; ++y) {
+        const float4 v = gp_red[y * CX + tx];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      const int64_t o = (int64_t)b * 3 * d + (int64_t)slot * d + c * 4;
+      if (g) *reinterpret_cast<float4*>(g + o) = acc;
+      if (g_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(acc.x, acc.y);
+        pk.y = pack_bf16x2(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(g_bf16 + o) = pk;
+      }
     }
-    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-    const int64_t o = (int64_t)b * 3 * d + (int64_t)slot * d + c * 4;
-    if (g) *reinterpret_cast<float4*>(g + o) = acc;
-    if (g_bf16) {
-      uint2 p;
-      p.x = pack_bf16x2(acc.x, acc.y);
-      p.y = pack_bf16x2(acc.z, acc.w);
-      *reinterpret_cast<uint2*>(g_bf16 + o) = p;
-    }
+    __syncthreads();
   }
 }
 
-// grid (B, 3): every valid triple of graph perm[b] receives the SAME slice dg[b, slot]/cnt_b, so the
-// value is loaded once into registers and pushed with one 16-byte L2 reduction per (triple, float4).
+// grid (B, 3, Z): every valid triple of graph perm[b] receives the SAME slice dg[b, slot]/cnt_b, so the value is
+// loaded once into registers and pushed with one 16-byte L2 reduction per (triple, float4); the Z CTAs of a
+// (graph, slot) split the triples.
 __global__ void __launch_bounds__(256) gather_pool_bwd_kernel(
     const float* __restrict__ dg, const int64_t* __restrict__ triples, const int32_t* __restrict__ perm,
     const float* __restrict__ inv_cnt, int T, int d, long long pad_rid, long long pad_eid,
@@ -80,7 +105,7 @@ __global__ void __launch_bounds__(256) gather_pool_bwd_kernel(
   for (int c = threadIdx.x; c < d4; c += blockDim.x) {
     float4 v = *reinterpret_cast<const float4*>(dg + (int64_t)b * 3 * d + (int64_t)slot * d + c * 4);
     v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-    for (int t = 0; t < T; ++t) {
+    for (int t = blockIdx.z; t < T; t += gridDim.z) {
       const int64_t rel = tri[t * 3 + 1];
       if (pad_rid >= 0 && rel == pad_rid) continue;
       const int64_t idx = tri[t * 3 + slot];
@@ -155,10 +180,15 @@ extern "C" int ark_gather_pool_fwd(const int64_t* triples, const int32_t* perm, 
   ARK_REQUIRE(d % 4 == 0, ARK_E_SHAPE, "gather_pool_fwd: d=%lld must be a multiple of 4", (long long)d);
   ARK_REQUIRE(aligned16(E) && aligned16(R) && (!g || aligned16(g)) && (!g_bf16 || aligned16(g_bf16)), ARK_E_ALIGN,
               "gather_pool_fwd: tables/outputs must be 16-byte aligned");
-  const int threads = (int)((d / 4 + 31) / 32 * 32 < 256 ? (d / 4 + 31) / 32 * 32 : 256);
+  // column lanes: a warp multiple covering d/4 (at most 128); t-lanes: as many as give ~4 triples per lane
+  const int d4 = (int)(d / 4);
+  const int cx = d4 >= 128 ? 128 : (d4 + 31) / 32 * 32;
+  int ty = (int)((T + 3) / 4);
+  if (ty > GP_MAX_THREADS / cx) ty = GP_MAX_THREADS / cx;
+  if (ty < 1) ty = 1;
   dim3 grid((unsigned)B, 3);
-  gather_pool_fwd_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>(triples, perm, E, R, (int)T, (int)d,
-                                                                      (long long)pad_rid, g, g_bf16, inv_cnt);
+  gather_pool_fwd_kernel<4><<<grid, cx * ty, (size_t)cx * ty * sizeof(float4), (cudaStream_t)stream>>>(
+      triples, perm, E, R, (int)T, (int)d, (long long)pad_rid, cx, g, g_bf16, inv_cnt);
   return launched("gather_pool_fwd");
 }
 
@@ -170,7 +200,12 @@ extern "C" int ark_gather_pool_bwd(const float* dg, const int64_t* triples, cons
   ARK_REQUIRE(d % 4 == 0, ARK_E_SHAPE, "gather_pool_bwd: d must be a multiple of 4");
   ARK_REQUIRE(aligned16(dg) && aligned16(dE) && aligned16(dR), ARK_E_ALIGN, "gather_pool_bwd: 16-byte alignment");
   const int threads = (int)((d / 4 + 31) / 32 * 32 < 256 ? (d / 4 + 31) / 32 * 32 : 256);
-  dim3 grid((unsigned)B, 3);
+  // split the triples of a graph over Z CTAs until the grid has a few waves (B = 16 graphs alone is 48 CTAs)
+  int z = (int)((4 * kNumSMs + 3 * B - 1) / (3 * B));
+  if (z > T) z = (int)T;
+  if (z > 32) z = 32;
+  if (z < 1) z = 1;
+  dim3 grid((unsigned)B, 3, (unsigned)z);
   gather_pool_bwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(dg, triples, perm, inv_cnt, (int)T, (int)d,
                                                                     (long long)pad_rid, (long long)pad_eid, dE, dR);
   return launched("gather_pool_bwd");

@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + BN - 1) / BN;
   const int num_tiles = mt * nt;
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int num_kb_all = (K + TC_BK - 1) / TC_BK;
+  // split-K (one-tile kernel only): blockIdx.y owns k-blocks [kb0, kb0 + num_kb)
+  const int kb0 = PERSIST ? 0 : (int)blockIdx.y * ep.kb_per_split;
+  const int num_kb = PERSIST ? num_kb_all : min(ep.kb_per_split, num_kb_all - kb0);
   const int tile_step = PERSIST ? (int)gridDim.x : num_tiles;   // one-tile kernel: a single trip
   // swap_raster: consecutive tile indices walk the M tiles (A is the smaller operand), so a B tile is fetched
   // once while A stays L2-resident; otherwise they walk the N tiles.
@@ -118,16 +121,16 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < TC_BM / 64; ++j)
-              ptx::tma_load_2d(a_s + j * (TC_BK * 128), &tmA, &full_bar[s], a_row0 + m0 + 64 * j, kb * TC_BK);
+              ptx::tma_load_2d(a_s + j * (TC_BK * 128), &tmA, &full_bar[s], a_row0 + m0 + 64 * j, (kb0 + kb) * TC_BK);
           } else {
-            ptx::tma_load_2d(a_s, &tmA, &full_bar[s], kb * TC_BK, a_row0 + m0);
+            ptx::tma_load_2d(a_s, &tmA, &full_bar[s], (kb0 + kb) * TC_BK, a_row0 + m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              ptx::tma_load_2d(b_s + j * (TC_BK * 128), &tmB, &full_bar[s], b_row0 + n0 + 64 * j, kb * TC_BK);
+              ptx::tma_load_2d(b_s + j * (TC_BK * 128), &tmB, &full_bar[s], b_row0 + n0 + 64 * j, (kb0 + kb) * TC_BK);
           } else {
-            ptx::tma_load_2d(b_s, &tmB, &full_bar[s], kb * TC_BK, b_row0 + n0);
+            ptx::tma_load_2d(b_s, &tmB, &full_bar[s], (kb0 + kb) * TC_BK, b_row0 + n0);
           }
         }
       }
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const int tid = threadIdx.x - 64;
     const bool vec_ok = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
                         (!ep.aux || (reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0);
-    const bool plain = vec_ok && ep.epilogue == ARK_EPI_NONE && !ep.aux && (ep.ldc % 8 == 0);
+    const bool plain = vec_ok && ep.epilogue == ARK_EPI_NONE && !ep.aux && (ep.ldc % 8 == 0) && !ep.atomic;
     constexpr int F4_PER_ROW = BN / 4;
     constexpr int G8_PER_ROW = BN / 8;
     int lt = 0;
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       tile_origin(tile, m0, n0);
       const int acc = PERSIST ? (lt & 1) : 0;
       // bias for the tile's columns: ONE coalesced global load per tile, issued before the MMA wait
-      if (tid < BN) bias_s[tid] = (ep.bias && n0 + tid < N) ? __ldg(ep.bias + n0 + tid) : 0.f;
+      if (tid < BN) bias_s[tid] = (ep.bias && n0 + tid < N && kb0 == 0) ? __ldg(ep.bias + n0 + tid) : 0.f;
       ptx::mbar_wait(&tmem_full_bar[acc], PERSIST ? ((lt >> 1) & 1) : 0);
       ptx::tc_fence_after();
       // Phase 1: raw accumulators TMEM -> smem; all of this warp's loads are in flight before the single wait
@@ -291,7 +294,16 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             }
           } else {
             float* cp = reinterpret_cast<float*>(ep.C) + o;
-            if (v4) {
+            if (ep.atomic) {          // split-K partial sum
+              if (v4) {
+                red_add_v4(cp, w);
+              } else {
+                const float e[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (col + i < N) atomicAdd(cp + i, e[i]);
+              }
+            } else if (v4) {
               float4 x = w;
               if (ep.accumulate) {
                 const float4 old = *reinterpret_cast<const float4*>(cp);
@@ -330,7 +342,23 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiPa
   EpiParams ep2 = ep;
   ep2.swap_raster = (M < N) ? 1 : 0;
   const int64_t tiles = nt * mt;
-  const unsigned grid = (unsigned)(PERSIST ? (tiles < kNumSMs ? tiles : kNumSMs) : tiles);
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  int splits = 1;
+  // split-K: few output tiles, long K (dW = dY^T X of the recurrent / attention weights: M,N = O(d), K = N_tok).
+  // Only for a plain f32 output; C is zeroed (unless accumulating) and the partial sums meet through red.add.
+  if (!PERSIST && !ep.c_bf16 && ep.epilogue == ARK_EPI_NONE && !ep.aux && tiles * 2 <= kNumSMs && num_kb >= 8) {
+    splits = (int)(kNumSMs / tiles);
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits < 1) splits = 1;
+  }
+  ep2.kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + ep2.kb_per_split - 1) / ep2.kb_per_split;
+  ep2.atomic = splits > 1 ? 1 : 0;
+  if (splits > 1 && !ep.accumulate) {
+    cudaError_t e = cudaMemset2DAsync(ep.C, (size_t)ep.ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, s);
+    if (e != cudaSuccess) return fail((int)e, "gemm_bf16_tc: split-K memset: %s", cudaGetErrorString(e));
+  }
+  dim3 grid((unsigned)(PERSIST ? (tiles < kNumSMs ? tiles : kNumSMs) : tiles), (unsigned)splits);
   kern<<<grid, TC_THREADS, L::TOTAL, s>>>(tmA, tmB, ep2, M, N, K, a_row0, b_row0);
   return launched("gemm_bf16_tc");
 }

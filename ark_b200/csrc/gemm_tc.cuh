@@ -14,6 +14,8 @@ struct EpiParams {
   int epilogue;
   int accumulate;
   int swap_raster;   // set by the launcher
+  int kb_per_split;  // set by the launcher: k-blocks per blockIdx.y slice (split-K: partial sums meet through f32 atomics)
+  int atomic;        // set by the launcher: C += via red.global.add (split-K)
 };
 
 int tc_pick_bn(int64_t M, int64_t N);
