@@ -72,31 +72,39 @@ def tsail_param_order(model):
 
 class TSailEngine(SailEngine):
     """Owns the flat parameters of one t-SAIL module and runs its ELBO step on one GPU (or one rank)."""
+    MODEL_TYPE = "t-SAIL"
+
+    @staticmethod
+    def _dropout_from_config(cfg):
+        return float(cfg.get("txf_dropout", 0.1))       # torch default of the reference's layers (models.py:73,104)
+
+    @staticmethod
+    def _param_order(model):
+        return tsail_param_order(model)
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gemm_backend="tc", dist_group=None,
                  bucket_mb=16.0, seed=0):
         cfg = model.config
-        if cfg["model_type"] != "t-SAIL":
-            raise NotImplementedError("TSailEngine accelerates model_type 't-SAIL'")
+        if cfg["model_type"] != self.MODEL_TYPE:
+            raise NotImplementedError(f"{type(self).__name__} accelerates model_type '{self.MODEL_TYPE}'")
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("TSailEngine needs the model on a CUDA device: there is no CPU path")
         self.model, self.cfg, self.device = model, cfg, dev
-        self.has_enc = True
-        self.d, self.dz, self.V = cfg["d_model"], cfg["d_latent"], cfg["vocab_size"]
+        self.has_enc = hasattr(model, "enc")
+        self.d, self.dz, self.V = cfg["d_model"], cfg.get("d_latent", 0), cfg["vocab_size"]
         self.D = 3 * self.d
         self.H = cfg["n_heads"]
-        self.nl_e, self.nl_d = len(model.enc.txf.layers), len(model.dec.txf.layers)
+        self.nl_e = len(model.enc.txf.layers) if self.has_enc else 0
+        self.nl_d = len(model.dec.txf.layers)
         self.nl = self.nl_d
-        self.ff_e = model.enc.txf.layers[0].linear1.out_features
-        self.ff_d = model.dec.txf.layers[0].linear1.out_features
-        self.ln_eps = float(model.enc.txf.layers[0].norm1.eps)
+        self.ln_eps = float(model.dec.txf.layers[0].norm1.eps)
         self.pad_rid, self.pad_eid = cfg.get("pad_rid"), cfg.get("pad_eid")
-        self.tied = False
-        self.p_drop = float(cfg.get("txf_dropout", 0.1))       # torch default of the reference's layers
+        self.tied = model.dec.out.weight is model.dec.tok_emb.weight
+        self.p_drop = self._dropout_from_config(cfg)
         if self.d % 8 or self.D % self.H or self.d % self.H or (self.D // self.H) % 4 or (self.d // self.H) % 4:
-            raise ValueError("t-SAIL needs d_model % 8 == 0 and head widths that are multiples of 4")
-        self.flat = FlatParams(tsail_param_order(model), dev)
+            raise ValueError("the Transformer models need d_model % 8 == 0 and head widths that are multiples of 4")
+        self.flat = FlatParams(self._param_order(model), dev)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.step_count = 0
         self.backend = gemm_backend
@@ -381,3 +389,94 @@ class TSailEngine(SailEngine):
     def train_step_graphed(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
         """The ragged index arrays of a t-SAIL batch change every step: no graph replay yet, eager launches."""
         return self.train_step(triples, seq, lay, eps, beta, lr, n_tok_global, batch_global)
+
+
+# ============================================================================================================
+# t-ARK: decoder-only Transformer (reference models.py:349-366 DecoderOnlyTransformer inside ARK, :368-405)
+# ============================================================================================================
+def tark_param_order(model):
+    named = dict(model.named_parameters())       # the tied dec.out.weight is deduplicated by torch
+    groups = []
+    add = lambda *names: groups.append([(n, named[n]) for n in names])  # noqa: E731
+    add("dec.out.bias")
+    if "dec.out.weight" in named:
+        add("dec.out.weight")
+    for l in range(len(model.dec.txf.layers) - 1, -1, -1):
+        p = f"dec.txf.layers.{l}."
+        for n in ("norm2.weight", "norm2.bias", "linear2.weight", "linear2.bias", "linear1.weight", "linear1.bias",
+                  "norm1.weight", "norm1.bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+                  "self_attn.in_proj_weight", "self_attn.in_proj_bias"):
+            add(p + n)
+    add("dec.tok_emb.weight")
+    add("dec.pos_emb.weight")
+    missing = set(named) - {n for g in groups for n, _ in g}
+    if missing:
+        raise RuntimeError(f"parameters without a slot in the flat layout: {sorted(missing)}")
+    return groups
+
+
+class TArkEngine(TSailEngine):
+    """CE-only step (reference train.py:42-58) of the decoder-only Transformer: tok_emb + pos_emb, n_layers post-LN
+    nn.TransformerEncoderLayer blocks under a causal mask, (tied) vocabulary projection."""
+    MODEL_TYPE = "t-ARK"
+
+    @staticmethod
+    def _dropout_from_config(cfg):
+        return float(cfg.get("dec_dropout", 0.1))        # models.py:353: dropout=dropout
+
+    @staticmethod
+    def _param_order(model):
+        return tark_param_order(model)
+
+    def forward_backward(self, triples, seq, lay: TLayout, eps, beta, n_tok_global=None, batch_global=None,
+                         train=True, stats_out=None):
+        f, dev, d, V, ldv, H = self.flat, self.device, self.d, self.V, self.ldv, self.H
+        bf = torch.bfloat16
+        N = lay.n_tok
+        n_tok_g = float(N if n_tok_global is None else n_tok_global)
+        out = torch.zeros(2, device=dev) if stats_out is None else stats_out
+        p = self.p_drop if train else 0.0
+        new = self._new
+        S = new(lay.dec.sq_total * H)
+        y, y_b = new(N, d), new(N, d, dtype=bf)
+        ops.embed_sum_fwd(f.p("dec.tok_emb.weight"), f.p("dec.pos_emb.weight"), lay.tok_dev, lay.pos_dev, y, y_b)
+        saved = []
+        for l in range(self.nl_d):
+            pre = f"dec.txf.layers.{l}."
+            a, sa = self._self_attn_fwd(y_b, pre + "self_attn.", lay.dec, d, True, S, p)
+            y1, y1_b, ln1 = self._add_ln_fwd(a, y, pre + "norm1.", p)
+            ff, h_b = self._ffn_fwd(y1_b, pre, p)
+            y2, y2_b, ln2 = self._add_ln_fwd(ff, y1, pre + "norm2.", p)
+            saved.append((y_b, sa, ln1, y1_b, h_b, ln2))
+            y, y_b = y2, y2_b
+        logits = new(N, ldv, dtype=bf)
+        w_out = f.s("dec.tok_emb.weight") if self.tied else f.s("dec.out.weight")
+        self._gemm(y_b, K, w_out, K, logits, N, V, d, tag="vocab_fwd", bias=f.p("dec.out.bias"))
+        with self._timed("softmax_ce", nbytes=2.0 * N * V * 2 + 12.0 * N):
+            ops.softmax_ce(logits, V, lay.tgt_dev, 1.0 / n_tok_g, True, out[0:1], None)
+        if not train:
+            return out
+        g_wout = f.g("dec.tok_emb.weight") if self.tied else f.g("dec.out.weight")
+        self._gemm(logits, MN, y_b, MN, g_wout, V, d, N, tag="vocab_dW")
+        ops.colsum(logits, N, V, f.g("dec.out.bias"))
+        dy = new(N, d)
+        self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")
+        del logits
+        self._grad_ready("dec.out.bias", "dec.out.bias" if self.tied else "dec.out.weight")
+        for l in range(self.nl_d - 1, -1, -1):
+            pre = f"dec.txf.layers.{l}."
+            y_in_b, sa, ln1, y1_b, h_b, ln2 = saved[l]
+            d_y1, d_ff_b = self._add_ln_bwd(dy, ln2, pre + "norm2.", p)
+            self._ffn_bwd(d_ff_b, y1_b, h_b, pre, p, d_y1)
+            d_y, d_a_b = self._add_ln_bwd(d_y1, ln1, pre + "norm1.", p)
+            self._self_attn_bwd(d_a_b, y_in_b, sa, pre + "self_attn.", lay.dec, d, True, S, p, d_y)
+            self._grad_ready(pre + "norm2.weight", pre + "self_attn.in_proj_bias")
+            dy = d_y
+        g_tok, g_pos = f.g("dec.tok_emb.weight"), f.g("dec.pos_emb.weight")
+        if not self.tied:
+            g_tok.zero_()
+        g_pos.zero_()
+        ops.tok_scatter_add(dy, lay.tok_dev, g_tok)
+        ops.tok_scatter_add(dy, lay.pos_dev, g_pos)
+        self._grad_ready("dec.tok_emb.weight", "dec.pos_emb.weight")
+        return out

@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--impl", default="ark", choices=["ark", "reference"])
     ap.add_argument("--workload", default="syn-types",
                     choices=["syn-paths", "syn-types", "syn-tipr", "wd-movies", "wd-articles"])
-    ap.add_argument("--model", default="SAIL", choices=["SAIL", "t-SAIL", "ARK"],
+    ap.add_argument("--model", default="SAIL", choices=["SAIL", "t-SAIL", "ARK", "t-ARK"],
                     help="SAIL = the KG-VAE ELBO path (headline); t-SAIL = Transformer KG-VAE; ARK = decoder-only GRU")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the YAML batch_size)")
     ap.add_argument("--dense", action="store_true", help="every graph at max_edges (what the reference pays for)")
@@ -177,17 +177,18 @@ def main():
     mt = args.model
     batch = args.batch or cfg["batch_size"]
     torch.manual_seed(0)                       # identical initial weights on every rank
-    model = (ARK if mt == "ARK" else SAIL)(cfg).to(dev)
+    dec_only = mt in ("ARK", "t-ARK")
+    model = (ARK if dec_only else SAIL)(cfg).to(dev)
     eng = model.engine(lr=1e-3, gemm_backend=args.backend, dist_group=group)
     n_params = sum(p.numel() for p in model.parameters())
 
     NB = 4
     host = make_host_batches(cfg, batch, rank, NB, args.dense)
     dbs = [DeviceBatch(t, s, n, dev, 1234 + 1000 * rank + i) for i, (t, s, n) in enumerate(host)]
-    if mt == "t-SAIL":                          # graph-major ragged rows instead of time-major packed rows
+    if mt in ("t-SAIL", "t-ARK"):               # graph-major ragged rows instead of time-major packed rows
         for b_, (t, s, _) in zip(dbs, host):
             b_.layout = pack_tlayout(t, s, cfg.get("pad_rid")).to(dev)
-    eps = [b.eps(cfg["d_latent"], dev) if mt != "ARK" else None for b in dbs]
+    eps = [b.eps(cfg["d_latent"], dev) if not dec_only else None for b in dbs]
     # global normalisers: the sampler knows every rank's lengths, so no per-step collective
     ntok = torch.tensor([b.layout.n_tok for b in dbs], device=dev, dtype=torch.float64)
     ntri = torch.tensor([b.n_triples for b in dbs], device=dev, dtype=torch.float64)
@@ -203,8 +204,8 @@ def main():
     def step(i, graph=use_graph):
         j = i % NB
         fn = eng.train_step_graphed if graph else eng.train_step
-        return fn(dbs[j].triples if mt != "ARK" else None, dbs[j].seq, dbs[j].layout, eps[j], beta if mt != "ARK" else 0.0,
-                  n_tok_global=ntok_g[j], batch_global=bg if mt != "ARK" else None)
+        return fn(dbs[j].triples if not dec_only else None, dbs[j].seq, dbs[j].layout, eps[j], beta if not dec_only else 0.0,
+                  n_tok_global=ntok_g[j], batch_global=bg if not dec_only else None)
 
     def barrier():
         if world > 1:
@@ -246,7 +247,7 @@ def main():
              + lay0.dec.graph.nbytes)
         h2d = pinned[0][0].numel() * 8 + pinned[0][1].numel() * 8 + meta_bytes
         def api_step(j):
-            if mt == "ARK":
+            if dec_only:
                 return model.ce_step(pinned[j][1], n_tok_global=ntok_g[j])
             return model.elbo_step(pinned[j][0], pinned[j][1], beta, n_tok_global=ntok_g[j], batch_global=bg, graph=use_graph)
 
@@ -268,7 +269,7 @@ def main():
             torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
         e2e = {"value": triples_done / (ems.item() / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 8, "ms_per_step": ems.item() / args.steps,
-               "api": "kgvae.model.models.ARK.ce_step(seq_cpu)" if mt == "ARK" else
+               "api": "kgvae.model.models.ARK.ce_step(seq_cpu)" if dec_only else
                       "kgvae.model.models.SAIL.elbo_step(triples_cpu, seq_cpu, beta)"}
 
     # ---------------- roofline pass: CUDA events around every op of the same steps (rank 0 reports)

@@ -140,8 +140,8 @@ def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None
     """One epoch of ELBO steps (reference: ablation_study.py:31-88, SAIL branch :59-81).
     Returns (avg_loss, avg_recon, avg_kl, avg_entity_loss) like the reference."""
     mt = config.get("model_type", "ARK")
-    if mt not in ("SAIL", "ARK", "t-SAIL"):
-        raise NotImplementedError("model_type 'SAIL', 't-SAIL' and 'ARK' run on the fused path (see DESIGN.md)")
+    if mt not in ("SAIL", "ARK", "t-SAIL", "t-ARK"):
+        raise NotImplementedError(f"unknown model_type {mt!r}")
     model.train()
     eng = model.engine()
     eng.stats.zero_()
@@ -150,7 +150,7 @@ def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None
         ntg = batch[2] if len(batch) > 2 else None
         bg = batch[3] if len(batch) > 3 else None
         optimizer.zero_grad()
-        if mt == "ARK":       # decoder-only: loss = CE, KL = 0 (reference train.py:42-58)
+        if mt in ("ARK", "t-ARK"):       # decoder-only: loss = CE, KL = 0 (reference train.py:42-58)
             model.ce_backward(seq, n_tok_global=ntg)
         else:
             model.elbo_backward(triples, seq, b, eps=None if eps_fn is None else eps_fn(i), n_tok_global=ntg,
@@ -216,10 +216,8 @@ def main(argv=None):
                       UserWarning, stacklevel=2)
 
     model_type = config.get("model_type", "ARK")
-    if model_type not in ("SAIL", "ARK", "t-SAIL"):
-        raise NotImplementedError(
-            f"model_type '{model_type}': this build accelerates SAIL / t-SAIL (the KG-VAE ELBO path, GRU and "
-            "Transformer variants) and the decoder-only GRU model ARK; t-ARK is not built yet (DESIGN.md).")
+    if model_type not in ("SAIL", "ARK", "t-SAIL", "t-ARK"):
+        raise NotImplementedError(f"Unknown model_type: {model_type}")      # reference: models.py:197,390
 
     train_g, val_g, test_g, (e2i, i2e), (r2i, i2r), (min_edges, max_edges) = load_graphs(config)
     n_ent, n_rel = len(e2i), len(r2i)
@@ -245,7 +243,7 @@ def main(argv=None):
         print(f"Train batches: {len(train_loader)}, Val batches: {len(val_loader)}  world={world}")
 
     torch.manual_seed(0)
-    model = (ARK if model_type == "ARK" else SAIL)(config).to(device)
+    model = (ARK if model_type in ("ARK", "t-ARK") else SAIL)(config).to(device)
     optimizer = FusedAdam(model, lr=config["learning_rate"], dist_group=group,
                           bucket_mb=float(config.get("ddp_bucket_mb", 32)))
     scheduler = None

@@ -199,6 +199,9 @@ class _EngineMixin:
             if self.config["model_type"] == "t-SAIL":
                 from ark_b200.tsail import TSailEngine
                 TSailEngine(self, **kw)     # attaches itself
+            elif self.config["model_type"] == "t-ARK":
+                from ark_b200.tsail import TArkEngine
+                TArkEngine(self, **kw)
             else:
                 SailEngine(self, **kw)      # attaches itself
         return self._engine
@@ -207,9 +210,12 @@ class _EngineMixin:
         """Host-side PAD-skipping layout of one batch (time-major packed rows for the GRU models, graph-major
         ragged rows for the Transformer models)."""
         seq_cpu = seq if not seq.is_cuda else seq.cpu()
-        if self.config["model_type"] == "t-SAIL":
-            tri_cpu = triples if not triples.is_cuda else triples.cpu()
-            return pack_tlayout(tri_cpu, seq_cpu, self.config.get("pad_rid")).to(self.engine().device)
+        if self.config["model_type"] in ("t-SAIL", "t-ARK"):
+            if triples is None:     # decoder-only: no encoder rows
+                tri_cpu, pad_rid = torch.zeros(seq_cpu.shape[0], 1, 3, dtype=torch.int64), None
+            else:
+                tri_cpu, pad_rid = (triples if not triples.is_cuda else triples.cpu()), self.config.get("pad_rid")
+            return pack_tlayout(tri_cpu, seq_cpu, pad_rid).to(self.engine().device)
         return pack_layout(seq_cpu).to(self.engine().device)
 
 
@@ -390,6 +396,25 @@ class DecoderOnlyGRU(nn.Module):
         return logits.view(Lp, B, -1).transpose(0, 1).contiguous()
 
 
+class DecoderOnlyTransformer(nn.Module):
+    """t-ARK decoder PARAMETERS (reference: models.py:349-366): same modules / names / init; the fused CE step lives
+    in ark_b200.tsail.TArkEngine."""
+
+    def __init__(self, d_model, nhead, num_layers, seq_len, vocab_size, dropout=0.1, tie_weights=True):
+        super().__init__()
+        self.tok_emb = nn.Embedding(vocab_size, d_model)
+        self.pos_emb = nn.Embedding(seq_len, d_model)
+        layer = nn.TransformerEncoderLayer(d_model, nhead, batch_first=True, dropout=dropout)
+        self.txf = nn.TransformerEncoder(layer, num_layers)
+        self.out = nn.Linear(d_model, vocab_size)
+        if tie_weights and self.out.weight.shape == self.tok_emb.weight.shape:
+            self.out.weight = self.tok_emb.weight
+
+    def forward(self, seq_in):
+        raise NotImplementedError("t-ARK runs through ARK.ce_step / engine().eval_step (fused training and validation "
+                                  "loss); the stand-alone fp32 inference path is built for the GRU models only so far")
+
+
 class ARK(_EngineMixin, nn.Module):
     """Decoder-only autoregressive model — the reference's default ``model_type`` (models.py:368-520).
     Training (``ce_backward`` / ``ce_step``) runs on the same fused engine as SAIL minus the encoder and KL."""
@@ -402,8 +427,10 @@ class ARK(_EngineMixin, nn.Module):
                                       vocab_size=config["vocab_size"], dropout=config.get("dec_dropout", 0.1),
                                       tie_weights=config.get("tie_weights", True))
         elif config["model_type"] == "t-ARK":
-            raise NotImplementedError("model_type 't-ARK' (Transformer decoder, reference models.py:349-366) is not "
-                                      "built yet; use 'ARK' or 'SAIL'")
+            self.dec = DecoderOnlyTransformer(d_model=config["d_model"], nhead=config["n_heads"],
+                                              num_layers=config["n_layers"], seq_len=config["seq_len"],
+                                              vocab_size=config["vocab_size"], dropout=config.get("dec_dropout", 0.1),
+                                              tie_weights=config.get("tie_weights", True))
         else:
             raise NotImplementedError(f"Unknown model_type: {config['model_type']}")
         self._init_engine_slot()
@@ -416,7 +443,7 @@ class ARK(_EngineMixin, nn.Module):
         """Fused CE forward + backward over packed rows (reference train step: train.py:42-58)."""
         eng = self.engine()
         if layout is None:
-            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+            layout = self._make_layout(None, seq)
         seq = seq.to(eng.device, non_blocking=True).contiguous()
         out = eng.forward_backward(None, seq, layout, None, 0.0, n_tok_global, None)
         eng.stats[0:2] += out
@@ -427,7 +454,7 @@ class ARK(_EngineMixin, nn.Module):
         """ce_backward + Adam (bucket by bucket, overlapped with backward): one optimisation step."""
         eng = self.engine()
         if layout is None:
-            layout = pack_layout(seq if not seq.is_cuda else seq.cpu()).to(eng.device)
+            layout = self._make_layout(None, seq)
         seq = seq.to(eng.device, non_blocking=True).contiguous()
         return eng.train_step(None, seq, layout, None, 0.0, lr, n_tok_global, None)
 

@@ -202,15 +202,20 @@ def train_epoch_golden():
     print(f"[golden] train_epoch: {res[:3]}")
 
 
-def ark_case(name, *, n_ent, n_rel, lo, hi, use_padding, d, nl, B, seed, tie=True):
-    """Decoder-only ARK (models.py:323-405) with the CE-only step of train.py:42-58."""
+def ark_case(name, *, n_ent, n_rel, lo, hi, use_padding, d, nl, B, seed, tie=True, model_type="ARK", heads=2):
+    """Decoder-only ARK / t-ARK (models.py:323-405) with the CE-only step of train.py:42-58."""
     rng = np.random.default_rng(seed)
     lay = layout_from_reference_rules(n_ent, n_rel, hi, use_padding)
     graphs = random_graphs(rng, B, n_ent, n_rel, lo, hi)
     triples, seq = dataset_batch(graphs, lay, use_padding)
-    cfg = dict(lay, model_type="ARK", d_model=d, d_latent=4, n_heads=2, n_layers=nl, dec_dropout=0.0, tie_weights=tie)
+    cfg = dict(lay, model_type=model_type, d_model=d, d_latent=4, n_heads=heads, n_layers=nl, dec_dropout=0.0, tie_weights=tie)
     torch.manual_seed(seed)
     model = ref_models.ARK(cfg)
+    if model_type == "t-ARK":
+        with torch.no_grad():   # LayerNorm affine / biases away from (1, 0) so their gradients are exercised
+            for n_, p_ in model.named_parameters():
+                if "norm" in n_ or n_.endswith("bias"):
+                    p_.add_(0.1 * torch.randn_like(p_))
     model.train()
     logits = model(seq[:, :-1])
     ce = F.cross_entropy(logits.reshape(-1, logits.size(-1)), seq[:, 1:].reshape(-1), ignore_index=0)
@@ -238,6 +243,8 @@ def ark_case(name, *, n_ent, n_rel, lo, hi, use_padding, d, nl, B, seed, tie=Tru
         gen = model.generate(lay["seq_len"], lay["special_tokens"], batch_size=3, sample=False)   # greedy
         arrays["greedy"] = gen.numpy()
         arrays["eval_logits_prefix5"] = model(seq[:2, :5]).numpy()
+    if model_type == "t-ARK":      # keep the fixture small: the Adam'd weights are not needed for the Transformer case
+        arrays = {k: v for k, v in arrays.items() if not k.startswith("adam_param::")}
     np.savez_compressed(os.path.join(OUT, f"ark_{name}.npz"), **arrays)
     with open(os.path.join(OUT, f"ark_{name}.json"), "w") as f:
         json.dump({"cfg": cfg, "adam_lr": 1e-2}, f)
@@ -299,6 +306,10 @@ def tsail_golden():
                beta=0.25, lengths=[6, 1, 3, 4, 2, 6])
 
 
+def tark_golden():
+    ark_case("t_wd", n_ent=23, n_rel=4, lo=1, hi=6, use_padding=True, d=16, nl=2, B=6, seed=13, model_type="t-ARK", heads=4)
+
+
 def ark_golden():
     ark_case("syn", n_ent=11, n_rel=3, lo=3, hi=3, use_padding=False, d=16, nl=3, B=5, seed=11)
     ark_case("wd", n_ent=23, n_rel=4, lo=1, hi=6, use_padding=True, d=16, nl=2, B=6, seed=12)
@@ -307,6 +318,9 @@ def ark_golden():
 if __name__ == "__main__":
     if "--ark-only" in sys.argv:
         ark_golden()
+        sys.exit(0)
+    if "--tark-only" in sys.argv:
+        tark_golden()
         sys.exit(0)
     if "--tsail-only" in sys.argv:
         tsail_golden()
@@ -322,3 +336,4 @@ if __name__ == "__main__":
     train_epoch_golden()
     ark_golden()
     tsail_golden()
+    tark_golden()

@@ -104,3 +104,31 @@ def elbo_step(params, cfg, triples, seq, eps, beta, n_tok_global=None, batch_glo
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy() for k, v in p.items()}
     return ({"loss": loss.item(), "ce": ce.item(), "kl": kl.item(), "n_tok": n_tok}, grads,
             {"mu": mu.detach().numpy(), "logv": logv.detach().numpy(), "logits": logits.detach().numpy()})
+
+
+def tark_step(params, cfg, seq, n_tok_global=None, dtype=torch.float64):
+    """Decoder-only Transformer (DecoderOnlyTransformer.forward, models.py:360-365) with the CE-only step of
+    train.py:42-58: tok_emb + pos_emb, post-LN encoder layers under a causal mask, (tied) vocabulary projection."""
+    p = {k: torch.as_tensor(v).to(dtype).clone().requires_grad_(True) for k, v in params.items() if k != "dec.out.weight"}
+    tied = cfg.get("tie_weights", True)
+    if not tied:
+        p["dec.out.weight"] = torch.as_tensor(params["dec.out.weight"]).to(dtype).clone().requires_grad_(True)
+    seq = torch.as_tensor(seq)
+    tgt_in, tgt = seq[:, :-1], seq[:, 1:]
+    B, L = tgt_in.shape
+    x = p["dec.tok_emb.weight"][tgt_in] + p["dec.pos_emb.weight"][torch.arange(L)][None]
+    for l in range(cfg["n_layers"]):
+        pre = f"dec.txf.layers.{l}."
+        x = _ln(x + _mha(p, pre + "self_attn.", x, x, cfg["n_heads"], causal=True), p[pre + "norm1.weight"], p[pre + "norm1.bias"])
+        x = _ln(x + _ffn(p, pre, x), p[pre + "norm2.weight"], p[pre + "norm2.bias"])
+    w_out = p["dec.tok_emb.weight"] if tied else p["dec.out.weight"]
+    logits = x @ w_out.T + p["dec.out.bias"]
+    valid = tgt != 0
+    nll = torch.logsumexp(logits, -1) - logits.gather(-1, tgt.unsqueeze(-1)).squeeze(-1)
+    n_tok = float(valid.sum()) if n_tok_global is None else float(n_tok_global)
+    ce = (nll * valid).sum() / n_tok
+    ce.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy() for k, v in p.items()}
+    if tied:
+        grads["dec.out.weight"] = grads["dec.tok_emb.weight"]
+    return {"loss": ce.item(), "ce": ce.item(), "kl": 0.0, "n_tok": n_tok}, grads, {"logits": logits.detach().numpy()}

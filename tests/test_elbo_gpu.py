@@ -454,3 +454,27 @@ def test_tsail_train_mode_dropout_and_adam_are_sane():
     for _ in range(30):
         last = model.elbo_step(tri_t, seq_t, 1.0, eps=eps)[0].item()
     assert last < first          # the optimiser is learning this batch
+
+
+def test_tark_ce_step_matches_reference_golden_and_port():
+    """Decoder-only Transformer (model_type 't-ARK', reference models.py:349-405): fused CE step vs the unmodified
+    reference (width-16 fixture) and vs the CPU port at width 64 on ragged graphs."""
+    from oracle import tsail_torch_port as T       # the checker
+    arr, meta, params, grads = load_ark_golden("t_wd")
+    model = _ark_from(params, meta["cfg"])
+    ce = model.ce_backward(torch.from_numpy(arr["seq"]))[0].item()
+    assert abs(ce - float(arr["ce"])) <= LOSS_RTOL * abs(float(arr["ce"]))
+    _check_grads(model.engine(), grads, GRAD_REL=6e-2, GRAD_COS=0.998)      # width-16 fixture, ReLU FFN (see t-SAIL)
+    cfg, tri, seq, rng = _random_case(41, nE=200, nR=5, lo=1, hi=9, pad=True, d=64, dz=16, nl=2, B=12)
+    cfg.update(model_type="t-ARK", n_heads=4, dec_dropout=0.0)
+    torch.manual_seed(7)
+    m = ARK(dict(cfg)).to(DEV)
+    p64 = {k: v.detach().double().cpu().numpy() for k, v in m.state_dict().items()}
+    losses, g_ref, _ = T.tark_step(p64, cfg, seq)
+    ce = m.ce_backward(torch.from_numpy(seq))[0].item()
+    assert abs(ce - losses["ce"]) <= LOSS_RTOL * abs(losses["ce"])
+    _check_grads(m.engine(), g_ref, GRAD_REL=TSAIL_GRAD_REL, GRAD_COS=TSAIL_GRAD_COS)
+    first = m.ce_step(torch.from_numpy(seq))[0].item()
+    for _ in range(20):
+        last = m.ce_step(torch.from_numpy(seq))[0].item()
+    assert last < first

@@ -181,3 +181,14 @@ def test_tsail_port_matches_reference(case):
             assert np.linalg.norm(g[k]) < 1e-6, k
             continue
         assert np.linalg.norm(g[k] - ref) / nr < 2e-4, (k, np.linalg.norm(g[k] - ref) / nr)
+
+
+def test_tark_port_matches_reference():
+    from oracle import tsail_torch_port as T
+    arr, meta, params, grads = load_ark_golden("t_wd")
+    losses, g, ex = T.tark_step(params, meta["cfg"], arr["seq"])
+    valid = arr["seq"][:, 1:] != 0
+    np.testing.assert_allclose(ex["logits"][valid], arr["logits"][valid], rtol=2e-4, atol=5e-5)
+    assert abs(losses["ce"] - float(arr["ce"])) <= 2e-5 * abs(float(arr["ce"]))
+    for k, ref in grads.items():
+        assert np.linalg.norm(g[k] - ref) / max(np.linalg.norm(ref), 1e-6) < 2e-4, k
