@@ -115,23 +115,49 @@ __global__ void __launch_bounds__(256) gather_pool_bwd_kernel(
   }
 }
 
+// grid-stride, 4 elements per thread per trip when dz % 4 == 0 (128-bit accesses), ONE atomic per CTA
+template <bool VEC>
 __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(
     const float* __restrict__ heads, int ld_heads, const float* __restrict__ eps, const int32_t* __restrict__ perm,
     int B, int dz, int clamp_logv, float kl_scale, float* __restrict__ z, uint16_t* __restrict__ z_bf16,
     int ld_zb, float* __restrict__ kl_acc) {
   __shared__ float red[33];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int W = VEC ? 4 : 1;
+  const int64_t n = (int64_t)B * dz / W;
   float term = 0.f;
-  if (i < B * dz) {
-    const int b = i / dz, j = i - b * dz;
-    const float mu = heads[(int64_t)b * ld_heads + j];
-    float lv = heads[(int64_t)b * ld_heads + dz + j];
-    if (clamp_logv) lv = fminf(fmaxf(lv, -10.f), 10.f);
-    const float e = eps[(int64_t)(perm ? perm[b] : b) * dz + j];
-    const float zz = fmaf(e, expf(0.5f * lv), mu);
-    z[i] = zz;
-    if (z_bf16) z_bf16[(int64_t)b * ld_zb + j] = f32_to_bf16_bits(zz);
-    term = -0.5f * (1.f + lv - mu * mu - expf(lv));
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q * W;
+    const int b = (int)(i / dz), j = (int)(i - (int64_t)b * dz);
+    float mu[W], lv[W], e[W], zz[W];
+    const float* hp = heads + (int64_t)b * ld_heads + j;
+    const float* ep = eps + (int64_t)(perm ? perm[b] : b) * dz + j;
+    if (VEC) {
+      const float4 a = *reinterpret_cast<const float4*>(hp), c = *reinterpret_cast<const float4*>(hp + dz);
+      const float4 r = *reinterpret_cast<const float4*>(ep);
+      mu[0] = a.x; mu[W > 1 ? 1 : 0] = a.y; mu[W > 2 ? 2 : 0] = a.z; mu[W > 3 ? 3 : 0] = a.w;
+      lv[0] = c.x; lv[W > 1 ? 1 : 0] = c.y; lv[W > 2 ? 2 : 0] = c.z; lv[W > 3 ? 3 : 0] = c.w;
+      e[0] = r.x; e[W > 1 ? 1 : 0] = r.y; e[W > 2 ? 2 : 0] = r.z; e[W > 3 ? 3 : 0] = r.w;
+    } else {
+      mu[0] = hp[0]; lv[0] = hp[dz]; e[0] = ep[0];
+    }
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      if (clamp_logv) lv[k] = fminf(fmaxf(lv[k], -10.f), 10.f);
+      zz[k] = fmaf(e[k], expf(0.5f * lv[k]), mu[k]);
+      term += -0.5f * (1.f + lv[k] - mu[k] * mu[k] - expf(lv[k]));
+    }
+    if (VEC) {
+      *reinterpret_cast<float4*>(z + i) = make_float4(zz[0], zz[W > 1 ? 1 : 0], zz[W > 2 ? 2 : 0], zz[W > 3 ? 3 : 0]);
+      if (z_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(zz[0], zz[W > 1 ? 1 : 0]);
+        pk.y = pack_bf16x2(zz[W > 2 ? 2 : 0], zz[W > 3 ? 3 : 0]);
+        *reinterpret_cast<uint2*>(z_bf16 + (int64_t)b * ld_zb + j) = pk;
+      }
+    } else {
+      z[i] = zz[0];
+      if (z_bf16) z_bf16[(int64_t)b * ld_zb + j] = f32_to_bf16_bits(zz[0]);
+    }
   }
   const float s = block_sum(term, red);
   if (threadIdx.x == 0 && kl_acc) atomicAdd(kl_acc, s * kl_scale);
@@ -217,9 +243,17 @@ extern "C" int ark_reparam_kl_fwd(const float* heads, int64_t ld_heads, const fl
   ARK_REQUIRE(heads && eps && z, ARK_E_BADARG, "reparam_kl_fwd: null pointer");
   ARK_REQUIRE(B > 0 && dz > 0 && ld_heads >= 2 * dz && (!z_bf16 || ld_zb >= dz), ARK_E_BADARG,
               "reparam_kl_fwd: bad sizes");
-  const int n = (int)(B * dz);
-  reparam_kl_fwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      heads, (int)ld_heads, eps, perm, (int)B, (int)dz, clamp_logv, kl_scale, z, z_bf16, (int)ld_zb, kl_acc);
+  const bool vec = dz % 4 == 0 && ld_heads % 4 == 0 && (!z_bf16 || ld_zb % 4 == 0) && aligned16(heads) && aligned16(eps) &&
+                   aligned16(z) && (!z_bf16 || (reinterpret_cast<uintptr_t>(z_bf16) & 7) == 0);
+  const int64_t work = B * dz / (vec ? 4 : 1);
+  int64_t blocks = (work + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (vec)
+    reparam_kl_fwd_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        heads, (int)ld_heads, eps, perm, (int)B, (int)dz, clamp_logv, kl_scale, z, z_bf16, (int)ld_zb, kl_acc);
+  else
+    reparam_kl_fwd_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        heads, (int)ld_heads, eps, perm, (int)B, (int)dz, clamp_logv, kl_scale, z, z_bf16, (int)ld_zb, kl_acc);
   return launched("reparam_kl_fwd");
 }
 

@@ -52,6 +52,7 @@ struct GruWaveFwdParams {
   int64_t layer_stride;        // N * d
   float p_drop;
   int L, d, nl, R, n_groups, C;   // ring of n_groups groups, one TMA op loads C k-chunks
+  int tile0, nbt_total;           // this launch covers batch tiles [tile0, tile0 + gridDim.y) of nbt_total
 };
 
 struct GruWaveBwdParams {
@@ -70,6 +71,7 @@ struct GruWaveBwdParams {
   int64_t layer_stride;         // N * d
   float p_drop;
   int L, d, nl, R, n_groups, C;   // ring of n_groups groups, one TMA op loads C k-chunks
+  int tile0, nbt_total;           // this launch covers batch tiles [tile0, tile0 + gridDim.y) of nbt_total
 };
 
 __device__ __forceinline__ void st_mask4(uint8_t* p, const bool* keep) {
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(192, 1) gru_wave_fwd_kernel(const __grid_const
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ji = blockIdx.x, bi = blockIdx.y, k = blockIdx.z, ns = gridDim.x, nbt = gridDim.y;
+  const int ji = blockIdx.x, bi = blockIdx.y + p.tile0, k = blockIdx.z, ns = gridDim.x, nbt = p.nbt_total;
   const int j0 = ji * DJ, m0 = bi * 128;
   const CUtensorMap* tmU = &p.tmU[k];
   const CUtensorMap* tmH = &p.tmH[k];
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(192, 1) gru_wave_bwd_kernel(const __grid_const
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ji = blockIdx.x, bi = blockIdx.y, k = blockIdx.z, ns = gridDim.x, nbt = gridDim.y;
+  const int ji = blockIdx.x, bi = blockIdx.y + p.tile0, k = blockIdx.z, ns = gridDim.x, nbt = p.nbt_total;
   const int j0 = ji * DJ, m0 = bi * 128;
   const bool top = (k == nl - 1);
   const CUtensorMap* tmA1 = &p.tmDgi[top ? k : k + 1];   // dgi of the layer above
@@ -620,13 +622,12 @@ static int round_rows(int64_t bt0) {
 // leaves >= 2 groups in shared memory.
 static bool plan_wave(int64_t d, int64_t bt0, int64_t nl, bool bwd, WavePlan* out) {
   if (d % 64 != 0 || d < 64 || bt0 <= 0 || nl < 1 || nl > GW_MAXL) return false;
-  const int64_t nbt = (bt0 + 127) / 128;
   const int R = round_rows(bt0);
   const int cand[2] = {16, 32};
   for (int i = 0; i < 2; ++i) {
     const int dj = cand[i];
     if (d % dj) continue;
-    if (nbt * (d / dj) * nl > kNumSMs) continue;
+    if ((d / dj) * nl > kNumSMs) continue;          // one batch tile of every layer must be co-resident
     const int64_t w = 2LL * 3 * dj * d * 2;
     const int nc = bwd ? 2 * dj : 4 * dj;
     const int64_t fixed = w + (int64_t)R * (nc + 1) * 4 + 4 * dj * 4 + 2048 + 1024;   // weights, acc, bias, barriers, align
@@ -717,9 +718,17 @@ extern "C" int ark_gru_wave_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t* o
   prm.r = r; prm.z = z; prm.n = n; prm.ghn = ghn; prm.mask = mask; prm.offset_dev = offset_dev;
   prm.seed = seed; prm.offset = offset; prm.drop_stride = (uint64_t)((N * d + 3) / 4); prm.layer_stride = LS;
   prm.p_drop = p_drop; prm.L = (int)L; prm.d = (int)d; prm.nl = (int)nl; prm.R = pl.R; prm.n_groups = pl.n_groups; prm.C = pl.C;
-  dim3 grid((unsigned)(d / pl.dj), (unsigned)nbt, (unsigned)nl);
-  if (pl.dj == 16) return launch_wave(gru_wave_fwd_kernel<16>, prm, grid, pl.smem, s, "gru_wave_fwd");
-  return launch_wave(gru_wave_fwd_kernel<32>, prm, grid, pl.smem, s, "gru_wave_fwd");
+  // batch tiles are independent: when all of them do not fit the 148 SMs at once, run groups of tiles back to back
+  const int tpl = (int)(kNumSMs / ((d / pl.dj) * nl));
+  prm.nbt_total = nbt;
+  for (int t0 = 0; t0 < nbt; t0 += tpl) {
+    prm.tile0 = t0;
+    dim3 grid((unsigned)(d / pl.dj), (unsigned)(nbt - t0 < tpl ? nbt - t0 : tpl), (unsigned)nl);
+    rc = pl.dj == 16 ? launch_wave(gru_wave_fwd_kernel<16>, prm, grid, pl.smem, s, "gru_wave_fwd")
+                     : launch_wave(gru_wave_fwd_kernel<32>, prm, grid, pl.smem, s, "gru_wave_fwd");
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 extern "C" int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const uint16_t* z, const uint16_t* n,
@@ -764,7 +773,14 @@ extern "C" int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const ui
   prm.ghn = ghn; prm.hp_b = hp_b; prm.mask = (p_drop > 0.f) ? mask : nullptr; prm.dgi_b = dgi_b; prm.dgh_b = dgh_b;
   prm.dh0 = dh0; prm.layer_stride = LS; prm.p_drop = p_drop; prm.L = (int)L; prm.d = (int)d; prm.nl = (int)nl;
   prm.R = pl.R; prm.n_groups = pl.n_groups; prm.C = pl.C;
-  dim3 grid((unsigned)(d / pl.dj), (unsigned)nbt, (unsigned)nl);
-  if (pl.dj == 16) return launch_wave(gru_wave_bwd_kernel<16>, prm, grid, pl.smem, s, "gru_wave_bwd");
-  return launch_wave(gru_wave_bwd_kernel<32>, prm, grid, pl.smem, s, "gru_wave_bwd");
+  const int tpl = (int)(kNumSMs / ((d / pl.dj) * nl));
+  prm.nbt_total = nbt;
+  for (int t0 = 0; t0 < nbt; t0 += tpl) {
+    prm.tile0 = t0;
+    dim3 grid((unsigned)(d / pl.dj), (unsigned)(nbt - t0 < tpl ? nbt - t0 : tpl), (unsigned)nl);
+    rc = pl.dj == 16 ? launch_wave(gru_wave_bwd_kernel<16>, prm, grid, pl.smem, s, "gru_wave_bwd")
+                     : launch_wave(gru_wave_bwd_kernel<32>, prm, grid, pl.smem, s, "gru_wave_bwd");
+    if (rc) return rc;
+  }
+  return 0;
 }

@@ -186,7 +186,8 @@ int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uint16_t* z, c
  * b_ih / b_hh (and WhhT_b / WihT_b = transposed [d,3d] bf16 weights; WihT_b[0] unused) are HOST arrays of nl
  * device pointers.  dh0 (optional) receives the SUM over layers of d loss / d h0.  sync_ws int32 [nl*ceil(bt0/128)].
  * ark_gru_wave_supported returns the hidden-slice width (16/32) or 0 when the stack does not fit (resident
- * weights 12*slice*d bytes per CTA, (d/slice)*ceil(bt0/128)*nl CTAs <= 148, nl <= 4, d % 64 == 0). */
+ * weights 12*slice*d bytes per CTA, (d/slice)*nl CTAs <= 148 for ONE 128-row batch tile, nl <= 4, d % 64 == 0).
+ * Batch tiles are independent; when they do not all fit the 148 SMs at once, groups of tiles run back to back. */
 int ark_gru_wave_supported(int64_t d, int64_t bt0, int64_t nl);
 int ark_gru_wave_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t* out_b, const float* h0,
                      const uint16_t* const* Wih_b, const uint16_t* const* Whh_b, const float* const* b_ih,

@@ -242,6 +242,7 @@ def test_state_dict_roundtrip_keeps_engine_in_sync():
     dict(nE=300, nR=6, lo=1, hi=15, pad=True, d=128, dz=16, nl=3, B=140),    # two batch tiles, ragged
     dict(nE=300, nR=6, lo=2, hi=40, pad=True, d=256, dz=16, nl=2, B=12),     # small batch (16-row TMA boxes), long chain
     dict(nE=50, nR=4, lo=4, hi=4, pad=False, d=64, dz=8, nl=4, B=33),        # four layers, fixed length
+    dict(nE=50, nR=4, lo=2, hi=5, pad=True, d=512, dz=8, nl=3, B=140),       # 2 batch tiles x 96 CTAs > 148 SMs: tile groups run back to back
 ])
 @pytest.mark.parametrize("p_drop", [0.0, 0.1])
 def test_gru_kernels_agree_wavefront_vs_per_layer_vs_per_step(spec, p_drop):
