@@ -170,6 +170,29 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(
   }
 }
 
+// fp32 inference path: S <- softmax(S) in place (zeros beyond the causal limit), no dropout, nothing saved
+__global__ void __launch_bounds__(256) attn_softmax_inplace_kernel(
+    float* __restrict__ S, const int32_t* __restrict__ cu, const int64_t* __restrict__ sq_off,
+    const int32_t* __restrict__ tok_graph, int64_t n_tok, int H, int causal) {
+  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= n_tok * H) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = w / H;
+  const int h = (int)(w % H);
+  const int b = tok_graph[tok];
+  const int r0 = cu[b], n = cu[b + 1] - r0, i = (int)(tok - r0);
+  const int64_t base = sq_off[b] * H + ((int64_t)h * n + i) * n;
+  const int lim = causal ? i + 1 : n;
+  float mx = -INFINITY;
+  for (int j = lane; j < lim; j += 32) mx = fmaxf(mx, S[base + j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < lim; j += 32) sum += expf(S[base + j] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < n; j += 32) S[base + j] = j < lim ? expf(S[base + j] - mx) * inv : 0.f;
+}
+
 __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(
     const uint16_t* __restrict__ P, const uint16_t* __restrict__ Pd, const float* __restrict__ dP,
     const int32_t* __restrict__ cu, const int64_t* __restrict__ sq_off, const int32_t* __restrict__ tok_graph,
@@ -521,6 +544,15 @@ extern "C" int ark_attn_softmax_fwd(const float* S, const int32_t* cu, const int
   attn_softmax_fwd_kernel<<<(unsigned)((n_tok * H + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       S, cu, sq_off, tok_graph, n_tok, (int)H, causal, p_drop, seed, offset, offset_dev, P, P_drop);
   return launched("attn_softmax_fwd");
+}
+
+extern "C" int ark_attn_softmax_inplace(float* S, const int32_t* cu, const int64_t* sq_off, const int32_t* tok_graph,
+                                        int64_t n_tok, int64_t H, int causal, void* stream) {
+  ARK_REQUIRE(S && cu && sq_off && tok_graph, ARK_E_BADARG, "attn_softmax_inplace: null pointer");
+  if (n_tok == 0) return 0;
+  attn_softmax_inplace_kernel<<<(unsigned)((n_tok * H + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, cu, sq_off, tok_graph,
+                                                                                                 n_tok, (int)H, causal);
+  return launched("attn_softmax_inplace");
 }
 
 extern "C" int ark_attn_softmax_bwd(const uint16_t* P, const uint16_t* P_drop, const float* dP, const int32_t* cu,

@@ -4,6 +4,9 @@
 // over [N,V] become ONE DRAM read and ONE in-place DRAM write; the second read of the row is served
 // by L2 (a row is at most 122 KB; 148 resident rows = 18 MB of the 126 MB L2).  The probability
 // matrix never exists in HBM.  HBM-bound: algorithmic bytes = 2*N*V*sizeof(logit).
+// (Tried and dropped: holding the whole bf16 row in registers between the passes — one 512-thread CTA per SM at
+// 128 registers/thread — removes the L2 re-read but also the overlap between a row's load and its neighbour's
+// compute/store: 3.65-3.84 TB/s stand-alone against 4.26-4.53 TB/s for this two-pass kernel at V = 60943.)
 #include "common.cuh"
 
 namespace ark {
@@ -156,92 +159,6 @@ __global__ void __launch_bounds__(kCeThreads, U == 4 ? 2 : 4) softmax_ce_kernel(
   if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, loss_local * grad_scale);
 }
 
-// Register-resident variant for bf16 rows of up to 65536 logits: the whole row is fetched ONCE into registers
-// (NCH 16-byte loads per thread, all in flight together), max / sum / gradient are computed from the registers
-// and the gradient is stored over the row — no second read at all (the two-pass kernel above re-reads the row
-// from L2, ~15 % of which misses to DRAM at V = 60943).  One CTA of 512 threads per row.
-template <int NCH>
-__global__ void __launch_bounds__(kCeThreads, 1) softmax_ce_reg_kernel(
-    uint16_t* __restrict__ logits, int64_t N, int V, int64_t ldv, const int32_t* __restrict__ tgt, float grad_scale,
-    int write_grad, float* __restrict__ loss_acc, float* __restrict__ lse_out) {
-  __shared__ float red[33];
-  const int nch = V >> 3, V8 = V & ~7;
-  float loss_local = 0.f;
-  for (int64_t row = blockIdx.x; row < N; row += gridDim.x) {
-    uint16_t* x = logits + row * ldv;
-    uint4 raw[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c = threadIdx.x + kCeThreads * i;
-      raw[i] = (c < nch) ? *reinterpret_cast<const uint4*>(x + c * 8) : make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // -inf
-    }
-    const int ct = V8 + threadIdx.x;              // the <= 7 elements behind the last full chunk
-    const float tail = (ct < V) ? ld1(x + ct) : -INFINITY;
-    float m = tail;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(w[k]);
-        m = fmaxf(m, fmaxf(f.x, f.y));
-      }
-    }
-    const float M = block_max(m, red);
-    const float nb = -M * kLog2e;
-    float sum = ex2(fmaf(tail, kLog2e, nb));      // ex2(-inf) = 0
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(w[k]);
-        sum += ex2(fmaf(f.x, kLog2e, nb)) + ex2(fmaf(f.y, kLog2e, nb));
-      }
-    }
-    const float S = block_sum(sum, red);
-    const float lse = M + __logf(S);
-    const int t = tgt[row];
-    if (threadIdx.x == 0) {
-      loss_local += lse - ld1(x + t);
-      if (lse_out) lse_out[row] = lse;
-    }
-    if (write_grad) {
-      __syncthreads();  // thread 0 has read x[t] before anyone overwrites it
-      const float kk = fmaf(-lse, kLog2e, __log2f(grad_scale));
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int c = threadIdx.x + kCeThreads * i;
-        if (c < nch) {
-          const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
-          float v[8];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 f = unpack_bf16x2(w[k]);
-            v[2 * k] = ex2(fmaf(f.x, kLog2e, kk));
-            v[2 * k + 1] = ex2(fmaf(f.y, kLog2e, kk));
-          }
-          if ((unsigned)(t - c * 8) < 8u) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (k == t - c * 8) v[k] -= grad_scale;
-          }
-          store8(x + c * 8, v);
-        }
-      }
-      for (int c = V8 + threadIdx.x; c < (int)ldv; c += kCeThreads) {
-        float g = 0.f;
-        if (c < V) {
-          g = ex2(fmaf(tail, kLog2e, kk));
-          if (c == t) g -= grad_scale;
-        }
-        st1(x + c, g);
-      }
-    }
-  }
-  if (threadIdx.x == 0 && loss_acc) atomicAdd(loss_acc, loss_local * grad_scale);
-}
-
 }  // namespace ark
 
 using namespace ark;
@@ -258,19 +175,6 @@ extern "C" int ark_softmax_ce(void* logits, int dtype, int64_t N, int64_t V, int
   const int per_sm = deep ? 2 : 4;
   const unsigned grid = (unsigned)(N < per_sm * kNumSMs ? N : per_sm * kNumSMs);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == ARK_BF16 && V <= kCeThreads * 8 * 16 && V >= 4096) {
-    const int need = (int)((V / 8 + kCeThreads - 1) / kCeThreads);   // 16-byte chunks per thread
-    const unsigned g1 = (unsigned)(N < 4 * kNumSMs ? N : 4 * kNumSMs);
-#define ARK_CE_REG(NN) softmax_ce_reg_kernel<NN><<<g1, kCeThreads, 0, s>>>((uint16_t*)logits, N, (int)V, ldv, tgt, grad_scale, write_grad, loss_acc, lse)
-    if (need <= 2) ARK_CE_REG(2);
-    else if (need <= 4) ARK_CE_REG(4);
-    else if (need <= 6) ARK_CE_REG(6);
-    else if (need <= 8) ARK_CE_REG(8);
-    else if (need <= 12) ARK_CE_REG(12);
-    else ARK_CE_REG(16);
-#undef ARK_CE_REG
-    return launched("softmax_ce");
-  }
 #define ARK_CE_GO(TT, UU) softmax_ce_kernel<TT, UU><<<grid, kCeThreads, 0, s>>>((TT*)logits, N, (int)V, ldv, tgt, grad_scale, write_grad, loss_acc, lse)
   if (dtype == ARK_BF16) {
     if (deep) ARK_CE_GO(uint16_t, 4); else ARK_CE_GO(uint16_t, 2);

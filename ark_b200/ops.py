@@ -327,6 +327,11 @@ def attn_softmax_fwd(S, seg, H, causal, p_drop, seed, offset, offset_dev, P, P_d
                   _ptr(offset_dev, torch.int64), _ptr(P, torch.bfloat16), _ptr(P_drop, torch.bfloat16), _stream())
 
 
+def attn_softmax_inplace(S, seg, H, causal):
+    _C.lib().call("ark_attn_softmax_inplace", _ptr(S, torch.float32), _ptr(seg.cu_dev, torch.int32),
+                  _ptr(seg.sq_dev, torch.int64), _ptr(seg.graph_dev, torch.int32), seg.n_rows, H, int(causal), _stream())
+
+
 def attn_softmax_bwd(P, P_drop, dP, seg, H, causal, p_drop, alpha, dS):
     _C.lib().call("ark_attn_softmax_bwd", _ptr(P, torch.bfloat16), _ptr(P_drop, torch.bfloat16), _ptr(dP, torch.float32),
                   _ptr(seg.cu_dev, torch.int32), _ptr(seg.sq_dev, torch.int64), _ptr(seg.graph_dev, torch.int32),

@@ -34,6 +34,14 @@ class FusedAdam(torch.optim.Optimizer):
         for st in self.state.values():
             st["step"] = torch.tensor(float(self.engine.step_count))
 
+    def sync_from_engine(self):
+        """After fused steps (SAIL.elbo_step / ARK.ce_step run Adam inside the engine): publish the engine's step
+        count through the per-parameter state so checkpoints and LR schedulers see it."""
+        g = self.param_groups[0]
+        self.engine.betas, self.engine.eps = tuple(g["betas"]), float(g["eps"])
+        for st in self.state.values():
+            st["step"] = torch.tensor(float(self.engine.step_count))
+
     def load_state_dict(self, state_dict):
         f = self.engine.flat
         keep = {p: (st["exp_avg"], st["exp_avg_sq"]) for p, st in self.state.items()}

@@ -386,6 +386,92 @@ class TSailEngine(SailEngine):
         self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight")
         return out
 
+    # ------------------------------------------------------------------ fp32 inference (generation / validation)
+    def _lin32(self, x, wname, bname, epilogue=ops.EPI_NONE):
+        """y = epi(x W^T + b) in fp32 on the FMA kernel, fp32 master weights (integer outputs of generation must
+        match the reference, so no bf16 here)."""
+        f = self.flat
+        w = wname if torch.is_tensor(wname) else f.p(wname)
+        b = bname if torch.is_tensor(bname) else f.p(bname)
+        M, Kd = x.shape
+        y = self._new(M, w.shape[0])
+        ops.gemm(x, K, w, K, y, M, w.shape[0], Kd, bias=b, epilogue=epilogue, backend="simt")
+        return y
+
+    def _layer32(self, x, pre, seg, Dm, causal, S, cross=None):
+        """One post-LN layer in fp32: self-attention, [collapsed cross-attention row `cross` per graph], ReLU FFN."""
+        f, H = self.flat, self.H
+        hd, n = Dm // H, x.shape[0]
+        zeros = lambda: (self._new(n), self._new(n))  # noqa: E731
+        qkv = self._lin32(x, pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias")
+        ops.attn_bgemm(qkv, TOK, False, 0, qkv, TOK, True, Dm, S, SQ, 0, seg, H, hd, 0, causal, 1.0 / math.sqrt(hd))
+        ops.attn_softmax_inplace(S, seg, H, causal)
+        o = self._new(n, Dm)
+        ops.attn_bgemm(S, SQ, False, 0, qkv, TOK, False, 2 * Dm, o, TOK, 0, seg, H, hd, 1, causal, 1.0)
+        a = self._lin32(o, pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias")
+        y = self._new(n, Dm)
+        ops.add_layernorm_fwd(a, x, f.p(pre + "norm1.weight"), f.p(pre + "norm1.bias"), self.ln_eps, 0.0, 0, 0, None, None, y,
+                              None, *zeros())
+        x, k_ff = y, 2
+        if cross is not None:
+            c = self._new(n, Dm)
+            ops.seg_broadcast(cross, seg, False, None, 0, c, None)
+            y = self._new(n, Dm)
+            ops.add_layernorm_fwd(c, x, f.p(pre + "norm2.weight"), f.p(pre + "norm2.bias"), self.ln_eps, 0.0, 0, 0, None, None,
+                                  y, None, *zeros())
+            x, k_ff = y, 3
+        h = self._lin32(x, pre + "linear1.weight", pre + "linear1.bias", ops.EPI_RELU)
+        ff = self._lin32(h, pre + "linear2.weight", pre + "linear2.bias")
+        y = self._new(n, Dm)
+        ops.add_layernorm_fwd(ff, x, f.p(pre + f"norm{k_ff}.weight"), f.p(pre + f"norm{k_ff}.bias"), self.ln_eps, 0.0, 0, 0,
+                              None, None, y, None, *zeros())
+        return y
+
+    @torch.no_grad()
+    def encode_stats(self, triples):
+        """(mu, logv) of AutoRegEncoder.forward in eval mode (models.py:78-93), fp32."""
+        from .layout import segments_from_lens
+        import numpy as np
+        tri = triples.detach().cpu().numpy()
+        live = (tri[:, :, 1] != self.pad_rid) if self.pad_rid is not None else np.ones(tri.shape[:2], dtype=bool)
+        seg = segments_from_lens(live.sum(1)).to(self.device)
+        idx = torch.from_numpy(np.ascontiguousarray(tri[live].astype(np.int32))).to(self.device)
+        f, D = self.flat, self.D
+        x, xb = self._new(seg.n_rows, D), self._new(seg.n_rows, D, dtype=torch.bfloat16)
+        ops.triple_embed_fwd(idx, f.p("enc.e_emb.weight"), f.p("enc.r_emb.weight"), x, xb)
+        S = self._new(max(seg.sq_total, 1) * self.H)
+        for l in range(self.nl_e):
+            x = self._layer32(x, f"enc.txf.layers.{l}.", seg, D, False, S)
+        pooled = self._new(seg.n_graphs, D)
+        ops.seg_reduce(x, seg, True, None, 0, pooled, None)
+        return self._lin32(pooled, "enc.mu.weight", "enc.mu.bias"), self._lin32(pooled, "enc.logv.weight", "enc.logv.bias")
+
+    @torch.no_grad()
+    def decode_logits(self, z, tgt):
+        """logits [B, L', V] of AutoRegDecoder.forward (models.py:108-114) / DecoderOnlyTransformer.forward (:360-365)
+        in eval mode for any prefix length L', fp32.  z is ignored by the decoder-only model."""
+        from .layout import segments_from_lens
+        import numpy as np
+        B, Lp = tgt.shape
+        f, d, dev = self.flat, self.d, self.device
+        seg = segments_from_lens(np.full(B, Lp, dtype=np.int32)).to(dev)
+        tok = tgt.reshape(-1).to(torch.int32).contiguous()
+        pos = torch.arange(Lp, device=dev, dtype=torch.int32).repeat(B).contiguous()
+        y, yb = self._new(B * Lp, d), self._new(B * Lp, d, dtype=torch.bfloat16)
+        ops.embed_sum_fwd(f.p("dec.tok_emb.weight"), f.p("dec.pos_emb.weight"), tok, pos, y, yb)
+        mem = self._lin32(z.to(torch.float32).contiguous(), "dec.z_proj.weight", "dec.z_proj.bias") if self.has_enc else None
+        S = self._new(seg.sq_total * self.H)
+        for l in range(self.nl_d):
+            pre = f"dec.txf.layers.{l}."
+            cross = None
+            if self.has_enc:   # uniform attention over L identical memory rows == out_proj(v_proj(mem))
+                w_in, b_in = f.p(pre + "multihead_attn.in_proj_weight"), f.p(pre + "multihead_attn.in_proj_bias")
+                vm = self._lin32(mem, w_in[2 * d:3 * d], b_in[2 * d:3 * d])
+                cross = self._lin32(vm, pre + "multihead_attn.out_proj.weight", pre + "multihead_attn.out_proj.bias")
+            y = self._layer32(y, pre, seg, d, True, S, cross)
+        w_out = f.p("dec.tok_emb.weight") if self.tied else f.p("dec.out.weight")
+        return self._lin32(y, w_out, f.p("dec.out.bias")).view(B, Lp, -1)
+
     def train_step_graphed(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
         """The ragged index arrays of a t-SAIL batch change every step: no graph replay yet, eager launches."""
         return self.train_step(triples, seq, lay, eps, beta, lr, n_tok_global, batch_global)

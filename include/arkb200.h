@@ -222,6 +222,9 @@ int ark_attn_bgemm(const void* A, int a_kind, int a_trans, int a_f32, int64_t a_
 int ark_attn_softmax_fwd(const float* S, const int32_t* cu, const int64_t* sq_off, const int32_t* tok_graph,
                          int64_t n_tok, int64_t H, int causal, float p_drop, uint64_t seed, uint64_t offset,
                          const uint64_t* offset_dev, uint16_t* P, uint16_t* P_drop, void* stream);
+/* fp32 inference path: S <- softmax(S) in place (zeros above the diagonal when causal), no dropout */
+int ark_attn_softmax_inplace(float* S, const int32_t* cu, const int64_t* sq_off, const int32_t* tok_graph,
+                             int64_t n_tok, int64_t H, int causal, void* stream);
 /* dS = alpha * P * (dP - sum_j P dP) with dP = dP_drop * keep/(1-p) (keep <=> P_drop != 0) */
 int ark_attn_softmax_bwd(const uint16_t* P, const uint16_t* P_drop, const float* dP, const int32_t* cu,
                          const int64_t* sq_off, const int32_t* tok_graph, int64_t n_tok, int64_t H, int causal,

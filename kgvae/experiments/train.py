@@ -98,41 +98,69 @@ def load_graphs(config, seed=1234):
 class BatchLoader:
     """Rank-sharded, vectorised replacement of DataLoader(GraphSeqDataset) for the train step.
 
-    Global batch g covers graphs [g*B*W, (g+1)*B*W); rank r owns the r-th slice of B graphs (drop_last).
-    Every rank can see all lengths, so the GLOBAL non-PAD token count of a step needs no collective.
-    Yields (triples, seq, n_tok_global) with pinned host tensors in the reference's format.
+    The whole split is tensorised ONCE (reference rules: utils.py:102-108,131-146) into pinned host tensors
+    `triples [G, T, 3]` and `seq [G, seq_len]`; an epoch is a (shuffled) row order of those tensors and a batch is a
+    contiguous slice — no per-graph Python in the step loop (the reference's `num_workers=0` DataLoader builds every
+    item with `random.sample` / `torch.tensor`, which caps real-data training two orders below the GPU step).
+    Global batch g covers rows [g*B*W, (g+1)*B*W) of the epoch order; rank r owns the r-th slice of B graphs
+    (drop_last).  Every rank can see all lengths, so the GLOBAL non-PAD token count of a step needs no collective.
+    Yields (triples, seq, n_tok_global, batch_global) with pinned host tensors in the reference's format.
     """
 
     def __init__(self, graphs, vocab, batch_size, rank=0, world=1, shuffle=False, drop_last=True, permute=False,
                  seed=0):
-        self.graphs, self.v, self.B, self.rank, self.world = graphs, vocab, batch_size, rank, world
+        self.v, self.B, self.rank, self.world = vocab, batch_size, rank, world
         self.shuffle, self.drop_last, self.permute, self.epoch, self.seed = shuffle, drop_last, permute, 0, seed
-        self.lens = np.fromiter((3 * len(g) + 1 for g in graphs), dtype=np.int64, count=len(graphs))
+        self.G = len(graphs)
+        self.n = np.fromiter((len(g) for g in graphs), dtype=np.int64, count=self.G)
+        self.lens = 3 * self.n + 1
+        if not vocab["use_padding"] and self.G and not (self.n == self.n[0]).all():
+            raise ValueError("without padding all graphs need the same number of triples (reference: default collate)")
+        # one vectorised pass over the split; chunked so the temporary Python list stays small
+        tri, seq = [], []
+        for c0 in range(0, self.G, 8192):
+            t_, s_ = build_batch(graphs[c0:c0 + 8192], special_tokens=SPECIAL, ent_base=vocab["ENT_BASE"],
+                                 rel_base=vocab["REL_BASE"], seq_len=vocab["seq_len"], max_triples=vocab["max_edges"],
+                                 use_padding=vocab["use_padding"], pad_eid=vocab["pad_eid"], pad_rid=vocab["pad_rid"])
+            tri.append(t_)
+            seq.append(s_)
+        pin = torch.cuda.is_available()
+        self.tri = torch.cat(tri) if tri else torch.zeros(0, 1, 3, dtype=torch.int64)
+        self.seq = torch.cat(seq) if seq else torch.zeros(0, vocab["seq_len"], dtype=torch.int64)
+        self.tri_e, self.seq_e = torch.empty_like(self.tri), torch.empty_like(self.seq)     # this epoch's row order
+        if pin:
+            self.tri, self.seq = self.tri.pin_memory(), self.seq.pin_memory()
+            self.tri_e, self.seq_e = self.tri_e.pin_memory(), self.seq_e.pin_memory()
 
     def __len__(self):
         per = self.B * self.world
-        return len(self.graphs) // per if self.drop_last else math.ceil(len(self.graphs) / per)
+        return self.G // per if self.drop_last else math.ceil(self.G / per)
 
     def __iter__(self):
-        order = np.arange(len(self.graphs))
-        if self.shuffle:
-            np.random.default_rng(self.seed + self.epoch).shuffle(order)
         self.epoch += 1
+        tri, seq, lens = self.tri, self.seq, self.lens
+        if self.shuffle or (self.permute and not self.v["use_padding"]):
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()     # last epoch's async H2D copies read tri_e / seq_e: finish them before rewriting
+            rng = np.random.default_rng(self.seed + self.epoch)
+            order = torch.from_numpy(rng.permutation(self.G) if self.shuffle else np.arange(self.G))
+            torch.index_select(self.tri, 0, order, out=self.tri_e)
+            torch.index_select(self.seq, 0, order, out=self.seq_e)
+            tri, seq, lens = self.tri_e, self.seq_e, self.lens[order.numpy()]
+            if self.permute and not self.v["use_padding"] and tri.shape[1] > 1:     # reference: utils.py:133-134
+                T = tri.shape[1]
+                p = torch.from_numpy(np.argsort(rng.random((self.G, T)), axis=1))     # a random order per graph
+                tri.copy_(torch.gather(tri, 1, p[:, :, None].expand(-1, -1, 3)))
+                tok = seq[:, 1:1 + 3 * T].reshape(self.G, T, 3)
+                seq[:, 1:1 + 3 * T] = torch.gather(tok, 1, p[:, :, None].expand(-1, -1, 3)).reshape(self.G, 3 * T)
         per = self.B * self.world
         for g in range(len(self)):
-            idx = order[g * per:(g + 1) * per]
-            mine = idx[self.rank * self.B:(self.rank + 1) * self.B]
-            if len(mine) == 0:
+            lo = g * per
+            hi = min(lo + per, self.G)
+            a, b = lo + self.rank * self.B, min(lo + (self.rank + 1) * self.B, hi)
+            if b <= a:
                 continue
-            gs = [self.graphs[i] for i in mine]
-            if self.permute and not self.v["use_padding"]:      # reference: utils.py:133-134
-                rng = np.random.default_rng(self.seed + 7919 * self.epoch + g)
-                gs = [[gr[j] for j in rng.permutation(len(gr))] for gr in gs]
-            tri, seq = build_batch(gs, special_tokens=SPECIAL, ent_base=self.v["ENT_BASE"], rel_base=self.v["REL_BASE"],
-                                   seq_len=self.v["seq_len"], max_triples=self.v["max_edges"],
-                                   use_padding=self.v["use_padding"], pad_eid=self.v["pad_eid"],
-                                   pad_rid=self.v["pad_rid"], pin=True)
-            yield tri, seq, int(self.lens[idx].sum()), len(idx)
+            yield tri[a:b], seq[a:b], int(lens[lo:hi].sum()), hi - lo
 
 
 # --------------------------------------------------------------------------------------------- loops
@@ -145,17 +173,29 @@ def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None
     model.train()
     eng = model.engine()
     eng.stats.zero_()
+    fused = hasattr(optimizer, "sync_from_engine")        # FusedAdam: one fused call per step, Adam overlapped with backward
+    # fixed-size datasets (syn-*) repeat one batch layout: replay the captured CUDA graph(s) instead of ~150 launches
+    replay = fused and mt == "SAIL" and not config.get("use_padding", False) and bool(config.get("cuda_graph", True))
     for i, batch in enumerate(dataloader):
         triples, seq = batch[0], batch[1]
         ntg = batch[2] if len(batch) > 2 else None
         bg = batch[3] if len(batch) > 3 else None
+        eps = None if eps_fn is None else eps_fn(i)
+        if fused:
+            lr = float(optimizer.param_groups[0]["lr"])
+            if mt in ("ARK", "t-ARK"):       # decoder-only: loss = CE, KL = 0 (reference train.py:42-58)
+                model.ce_step(seq, lr=lr, n_tok_global=ntg)
+            else:
+                model.elbo_step(triples, seq, b, eps=eps, lr=lr, n_tok_global=ntg, batch_global=bg, graph=replay)
+            continue
         optimizer.zero_grad()
-        if mt in ("ARK", "t-ARK"):       # decoder-only: loss = CE, KL = 0 (reference train.py:42-58)
+        if mt in ("ARK", "t-ARK"):
             model.ce_backward(seq, n_tok_global=ntg)
         else:
-            model.elbo_backward(triples, seq, b, eps=None if eps_fn is None else eps_fn(i), n_tok_global=ntg,
-                                batch_global=bg)
+            model.elbo_backward(triples, seq, b, eps=eps, n_tok_global=ntg, batch_global=bg)
         optimizer.step()
+    if fused:
+        optimizer.sync_from_engine()
     loss, ce, kl = eng.read_stats(b)            # one device->host read for the whole epoch
     return loss, ce, kl, 0.0
 

@@ -157,10 +157,21 @@ class AutoRegEncoder(nn.Module):
         self.mu = nn.Linear(d_model * 3, latent_dim)
         self.logv = nn.Linear(d_model * 3, latent_dim)
 
+    _owner = None     # the SAIL module whose engine runs the kernels (set by SAIL.__init__, not a submodule)
+
+    @torch.no_grad()
+    def encode_stats(self, triples):
+        _need_cuda(triples, "enc")
+        return self._owner().engine().encode_stats(triples)
+
+    @torch.no_grad()
     def forward(self, triples):
-        raise NotImplementedError("t-SAIL runs through SAIL.elbo_step / engine().eval_step (fused training and "
-                                  "validation loss); the stand-alone fp32 enc()/dec() inference path is built for the "
-                                  "GRU models only so far")
+        """(z, mu, logv), eval semantics (no dropout), fp32 kernels; no clamp on logv (reference models.py:92-94)."""
+        if self.training and self._owner().engine().p_drop > 0:
+            raise RuntimeError("enc() is the fp32 inference path; train with SAIL.elbo_step (dropout lives there)")
+        mu, logv = self.encode_stats(triples)
+        z = mu + torch.randn_like(mu) * torch.exp(0.5 * logv)
+        return z, mu, logv
 
 
 class AutoRegDecoder(nn.Module):
@@ -175,8 +186,15 @@ class AutoRegDecoder(nn.Module):
         self.txf = nn.TransformerDecoder(layer, num_layers)
         self.out = nn.Linear(d_model, vocab_size)
 
+    _owner = None
+
+    @torch.no_grad()
     def forward(self, z, tgt):
-        raise NotImplementedError("t-SAIL runs through SAIL.elbo_step / engine().eval_step; see AutoRegEncoder.forward")
+        """logits [B, L', V] for any prefix length (fp32, eval semantics)."""
+        _need_cuda(tgt, "dec")
+        if self.training and self._owner().engine().p_drop > 0:
+            raise RuntimeError("dec() is the fp32 inference path; train with SAIL.elbo_step (dropout lives there)")
+        return self._owner().engine().decode_logits(z, tgt)
 
 
 class _EngineMixin:
@@ -243,6 +261,8 @@ class SAIL(_EngineMixin, nn.Module):
             self.dec = AutoRegDecoder(
                 d_model=config["d_model"], nhead=config["n_heads"], num_layers=config["n_layers"],
                 seq_len=config["seq_len"], vocab_size=config["vocab_size"], latent_dim=config["d_latent"])
+            import weakref
+            self.enc._owner = self.dec._owner = weakref.ref(self)      # their forward() runs on this module's engine
         else:
             raise NotImplementedError(f"Unknown model_type: {mt}")
         self._init_engine_slot()
@@ -410,9 +430,14 @@ class DecoderOnlyTransformer(nn.Module):
         if tie_weights and self.out.weight.shape == self.tok_emb.weight.shape:
             self.out.weight = self.tok_emb.weight
 
+    _owner = None
+
+    @torch.no_grad()
     def forward(self, seq_in):
-        raise NotImplementedError("t-ARK runs through ARK.ce_step / engine().eval_step (fused training and validation "
-                                  "loss); the stand-alone fp32 inference path is built for the GRU models only so far")
+        _need_cuda(seq_in, "dec")
+        if self.training and self._owner().engine().p_drop > 0:
+            raise RuntimeError("dec() is the fp32 inference path; train with ARK.ce_step (dropout lives there)")
+        return self._owner().engine().decode_logits(None, seq_in)
 
 
 class ARK(_EngineMixin, nn.Module):
@@ -431,6 +456,8 @@ class ARK(_EngineMixin, nn.Module):
                                               num_layers=config["n_layers"], seq_len=config["seq_len"],
                                               vocab_size=config["vocab_size"], dropout=config.get("dec_dropout", 0.1),
                                               tie_weights=config.get("tie_weights", True))
+            import weakref
+            self.dec._owner = weakref.ref(self)
         else:
             raise NotImplementedError(f"Unknown model_type: {config['model_type']}")
         self._init_engine_slot()

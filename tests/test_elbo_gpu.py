@@ -479,3 +479,60 @@ def test_tark_ce_step_matches_reference_golden_and_port():
     for _ in range(20):
         last = m.ce_step(torch.from_numpy(seq))[0].item()
     assert last < first
+
+
+@pytest.mark.parametrize("case", TSAIL_CASES)
+def test_tsail_fp32_inference_path_matches_reference(case):
+    """enc()/dec() of the Transformer KG-VAE on the fp32 kernels (eval semantics) vs the unmodified reference, and
+    beam-search graphs under fixed latents vs the CPU port (integer outputs: exact)."""
+    from oracle import tsail_torch_port as T       # the checker
+    arr, meta, params, _ = load_tsail_golden(case)
+    cfg = meta["cfg"]
+    torch.manual_seed(0)
+    m = SAIL(dict(cfg)).to(DEV).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    tri, seq = torch.from_numpy(arr["triples"]).to(DEV), torch.from_numpy(arr["seq"]).to(DEV)
+    mu, logv = m.enc.encode_stats(tri)
+    np.testing.assert_allclose(mu.cpu().numpy(), arr["mu"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(logv.cpu().numpy(), arr["logv"], rtol=1e-4, atol=2e-5)
+    z = torch.from_numpy(arr["mu"] + arr["eps"] * np.exp(0.5 * arr["logv"])).to(DEV)
+    logits = m.dec(z, seq[:, :-1]).cpu().numpy()
+    valid = arr["seq"][:, 1:] != 0
+    np.testing.assert_allclose(logits[valid], arr["logits"][valid], rtol=1e-4, atol=3e-4)
+    # prefix calls (generation) see the same distribution as the full pass: causal
+    np.testing.assert_allclose(m.dec(z[:2], seq[:2, :4]).cpu().numpy(), logits[:2, :4], rtol=1e-4, atol=3e-4)
+    p64 = {k: torch.as_tensor(v).double() for k, v in params.items()}
+
+    def dec_fn(zz, prefix):
+        return T.decoder(p64, cfg, torch.as_tensor(zz).double(), torch.as_tensor(prefix)).numpy()
+
+    want = O.beam_generate(dec_fn, z.cpu().numpy().astype(np.float64), cfg, beam=3)
+    got = m.decode_latent(z, cfg["seq_len"], cfg["special_tokens"], seq_to_triples, cfg["ENT_BASE"], cfg["REL_BASE"], beam=3)
+    assert [[list(t) for t in g] for g in got] == [[list(t) for t in g] for g in want]
+    torch.manual_seed(5)
+    zz, mu2, logv2 = m.enc(tri)
+    torch.manual_seed(5)
+    assert torch.equal(zz, mu2 + torch.randn_like(mu2) * torch.exp(0.5 * logv2))     # the reference's draw (models.py:94)
+
+
+def test_tark_fp32_inference_and_greedy_generation():
+    from oracle import tsail_torch_port as T       # the checker
+    arr, meta, params, _ = load_ark_golden("t_wd")
+    cfg = meta["cfg"]
+    model = _ark_from(params, cfg).eval()
+    seq = torch.from_numpy(arr["seq"]).to(DEV)
+    logits = model(seq[:, :-1]).cpu().numpy()
+    valid = arr["seq"][:, 1:] != 0
+    np.testing.assert_allclose(logits[valid], arr["logits"][valid], rtol=1e-4, atol=3e-4)
+    gen = model.generate(cfg["seq_len"], cfg["special_tokens"], batch_size=2, sample=False).cpu().numpy()
+    # greedy decoding of the CPU port from the same weights
+    s = np.full((2, 1), 1, dtype=np.int64)
+    for _ in range(cfg["seq_len"] - 1):
+        pad = np.concatenate([s, np.zeros((2, 1), dtype=np.int64)], 1)            # tark_step consumes seq[:, :-1]
+        lg = T.tark_step(params, cfg, pad)[2]["logits"][:, -1]
+        s = np.concatenate([s, lg.argmax(-1)[:, None]], 1)
+        if (s[:, -1] == 2).all():
+            break
+    if s.shape[1] < cfg["seq_len"]:
+        s = np.concatenate([s, np.full((2, cfg["seq_len"] - s.shape[1]), 2, dtype=np.int64)], 1)
+    assert gen.tolist() == s[:, :cfg["seq_len"]].tolist()

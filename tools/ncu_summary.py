@@ -63,7 +63,10 @@ def full(paths, only=None, limit_per_kernel=3):
     out = ["| kernel | grid | time | dram rd | dram wr | dram % | tensor pipe % | warps active % | regs |",
            "|---|---|---|---|---|---|---|---|---|"]
     for path in paths:
-        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if path.endswith(".csv"):      # already exported on the GPU box (`ncu -i rep --page raw --csv`): reports > 64 MiB cannot travel
+            txt = open(path).read()
+        else:
+            txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rd = csv.reader(io.StringIO(txt))
         hdr, units = next(rd), next(rd)
         col = {h: i for i, h in enumerate(hdr)}
