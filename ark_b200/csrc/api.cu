@@ -50,6 +50,23 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+int make_tmap_2d_bf16_nosw(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                           uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(ARK_E_NODRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstride[1] = {ld * 2};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ARK_E_SHAPE, "cuTensorMapEncodeTiled (no swizzle) failed (CUresult %d) dims=(%llu,%llu) ld=%llu box=(%u,%u)",
+                (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+  return 0;
+}
+
 int make_tmap_kchunked_bf16(CUtensorMap* out, const void* base, uint64_t K, uint64_t rows, uint64_t ld,
                             uint32_t box_rows, uint32_t box_chunks) {
   EncodeTiledFn fn = encode_fn();

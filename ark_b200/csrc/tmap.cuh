@@ -17,4 +17,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
 int make_tmap_kchunked_bf16(CUtensorMap* out, const void* base, uint64_t K, uint64_t rows, uint64_t ld,
                             uint32_t box_rows, uint32_t box_chunks);
 
+// 2-D bf16 tensor WITHOUT swizzle: a box {8, box_outer} lands as box_outer rows of 16 bytes = the 8x16-byte core
+// matrices of the interleaved (no-swizzle) K-major UMMA layout stacked along M/N.
+int make_tmap_2d_bf16_nosw(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                           uint32_t box_inner, uint32_t box_outer);
+
 }  // namespace ark

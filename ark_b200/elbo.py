@@ -78,8 +78,10 @@ class SailEngine:
         self.dyn_i = torch.zeros(1, device=dev, dtype=torch.int64)   # running Philox offset for graph replay
         self.launches_replayed = 0       # kernels of libarkb200 executed through graph replays
         self.force_unfused_gru = False   # tests: compare the persistent GRU kernel with the per-step path
-        self.gru_mode = "auto"           # "auto": wavefront stack kernel when it fits, else per-layer persistent;
-                                         # "layer": never the wavefront kernel (tests / A-B timing)
+        self.gru_mode = "auto"           # "auto": cluster stack kernel (long chains of short batch tiles), else the
+                                         # wavefront stack kernel when it fits, else per-layer persistent;
+                                         # "wave": never the cluster kernel; "layer": neither (tests / A-B timing)
+        self._gru_cluster_ws = None      # scratch of the cluster GRU kernels (gi^T / dx^T slices), grown on demand
         self.stats = torch.zeros(4, device=dev)  # [ce, kl, steps, unused] accumulated on device
         self.refresh_shadow()
         if hasattr(model, "_attach_engine"):
@@ -97,6 +99,22 @@ class SailEngine:
         backend = "tc" if (self.backend == "tc" and ops.tc_eligible(A, B)) else "simt"
         with self._timed(f"gemm_{backend}:{tag}", flops=2.0 * M * N * Kd):
             ops.gemm(A, am, B, bm, C, M, N, Kd, backend=backend, **kw)
+
+    # ------------------------------------------------------------------ GRU driver choice
+    def _use_gru_cluster(self, d, b0, nl, L):
+        """The cluster kernel wins where the chain is long and the batch tile short (its DSMEM exchange costs
+        ~1 us per step whatever the tile; the wavefront kernel's global-memory exchange ~2.3 us)."""
+        if self.gru_mode != "cluster" and L < 32:
+            return False
+        return ops.gru_cluster_supported(d, b0, nl) > 0
+
+    def _cluster_ws(self, L, b0, d, nl):
+        need = ops.gru_cluster_workspace_bytes(L, b0, d, nl)
+        if self._gru_cluster_ws is None or self._gru_cluster_ws.numel() < need:
+            if self._capturing:
+                raise RuntimeError("cluster GRU scratch must be allocated before graph capture")
+            self._gru_cluster_ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return self._gru_cluster_ws
 
     # ------------------------------------------------------------------ optional per-op device timing
     class _Timer:
@@ -185,11 +203,14 @@ class SailEngine:
         b0 = int(lay.bt[0])
         saved = []
         u_b = x_b
-        wave = (use_tc and self.gru_mode in ("auto", "wave") and not self.force_unfused_gru
-                and ops.gru_wave_supported(d, b0, nl) > 0)
+        cluster = (use_tc and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru
+                   and self._use_gru_cluster(d, b0, nl, L))
+        wave = cluster or (use_tc and self.gru_mode in ("auto", "wave") and not self.force_unfused_gru
+                           and ops.gru_wave_supported(d, b0, nl) > 0)
         persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru and not wave
         gh_ws = None if (persist or wave) else new(b0, d3)
-        sync_ws = new(nl * ((b0 + 127) // 128), dtype=torch.int32) if (persist or wave) else None
+        sync_ws = new(2 * nl * ((b0 + 15) // 16), dtype=torch.int32) if (persist or wave) else None
+        cl_ws = self._cluster_ws(L, b0, d, nl) if cluster else None
         if wave:
             # the whole stack in ONE cooperative launch: layers run as a diagonal wavefront (L+nl-1 dependent
             # steps instead of nl*L), W_ih u_t inside the recurrence (no gi buffer), dropout in the epilogue
@@ -201,16 +222,20 @@ class SailEngine:
             dropping = train and self.p_drop > 0 and nl > 1
             wave_mask = new(nl - 1, N, d, dtype=torch.uint8) if dropping else None
             stride = (N * d + 3) // 4
-            with self._timed("gru_wave_fwd", flops=4.0 * N * d * d3 * nl):
-                ops.gru_wave_fwd(x_b, hp_all, out_all, h0 if self.has_enc else None,
-                                 [self._w(f"dec.gru.weight_ih_l{k}") for k in range(nl)],
-                                 [self._w(f"dec.gru.weight_hh_l{k}") for k in range(nl)],
-                                 [f.p(f"dec.gru.bias_ih_l{k}") for k in range(nl)],
-                                 [f.p(f"dec.gru.bias_hh_l{k}") for k in range(nl)],
-                                 lay.bt_dev, lay.off_dev, L, b0, d, wave_gates, wave_mask,
-                                 self.p_drop if dropping else 0.0, self.seed,
-                                 self._drop_calls * stride if self._capturing else self.philox_offset,
-                                 self.dyn_i if (self._capturing and dropping) else None, sync_ws)
+            with self._timed("gru_cluster_fwd" if cluster else "gru_wave_fwd", flops=4.0 * N * d * d3 * nl):
+                fwd_args = (x_b, hp_all, out_all, h0 if self.has_enc else None,
+                            [self._w(f"dec.gru.weight_ih_l{k}") for k in range(nl)],
+                            [self._w(f"dec.gru.weight_hh_l{k}") for k in range(nl)],
+                            [f.p(f"dec.gru.bias_ih_l{k}") for k in range(nl)],
+                            [f.p(f"dec.gru.bias_hh_l{k}") for k in range(nl)],
+                            lay.bt_dev, lay.off_dev, L, b0, d, wave_gates, wave_mask,
+                            self.p_drop if dropping else 0.0, self.seed,
+                            self._drop_calls * stride if self._capturing else self.philox_offset,
+                            self.dyn_i if (self._capturing and dropping) else None, sync_ws)
+                if cluster:
+                    ops.gru_cluster_fwd(*fwd_args, cl_ws)
+                else:
+                    ops.gru_wave_fwd(*fwd_args)
             if dropping:
                 if not self._capturing:
                     self.philox_offset += (nl - 1) * stride
@@ -276,11 +301,15 @@ class SailEngine:
                 if k > 0:
                     ops.transpose_bf16(self._w(f"dec.gru.weight_ih_l{k}"), w_t[nl + k])
             dgi_all, dgh_all = new(nl, N, d3, dtype=bf), new(nl, N, d3, dtype=bf)
-            with self._timed("gru_wave_bwd", flops=4.0 * N * d * d3 * nl - 2.0 * N * d * d3):
-                ops.gru_wave_bwd(dy, wave_gates, hp_all, wave_mask, self.p_drop if wave_mask is not None else 0.0,
-                                 [w_t[k] for k in range(nl)], [None] + [w_t[nl + k] for k in range(1, nl)],
-                                 lay.bt_dev, lay.off_dev, L, b0, d, dgi_all, dgh_all, dh0 if self.has_enc else None,
-                                 sync_ws)
+            with self._timed("gru_cluster_bwd" if cluster else "gru_wave_bwd", flops=4.0 * N * d * d3 * nl - 2.0 * N * d * d3):
+                bwd_args = (dy, wave_gates, hp_all, wave_mask, self.p_drop if wave_mask is not None else 0.0,
+                            [w_t[k] for k in range(nl)], [None] + [w_t[nl + k] for k in range(1, nl)],
+                            lay.bt_dev, lay.off_dev, L, b0, d, dgi_all, dgh_all, dh0 if self.has_enc else None,
+                            sync_ws)
+                if cluster:
+                    ops.gru_cluster_bwd(*bwd_args, cl_ws)
+                else:
+                    ops.gru_wave_bwd(*bwd_args)
             for k in range(nl - 1, -1, -1):
                 u_in = x_b if k == 0 else out_all[k - 1]
                 self._gemm(dgi_all[k], MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
@@ -489,6 +518,10 @@ class SailEngine:
                 begin()
 
             # warm-up outside capture is NOT wanted (it would apply an extra optimiser step): capture directly
+            b0 = int(lay.bt[0])
+            if (self.backend == "tc" and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru
+                    and self._use_gru_cluster(self.d, b0, self.nl, lay.L)):
+                self._cluster_ws(lay.L, b0, self.d, self.nl)      # scratch must exist before capture
             torch.cuda.synchronize()
             n0 = _C.lib().launch_count()
             cap = torch.cuda.Stream(device=dev)

@@ -300,6 +300,43 @@ def gru_wave_bwd(dy_top, gates, hp_b, mask, p_drop, WhhT, WihT, bt_dev, off_dev,
                   _ptr(sync_ws, torch.int32), _stream())
 
 
+def gru_cluster_supported(d, bt0, nl) -> int:
+    """Batch-tile rows (16/32/64) of the cluster GRU stack kernel (csrc/gru_cluster.cu) or 0."""
+    return int(_C.lib().raw("ark_gru_cluster_supported")(int(d), int(bt0), int(nl)))
+
+
+def gru_cluster_workspace_bytes(L, bt0, d, nl) -> int:
+    return int(_C.lib().raw("ark_gru_cluster_workspace_bytes")(int(L), int(bt0), int(d), int(nl)))
+
+
+def gru_cluster_fwd(x_b, hp_b, out_b, h0, Wih, Whh, b_ih, b_hh, bt_dev, off_dev, L, bt0, d, gates, mask, p_drop, seed,
+                    offset, offset_dev, sync_ws, ws):
+    """gru_wave_fwd's contract through thread-block clusters + distributed shared memory (csrc/gru_cluster.cu)."""
+    nl, N = hp_b.shape[0], hp_b.shape[1]
+    r, z, n, ghn = gates if gates is not None else (None, None, None, None)
+    _contig(x_b, hp_b, out_b, h0, r, z, n, ghn, mask, ws, *Wih, *Whh)
+    a_ih, a_hh = _ptr_array(Wih, torch.bfloat16), _ptr_array(Whh, torch.bfloat16)
+    a_bi, a_bh = _ptr_array(b_ih, torch.float32), _ptr_array(b_hh, torch.float32)
+    _C.lib().call("ark_gru_cluster_fwd", _ptr(x_b, torch.bfloat16), _ptr(hp_b, torch.bfloat16), _ptr(out_b, torch.bfloat16),
+                  _ptr(h0, torch.float32), a_ih, a_hh, a_bi, a_bh, _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32),
+                  L, bt0, N, d, nl, _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16), _ptr(n, torch.bfloat16),
+                  _ptr(ghn, torch.bfloat16), _ptr(mask, torch.uint8), float(p_drop), int(seed), int(offset),
+                  _ptr(offset_dev, torch.int64), _ptr(sync_ws, torch.int32), _ptr(ws, torch.uint8), ws.numel(), _stream())
+
+
+def gru_cluster_bwd(dy_top, gates, hp_b, mask, p_drop, WhhT, WihT, bt_dev, off_dev, L, bt0, d, dgi_b, dgh_b, dh0, sync_ws,
+                    ws):
+    nl, N = hp_b.shape[0], hp_b.shape[1]
+    r, z, n, ghn = gates
+    _contig(dy_top, r, z, n, ghn, hp_b, mask, dgi_b, dgh_b, dh0, ws, *WhhT, *[w for w in WihT if w is not None])
+    a_hh, a_ih = _ptr_array(WhhT, torch.bfloat16), _ptr_array(WihT, torch.bfloat16)
+    _C.lib().call("ark_gru_cluster_bwd", _ptr(dy_top, torch.float32), _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16),
+                  _ptr(n, torch.bfloat16), _ptr(ghn, torch.bfloat16), _ptr(hp_b, torch.bfloat16), _ptr(mask, torch.uint8),
+                  float(p_drop), a_hh, a_ih, _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32), L, bt0, N, d, nl,
+                  _ptr(dgi_b, torch.bfloat16), _ptr(dgh_b, torch.bfloat16), _ptr(dh0, torch.float32),
+                  _ptr(sync_ws, torch.int32), _ptr(ws, torch.uint8), ws.numel(), _stream())
+
+
 # ------------------------------------------------------------------ t-SAIL (Transformer) blocks: csrc/attn_ops.cu
 TOK, SQ = 0, 1
 

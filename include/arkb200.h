@@ -200,6 +200,31 @@ int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const uint16_t* z, 
                      const uint16_t* const* WihT_b, const int32_t* bt_dev, const int32_t* off_dev, int64_t L,
                      int64_t bt0, int64_t N, int64_t d, int64_t nl, uint16_t* dgi_b, uint16_t* dgh_b, float* dh0,
                      int32_t* sync_ws, void* stream);
+/* Cluster GRU STACK (ark_b200/csrc/gru_cluster.cu): same contract, tensors and Philox stream as ark_gru_wave_*
+ * (models.py:121-127,141) for short batch tiles and long chains: one thread-block cluster of d/32 CTAs per (layer,
+ * batch tile) keeps W_hh resident and exchanges the recurrent state (forward: h_t slices; backward: bf16 partial
+ * sums of dgh_t W_hh, reduce-scattered) through distributed shared memory instead of global memory; the input
+ * projections (forward W_ih u_t, backward dgi^{k+1} W_ih^{k+1}) run in separate pipelined CTAs of the same launch.
+ * ark_gru_cluster_supported returns the batch-tile rows NB (16/32/64) or 0 (needs d in {128,256,384,512}, nl <= 4,
+ * 2*nl*(d/32)*ceil(bt0/NB) <= 148 co-resident CTAs; queries the device).  ws: scratch of
+ * ark_gru_cluster_workspace_bytes(L, bt0, d, nl) bytes (16-byte aligned; the same buffer may serve fwd and bwd);
+ * sync_ws int32 [2*nl*ceil(bt0/NB)]. */
+int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl);
+/* debugging aid: with ARK_GRU_CLUSTER_DBG=<first iteration> in the environment the cluster kernels record a clock64
+ * timeline [2 dir][8 blockIdx.z][3 thread roles][4 iterations][16 points] of CTA (0,0) of every stage */
+int ark_gru_cluster_debug_dump(int64_t* out_host, int64_t n_words);
+int64_t ark_gru_cluster_workspace_bytes(int64_t L, int64_t bt0, int64_t d, int64_t nl);
+int ark_gru_cluster_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t* out_b, const float* h0,
+                        const uint16_t* const* Wih_b, const uint16_t* const* Whh_b, const float* const* b_ih,
+                        const float* const* b_hh, const int32_t* bt_dev, const int32_t* off_dev, int64_t L, int64_t bt0,
+                        int64_t N, int64_t d, int64_t nl, uint16_t* r, uint16_t* z, uint16_t* n, uint16_t* ghn,
+                        uint8_t* mask, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                        int32_t* sync_ws, void* ws, int64_t ws_bytes, void* stream);
+int ark_gru_cluster_bwd(const float* dy_top, const uint16_t* r, const uint16_t* z, const uint16_t* n, const uint16_t* ghn,
+                        const uint16_t* hp_b, const uint8_t* mask, float p_drop, const uint16_t* const* WhhT_b,
+                        const uint16_t* const* WihT_b, const int32_t* bt_dev, const int32_t* off_dev, int64_t L,
+                        int64_t bt0, int64_t N, int64_t d, int64_t nl, uint16_t* dgi_b, uint16_t* dgh_b, float* dh0,
+                        int32_t* sync_ws, void* ws, int64_t ws_bytes, void* stream);
 /* out[C,R] = in[R,C]^T (bf16) */
 int ark_transpose_bf16(const uint16_t* in, int64_t R, int64_t C, uint16_t* out, void* stream);
 

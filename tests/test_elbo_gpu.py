@@ -273,6 +273,40 @@ def test_gru_kernels_agree_wavefront_vs_per_layer_vs_per_step(spec, p_drop):
         assert rel < 2e-2, (other, rel)
 
 
+@pytest.mark.parametrize("spec", [
+    dict(nE=300, nR=6, lo=1, hi=15, pad=True, d=128, dz=16, nl=3, B=140),    # 4-CTA clusters, 3 ragged tiles of 64 rows
+    dict(nE=300, nR=6, lo=2, hi=40, pad=True, d=256, dz=16, nl=2, B=12),     # 8-CTA clusters, one 16-row tile, long chain
+    dict(nE=300, nR=6, lo=2, hi=30, pad=True, d=512, dz=16, nl=3, B=16),     # wd-articles shape: 16-CTA clusters
+    dict(nE=50, nR=4, lo=6, hi=6, pad=False, d=256, dz=8, nl=4, B=40),       # four layers, fixed length, 32-row tiles
+])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_gru_cluster_kernel_agrees_with_wavefront_and_per_layer(spec, p_drop):
+    """The cluster GRU stack (gru_cluster.cu: recurrent state exchanged through distributed shared memory, bf16
+    partial sums reduce-scattered in the backward) computes the same step as the wavefront and per-layer kernels,
+    with the same Philox dropout mask."""
+    from ark_b200 import ops
+    cfg, tri, seq, rng = _random_case(13, **spec)
+    cfg["dec_dropout"] = p_drop
+    B, d, nl = spec["B"], spec["d"], spec["nl"]
+    assert ops.gru_cluster_supported(d, B, nl) > 0
+    eps = torch.from_numpy(rng.standard_normal((B, spec["dz"])).astype(np.float32)).to(DEV)
+    seq_t = torch.from_numpy(seq)
+    lay = pack_layout(seq_t).to(DEV)
+    res = {}
+    for mode in ("cluster", "wave", "layer"):
+        torch.manual_seed(4)
+        model = SAIL(dict(cfg)).to(DEV)
+        eng = model.engine(seed=11)
+        eng.gru_mode = mode
+        out = eng.forward_backward(torch.from_numpy(tri).to(DEV), seq_t.to(DEV), lay, eps, 0.5).clone()
+        res[mode] = (out, eng.flat.grad.clone(), eng.philox_offset)
+    assert res["cluster"][2] == res["wave"][2] == res["layer"][2]
+    for other in ("wave", "layer"):
+        torch.testing.assert_close(res["cluster"][0], res[other][0], rtol=5e-3, atol=1e-5)
+        rel = ((res["cluster"][1] - res[other][1]).norm() / res[other][1].norm()).item()
+        assert rel < 2e-2, (other, rel)
+
+
 def test_cuda_graph_step_matches_eager_step():
     """Replaying the captured step (device-resident Adam scalars / Philox offset) == launching it eagerly."""
     cfg, tri, seq, rng = _random_case(21, nE=60, nR=4, lo=4, hi=4, pad=False, d=64, dz=8, nl=2, B=40)
