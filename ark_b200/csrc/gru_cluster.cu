@@ -38,12 +38,11 @@ namespace ark {
 constexpr int GC_MAXL = 4;
 constexpr int GC_DJ = 32;      // hidden units per CTA
 constexpr int GC_GS = 4;       // slots of the gi / dx prefetch ring in a recurrence CTA
-constexpr int GC_WCH = 96 * 128;   // bytes of one 64-wide k-chunk of a resident [96 x d] weight slice (128B swizzle)
 
 struct GruClFwdParams {
   CUtensorMap tmU[GC_MAXL];    // layer input rows u^k [N,d] bf16 (u^0 = token embeddings), k-chunked box {64, NB, d/64}
-  CUtensorMap tmWih[GC_MAXL];  // W_ih^k [3d,d] bf16, box {64, 32}
-  CUtensorMap tmWhh[GC_MAXL];  // W_hh^k [3d,d] bf16, box {64, 32}
+  const uint16_t* wih[GC_MAXL];   // W_ih^k / W_hh^k [3d,d] bf16: every CTA copies its 96 rows into TENSOR MEMORY once
+  const uint16_t* whh[GC_MAXL];   // (the UMMA A operand), so a step only streams the [NB x d] B operand from smem
   const float* b_ih[GC_MAXL];
   const float* b_hh[GC_MAXL];
   const int32_t* bt;
@@ -67,7 +66,7 @@ struct GruClFwdParams {
 
 struct GruClBwdParams {
   CUtensorMap tmDgi[GC_MAXL];     // dgi^k [N,3d] bf16, k-chunked box {64, NB, 3d/64}   (read by projection k-1)
-  CUtensorMap tmWhhT[GC_MAXL];    // W_hh^k^T [d,3d] bf16, NO swizzle, box {8, 128}
+  const uint16_t* whhT[GC_MAXL];  // W_hh^k^T [d,3d] bf16: every recurrence CTA copies its [d x 96] slice into TMEM
   CUtensorMap tmWihT[GC_MAXL];    // W_ih^k^T [d,3d] bf16, box {64, 32}                   (read by projection k-1)
   const int32_t* bt;
   const int32_t* off;
@@ -156,13 +155,31 @@ __device__ __forceinline__ void signaller_loop(uint32_t* ctr, uint32_t per_iter,
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Copy rows {g*d + j0 + lane} (g = TMEM lane quadrant q < 3) of a [3d, d] bf16 weight matrix into TMEM columns
+// [0, d/2) of lanes 32q..32q+31 (A operand of kind::f16 in tensor memory: column c = K elements 2c, 2c+1).
+// Called by the four epilogue warps.
+__device__ __forceinline__ void load_gate_rows_to_tmem(uint32_t tmem_base, const uint16_t* W, int d, int j0, int q, int lane) {
+  const uint4* src = reinterpret_cast<const uint4*>(W + ((int64_t)q * d + j0 + lane) * d);
+  for (int c0 = 0; c0 < d / 2; c0 += 16) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (q < 3) v = src[c0 / 4 + i];
+      r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+    ptx::tmem_st_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+  }
+  ptx::tmem_st_wait();
+}
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
 template <int NB>
 __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __grid_constant__ GruClFwdParams p) {
   constexpr int NI = NB / 16;                 // work items per epilogue thread
-  constexpr uint32_t TMEM_COLS = 2 * NB < 32 ? 32 : 2 * NB;
+  constexpr uint32_t TMEM_COLS = 512;        // weight slice (d/2 columns) + two accumulators of NB columns
   constexpr int XROW = 100;                   // staged recurrent pre-activations [NB][r 32 | z 32 | n_h 32 | pad]
   constexpr uint32_t SB = NB * 64;            // bytes of one CTA's slice of an h buffer: [4 k-groups][NB/8][8 x 16 B]
   constexpr uint32_t GB = 96 * NB * 4;        // bytes of one gi slice [NB][96] fp32
@@ -170,6 +187,12 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int d = p.d, L = p.L, nl = p.nl, nbt = p.nbt;
+  // the step table (rows alive per step, first packed row of a step) is read on the recurrent chain: keep it in
+  // shared memory (visible after the __syncthreads of the set-up below)
+  int32_t* bt_s = reinterpret_cast<int32_t*>(smem);
+  int32_t* off_s = bt_s + L;
+  for (int i = threadIdx.x; i < L; i += GC_THREADS) { bt_s[i] = p.bt[i]; off_s[i] = p.off[i]; }
+  smem += (2 * L * 4 + 1023) / 1024 * 1024;
   const int CS = d / GC_DJ, nkc = d / 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x, bi = blockIdx.y;
@@ -178,10 +201,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
   const int j0 = c * GC_DJ, m0 = bi * NB;
   int32_t* rec_done = p.sync + k * nbt + bi;
   int32_t* proj_done = p.sync + (nl + k) * nbt + bi;
-  const uint32_t w_bytes = (uint32_t)nkc * GC_WCH;
-  uint8_t* w_sm = smem;                       // resident weight slice (A operand); its last chunk's 128-row UMMA
-                                              // window overshoots 4 KB into the next region (in-allocation)
-  const CUtensorMap* tmW = is_proj ? &p.tmWih[k] : &p.tmWhh[k];
+  const uint16_t* W = is_proj ? p.wih[k] : p.whh[k];
+  const uint32_t A_COLS = (uint32_t)d / 2;    // TMEM columns of the resident weight slice [128 lanes x d bf16]
   const int q = warp & 3;                     // TMEM lane quadrant of an epilogue warp
   const int tid = threadIdx.x - 64;           // epilogue thread index (warps 2..5)
   const int n_steps = active_steps(p.bt, L, m0);
@@ -190,10 +211,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
     // ------------------------------------------------------------------------------ projection CTA
     const int S = p.S;
     const uint32_t slot_bytes = (uint32_t)nkc * NB * 128;
-    uint8_t* ring = w_sm + w_bytes;
+    uint8_t* ring = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * slot_bytes);
-    uint64_t* w_bar = bars;
-    uint64_t* full_bar = bars + 1;
+    uint64_t* full_bar = bars;
     uint64_t* empty_bar = full_bar + S;
     uint64_t* tmem_full = empty_bar + S;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -201,7 +221,6 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
     uint32_t* tmem_ptr_smem = sig_ctr + 1;
     if (threadIdx.x == 0) {
       ptx::prefetch_tmap(&p.tmU[k]);
-      ptx::mbar_init(w_bar, 1);
       for (int s = 0; s < S; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
       for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 128); }
       *sig_ctr = 0;
@@ -212,13 +231,13 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp >= 2 && warp < 6) load_gate_rows_to_tmem(tmem_base, W, d, j0, q, lane);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
     ptx::cluster_sync_all();
     if (warp == 0) {
       if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(w_bar, w_bytes);
-        for (int kc = 0; kc < nkc; ++kc)
-          for (int g = 0; g < 3; ++g)
-            ptx::tma_load_2d(w_sm + kc * GC_WCH + g * 4096, tmW, w_bar, kc * 64, g * d + j0);
         const int32_t* below = p.sync + (k - 1) * nbt + bi;
         for (int t = 0; t < n_steps; ++t) {
           GC_DBG(0, 0, t, 0);
@@ -227,29 +246,28 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
           const int s = t % S;
           ptx::mbar_wait(&empty_bar[s], ((t / S) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[s], slot_bytes);
-          ptx::tma_load_3d(ring + (size_t)s * slot_bytes, &p.tmU[k], &full_bar[s], 0, p.off[t] + m0, 0);
+          ptx::tma_load_3d(ring + (size_t)s * slot_bytes, &p.tmU[k], &full_bar[s], 0, off_s[t] + m0, 0);
           GC_DBG(0, 0, t, 2);
         }
       }
     } else if (warp == 1) {
       if (ptx::elect_one()) {
         constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
-        ptx::mbar_wait(w_bar, 0);
-        const uint32_t w_addr = ptx::smem_u32(w_sm), r_addr = ptx::smem_u32(ring);
+        const uint32_t r_addr = ptx::smem_u32(ring);
         for (int t = 0; t < n_steps; ++t) {
           const int s = t % S, par = t & 1;
           if (t >= 2) ptx::mbar_wait(&tmem_empty[par], ((t >> 1) - 1) & 1);
           ptx::mbar_wait(&full_bar[s], (t / S) & 1);
           ptx::tc_fence_after();
           GC_DBG(0, 1, t, 0);
-          const uint32_t acc = tmem_base + (uint32_t)(par * NB);
-          uint64_t adesc = ptx::make_smem_desc_sw128(w_addr, 16, 1024);
+          const uint32_t acc = tmem_base + A_COLS + (uint32_t)(par * NB);
+          uint32_t a_tm = tmem_base;
           uint64_t bdesc = ptx::make_smem_desc_sw128(r_addr + s * slot_bytes, 16, 1024);
           for (int kc = 0; kc < nkc; ++kc) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              ptx::umma_f16(acc, desc_adv(adesc, kk * 32), desc_adv(bdesc, kk * 32), idesc, (kc | kk) != 0 ? 1u : 0u);
-            adesc = desc_adv(adesc, GC_WCH);
+              ptx::umma_f16_ts(acc, a_tm + kk * 8, desc_adv(bdesc, kk * 32), idesc, (kc | kk) != 0 ? 1u : 0u);
+            a_tm += 32;
             bdesc = desc_adv(bdesc, NB * 128);
           }
           ptx::umma_commit(&empty_bar[s]);
@@ -271,7 +289,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
         if (tid == 0) GC_DBG(0, 2, t, 1);
         if (q < 3) {
           uint32_t v[NB];
-          tmem_ld_cols<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(par * NB), v);
+          tmem_ld_cols<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + A_COLS + (uint32_t)(par * NB), v);
           // gi slice [NB][96]: lanes of a warp write 128 contiguous bytes per batch row
           float* dst = p.git + ((((int64_t)k * L + t) * nbt + bi) * CS + c) * 96 * NB + q * 32 + lane;
 #pragma unroll
@@ -294,20 +312,18 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
 
   // -------------------------------------------------------------------------------- recurrence CTA
   const uint32_t HB = (uint32_t)NB * d * 2;    // one h buffer
-  uint8_t* hbuf = w_sm + w_bytes;              // [2][HB]
+  uint8_t* hbuf = smem;                        // [2][HB]
   uint8_t* send = hbuf + 2 * HB;               // [2][SB]
   uint8_t* gi_sm = send + 2 * SB;              // [GC_GS][GB]
   float* xs = reinterpret_cast<float*>(gi_sm + GC_GS * GB);   // [NB][XROW]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xs + NB * XROW);
-  uint64_t* w_bar = bars;
-  uint64_t* hbar = bars + 1;                   // [2]
+  uint64_t* hbar = bars;                       // [2]
   uint64_t* gi_full = hbar + 2;                // [GC_GS]
   uint64_t* gi_empty = gi_full + GC_GS;        // [GC_GS]
   uint64_t* tmem_full = gi_empty + GC_GS;      // [2]
   uint32_t* sig_ctr = reinterpret_cast<uint32_t*>(tmem_full + 2);
   uint32_t* tmem_ptr_smem = sig_ctr + 1;
   if (threadIdx.x == 0) {
-    ptx::mbar_init(w_bar, 1);
     ptx::mbar_init(&hbar[0], 1);
     ptx::mbar_init(&hbar[1], 1);
     for (int s = 0; s < GC_GS; ++s) { ptx::mbar_init(&gi_full[s], 1); ptx::mbar_init(&gi_empty[s], 1); }
@@ -321,14 +337,14 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp >= 2 && warp < 6) load_gate_rows_to_tmem(tmem_base, W, d, j0, q, lane);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
   ptx::cluster_sync_all();                     // every peer's mbarriers exist before the first remote complete_tx
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(w_bar, w_bytes);
-      for (int kc = 0; kc < nkc; ++kc)
-        for (int g = 0; g < 3; ++g)
-          ptx::tma_load_2d(w_sm + kc * GC_WCH + g * 4096, tmW, w_bar, kc * 64, g * d + j0);
       for (int t = 0; t < n_steps; ++t) {
         const int s = t % GC_GS;
         GC_DBG(0, 0, t, 0);
@@ -344,22 +360,21 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
-      ptx::mbar_wait(w_bar, 0);
-      const uint32_t w_addr = ptx::smem_u32(w_sm), h_addr = ptx::smem_u32(hbuf);
+      const uint32_t h_addr = ptx::smem_u32(hbuf);
       for (int t = 0; t < n_steps; ++t) {
         const int par = t & 1;
         GC_DBG(0, 1, t, 0);
         ptx::mbar_wait_cluster(&hbar[par], (t >> 1) & 1);     // all CS slices of h_{t-1} landed in hbuf[par]
         ptx::tc_fence_after();
         GC_DBG(0, 1, t, 1);
-        const uint32_t acc = tmem_base + (uint32_t)(par * NB);
-        uint64_t adesc = ptx::make_smem_desc_sw128(w_addr, 16, 1024);
+        const uint32_t acc = tmem_base + A_COLS + (uint32_t)(par * NB);
+        uint32_t a_tm = tmem_base;
         uint64_t bdesc = nosw_desc(h_addr + par * HB, H_LBO, H_SBO, p.swap_lbo);
         for (int kc = 0; kc < nkc; ++kc) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            ptx::umma_f16(acc, desc_adv(adesc, kk * 32), desc_adv(bdesc, kk * 2 * H_LBO), idesc, (kc | kk) != 0 ? 1u : 0u);
-          adesc = desc_adv(adesc, GC_WCH);
+            ptx::umma_f16_ts(acc, a_tm + kk * 8, desc_adv(bdesc, kk * 2 * H_LBO), idesc, (kc | kk) != 0 ? 1u : 0u);
+          a_tm += 32;
           bdesc = desc_adv(bdesc, 8 * H_LBO);
         }
         ptx::umma_commit(&tmem_full[par]);
@@ -387,9 +402,13 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
     // byte offset of (row bl, unit 4*quad) inside a slice [4 k-groups][NB/8][8 rows x 16 B]
     auto slice_off = [&](int bl) { return (uint32_t)((quad >> 1) * (NB * 16) + (bl >> 3) * 128 + (bl & 7) * 16 + (quad & 1) * 8); };
     // loop-invariant remote addresses of the bulk copies this thread issues (tid < CS: to peer (tid + me) % CS)
+    // (peer index pidx = 4 * (tid & 31) + (tid >> 5) for the first CS/4 lanes of each warp: the copies are issued by
+    // four warps in parallel)
     uint32_t dst_h[2] = {0, 0}, dst_bar[2] = {0, 0};
-    if (tid < CS) {
-      const uint32_t peer = ((uint32_t)tid + me) % (uint32_t)CS;
+    const int pidx = 4 * (tid & 31) + (tid >> 5);
+    const bool sender = pidx < CS;
+    if (sender) {
+      const uint32_t peer = ((uint32_t)pidx + me) % (uint32_t)CS;
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         dst_h[par] = ptx::mapa_u32(ptx::smem_u32(hbuf + par * HB + me * SB), peer);
@@ -400,10 +419,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       epi_bar_sync();
       if (tid == 0) ptx::mbar_arrive_expect_tx(&hbar[par], (uint32_t)CS * SB);
-      if (tid < CS) ptx::bulk_copy_s2c(dst_h[par], ptx::smem_u32(send + par * SB), SB, dst_bar[par]);
+      if (sender) ptx::bulk_copy_s2c(dst_h[par], ptx::smem_u32(send + par * SB), SB, dst_bar[par]);
     };
     float hreg[NI][4];
-    const int bt0 = p.bt[0];
+    const int bt0 = bt_s[0];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int bl = row0 + 16 * i, b = m0 + bl;
@@ -417,8 +436,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
     }
     send_slice(0);
     for (int t = 0; t < n_steps; ++t) {
-      const int Bt = p.bt[t];
-      const int Bn = (t + 1 < L) ? p.bt[t + 1] : 0;
+      const int Bt = bt_s[t];
+      const int Bn = (t + 1 < L) ? bt_s[t + 1] : 0;
       const bool next = t + 1 < n_steps;
       const int par = t & 1, s = t % GC_GS;
       const float* gi = reinterpret_cast<const float*>(gi_sm + s * GB);   // [NB][96]
@@ -429,7 +448,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
       if (tid == 0) GC_DBG(0, 2, t, 1);
       if (q < 3) {                              // TMEM lane = gate row (q, lane), column = batch row
         uint32_t v[NB];
-        tmem_ld_cols<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(par * NB), v);
+        tmem_ld_cols<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + A_COLS + (uint32_t)(par * NB), v);
         float* dst = xs + q * 32 + lane;
 #pragma unroll
         for (int b = 0; b < NB; ++b) dst[b * XROW] = __uint_as_float(v[b]) + bhn;
@@ -473,8 +492,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
       if (tid == 0) ptx::mbar_arrive(&gi_empty[s]);
       if (tid == 0) GC_DBG(0, 2, t, 4);
       // ---- off the recurrent chain: saved tensors, layer output (+ dropout); the signaller releases the counter
-      const int64_t base = (int64_t)p.off[t] + m0;
-      const int64_t base_n = next ? (int64_t)p.off[t + 1] + m0 : 0;
+      const int64_t base = (int64_t)off_s[t] + m0;
+      const int64_t base_n = next ? (int64_t)off_s[t + 1] + m0 : 0;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int bl = row0 + 16 * i, b = m0 + bl;
@@ -518,12 +537,20 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
 template <int NB>
 __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __grid_constant__ GruClBwdParams p) {
   constexpr int NI = NB / 16;
-  constexpr uint32_t SB = NB * 64;            // one (source, destination) block of partial sums: [NB][32] bf16
+  constexpr int BQ = NB / 4;                  // batch rows per (unit, quarter) cell of a partial-sum block
+  constexpr int RT = 36;
+  constexpr uint32_t SB = NB * 64;            // one (source, destination) block of partial sums: [4][32 units][BQ] bf16
   constexpr uint32_t DXB = 32 * NB * 4;       // one dx slice [NB][32] fp32
   constexpr uint32_t B_LBO = NB * 16, B_SBO = 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int d = p.d, L = p.L, nl = p.nl, nbt = p.nbt;
+  // the step table (rows alive per step, first packed row of a step) is read on the recurrent chain: keep it in
+  // shared memory (visible after the __syncthreads of the set-up below)
+  int32_t* bt_s = reinterpret_cast<int32_t*>(smem);
+  int32_t* off_s = bt_s + L;
+  for (int i = threadIdx.x; i < L; i += GC_THREADS) { bt_s[i] = p.bt[i]; off_s[i] = p.off[i]; }
+  smem += (2 * L * 4 + 1023) / 1024 * 1024;
   const int CS = d / GC_DJ, MT = d / 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x, bi = blockIdx.y;
@@ -581,7 +608,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
           ptx::mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
           GC_DBG(1, 0, it, 2);
           ptx::mbar_arrive_expect_tx(&full_bar[s], slot_bytes);
-          ptx::tma_load_3d(ring + (size_t)s * slot_bytes, tmA, &full_bar[s], 0, p.off[t] + m0, 0);
+          ptx::tma_load_3d(ring + (size_t)s * slot_bytes, tmA, &full_bar[s], 0, off_s[t] + m0, 0);
         }
       }
     } else if (warp == 1) {
@@ -641,17 +668,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
   }
 
   // -------------------------------------------------------------------------------- recurrence CTA
-  constexpr uint32_t TMEM_COLS_R = 4 * NB < 32 ? 32 : 4 * NB;   // MT <= 4 accumulators of NB columns
+  constexpr uint32_t TMEM_COLS_R = 512;   // MT <= 4 weight tiles of 48 columns + MT accumulators of NB columns
   const bool top = (k == nl - 1);
-  const uint32_t a_bytes = (uint32_t)d * 192;                // [MT][12 k-groups][128 rows x 16 B], no swizzle
-  uint8_t* a_sm = smem;
-  uint8_t* bop = a_sm + a_bytes;                             // dgh_c^T [NB x 96] bf16, no swizzle: [12][NB/8][128 B]
+  const uint32_t ACC0 = (uint32_t)MT * 48;                   // first accumulator column
+  uint8_t* bop = smem;                                       // dgh_c^T [NB x 96] bf16, no swizzle: [12][NB/8][128 B]
   uint8_t* stage = bop + NB * 192;                           // [2][CS][SB]
   uint8_t* recv = stage + 2 * CS * SB;                       // [2][CS][SB]
   uint8_t* dx_sm = recv + 2 * CS * SB;                       // [GC_GS][DXB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dx_sm + GC_GS * DXB);
-  uint64_t* w_bar = bars;
-  uint64_t* rbar = bars + 1;                                 // [2]
+  float* recT = reinterpret_cast<float*>(dx_sm + GC_GS * DXB);   // [NB][RT]: summed partials, transposed for the gate math
+  uint64_t* bars = reinterpret_cast<uint64_t*>(recT + NB * RT);
+  uint64_t* rbar = bars;                                     // [2]
   uint64_t* bop_full = rbar + 2;
   uint64_t* tmem_full = bop_full + 1;
   uint64_t* dx_full = tmem_full + 1;                         // [GC_GS]
@@ -659,7 +685,6 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
   uint32_t* sig_ctr = reinterpret_cast<uint32_t*>(dx_empty + GC_GS);
   uint32_t* tmem_ptr_smem = sig_ctr + 1;
   if (threadIdx.x == 0) {
-    ptx::mbar_init(w_bar, 1);
     ptx::mbar_init(&rbar[0], 1);
     ptx::mbar_init(&rbar[1], 1);
     ptx::mbar_init(bop_full, 1);
@@ -673,14 +698,31 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp >= 2 && warp < 6) {
+    // A operand in tensor memory: M-tile mt = output units mt*128 .. +128 (lane = unit), K = the 96 gate rows of this
+    // CTA (column 16 g + c = rows g*d + j0 + 2c, 2c+1 of W_hh, i.e. columns of W_hh^T)
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint16_t* row = p.whhT[k] + (int64_t)(mt * 128 + q * 32 + lane) * (3 * d) + j0;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 v = *reinterpret_cast<const uint4*>(row + (int64_t)g * d + i * 8);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        ptx::tmem_st_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 48 + g * 16), r);
+      }
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
   ptx::cluster_sync_all();
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(w_bar, a_bytes);
-      for (int mt = 0; mt < MT; ++mt)
-        for (int kg = 0; kg < 12; ++kg)
-          ptx::tma_load_2d(a_sm + (mt * 12 + kg) * 2048, &p.tmWhhT[k], w_bar, (kg >> 2) * d + j0 + (kg & 3) * 8, mt * 128);
       if (!top) {
         for (int it = 0; it <= t_first; ++it) {
           const int t = t_first - it, s = it % GC_GS;
@@ -698,21 +740,18 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
-      ptx::mbar_wait(w_bar, 0);
-      const uint32_t a_addr = ptx::smem_u32(a_sm), b_addr = ptx::smem_u32(bop);
+      const uint32_t b_addr = ptx::smem_u32(bop);
       for (int it = 0; it <= t_first; ++it) {
         GC_DBG(1, 1, it, 0);
         ptx::mbar_wait(bop_full, it & 1);
         ptx::tc_fence_after();
         GC_DBG(1, 1, it, 1);
-        uint64_t adesc = nosw_desc(a_addr, 2048, 128, p.swap_lbo);
         const uint64_t bdesc = nosw_desc(b_addr, B_LBO, B_SBO, p.swap_lbo);
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
           for (int ks = 0; ks < 6; ++ks)
-            ptx::umma_f16(tmem_base + (uint32_t)(mt * NB), desc_adv(adesc, ks * 2 * 2048), desc_adv(bdesc, ks * 2 * B_LBO), idesc,
-                          ks != 0 ? 1u : 0u);
-          adesc = desc_adv(adesc, 12 * 2048);
+            ptx::umma_f16_ts(tmem_base + ACC0 + (uint32_t)(mt * NB), tmem_base + (uint32_t)(mt * 48 + ks * 8),
+                             desc_adv(bdesc, ks * 2 * B_LBO), idesc, ks != 0 ? 1u : 0u);
         }
         ptx::umma_commit(tmem_full);
         GC_DBG(1, 1, it, 2);
@@ -736,8 +775,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
     uint16_t* dgi_k = p.dgi_b + (int64_t)k * LS * 3;
     uint16_t* dgh_k = p.dgh_b + (int64_t)k * LS * 3;
     uint32_t dst_r[2] = {0, 0}, dst_bar[2] = {0, 0}, src_off = 0;
-    if (tid < CS) {
-      const uint32_t peer = ((uint32_t)tid + me) % (uint32_t)CS;
+    const int pidx = 4 * (tid & 31) + (tid >> 5);           // the copies are issued by four warps in parallel
+    const bool sender = pidx < CS;
+    if (sender) {
+      const uint32_t peer = ((uint32_t)pidx + me) % (uint32_t)CS;
       src_off = peer * SB;
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
@@ -755,8 +796,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
     uint32_t mk[NI];
     uint2 sp[NI][5];
     auto prefetch = [&](int t) {
-      const int Bt = p.bt[t];
-      const int64_t base = (int64_t)p.off[t] + m0;
+      const int Bt = bt_s[t];
+      const int64_t base = (int64_t)off_s[t] + m0;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int bl = row0 + 16 * i;
@@ -773,8 +814,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
       }
     };
     auto prefetch_far = [&](int t) {           // pull the rows of a later iteration into L2 (they come from HBM)
-      const int Bt = p.bt[t];
-      const int64_t base = (int64_t)p.off[t] + m0;
+      const int Bt = bt_s[t];
+      const int64_t base = (int64_t)off_s[t] + m0;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int bl = row0 + 16 * i;
@@ -795,27 +836,50 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
     if (t_first >= 2) prefetch_far(t_first - 2);
     for (int it = 0; it <= t_first + 1; ++it) {
       const int t = t_first - it;                           // t = -1: gradient of the initial state
-      const int Bt = p.bt[t < 0 ? 0 : t];
-      const int B_next = (t + 1 <= L - 1) ? p.bt[t + 1] : 0;
-      float rec[NI][4];
-#pragma unroll
-      for (int i = 0; i < NI; ++i)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) rec[i][e] = 0.f;
+      const int Bt = bt_s[t < 0 ? 0 : t];
+      const int B_next = (t + 1 <= L - 1) ? bt_s[t + 1] : 0;
       if (tid == 0) GC_DBG(1, 2, it, 0);
       if (it > 0) {                                         // partial sums of dgh_{t+1} W_hh from every CTA of the cluster
         const int e = it - 1;
         ptx::mbar_wait_cluster(&rbar[e & 1], (e >> 1) & 1);
         if (tid == 0) GC_DBG(1, 2, it, 1);
-        const uint8_t* rb = recv + (e & 1) * CS * SB + quad * 8;
-        for (int cc = 0; cc < CS; ++cc) {
+        // thread (unit = lane, quarter = tid >> 5) adds the CS blocks of its BQ batch rows, then the sums are
+        // transposed through shared memory into the (row, 4 units) items of the gate math
+        const uint8_t* rb = recv + (e & 1) * CS * SB + tid * (BQ * 2);
+        float acc[4][BQ];
 #pragma unroll
-          for (int i = 0; i < NI; ++i) {
-            const uint2 v = *reinterpret_cast<const uint2*>(rb + cc * SB + (row0 + 16 * i) * 64);
-            const float2 a = unpack_bf16x2(v.x), b2 = unpack_bf16x2(v.y);
-            rec[i][0] += a.x; rec[i][1] += a.y; rec[i][2] += b2.x; rec[i][3] += b2.y;
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int i = 0; i < BQ; ++i) acc[u][i] = 0.f;
+        for (int cc = 0; cc < CS; cc += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if constexpr (BQ == 4) {
+              const uint2 v = *reinterpret_cast<const uint2*>(rb + (cc + u) * SB);
+              const float2 a = unpack_bf16x2(v.x), b2 = unpack_bf16x2(v.y);
+              acc[u][0] += a.x; acc[u][1] += a.y; acc[u][2] += b2.x; acc[u][3] += b2.y;
+            } else {
+#pragma unroll
+              for (int i = 0; i < BQ; i += 8) {
+                const uint4 v = *reinterpret_cast<const uint4*>(rb + (cc + u) * SB + i * 2);
+                const float2 a = unpack_bf16x2(v.x), b2 = unpack_bf16x2(v.y), c2 = unpack_bf16x2(v.z), e2 = unpack_bf16x2(v.w);
+                acc[u][i] += a.x; acc[u][i + 1] += a.y; acc[u][i + 2] += b2.x; acc[u][i + 3] += b2.y;
+                acc[u][i + 4] += c2.x; acc[u][i + 5] += c2.y; acc[u][i + 6] += e2.x; acc[u][i + 7] += e2.y;
+              }
+            }
           }
         }
+        float* rt = recT + (tid >> 5) * BQ * RT + lane;
+#pragma unroll
+        for (int i = 0; i < BQ; ++i) rt[i * RT] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
+        epi_bar_sync();
+      }
+      float rec[NI][4];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (it > 0) v = *reinterpret_cast<const float4*>(recT + (row0 + 16 * i) * RT + quad * 4);
+        rec[i][0] = v.x; rec[i][1] = v.y; rec[i][2] = v.z; rec[i][3] = v.w;
       }
       const int s = it % GC_GS;
       const float* dxs = reinterpret_cast<const float*>(dx_sm + s * DXB);   // [NB][32]
@@ -880,8 +944,6 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
         if (!top) ptx::mbar_arrive(&dx_empty[s]);
       }
       if (tid == 0) GC_DBG(1, 2, it, 5);
-      // while the MMA runs: the saved rows of the next iteration (their latency hides behind the exchange)
-      if (t - 1 >= 0) prefetch(t - 1);
       if (tid == 0) GC_DBG(1, 2, it, 6);
       ptx::mbar_wait(tmem_full, it & 1);
       ptx::tc_fence_after();
@@ -889,15 +951,27 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
       uint8_t* st = stage + (it & 1) * CS * SB;
       for (int mt = 0; mt < MT; ++mt) {
         uint32_t v[NB];
-        tmem_ld_cols<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB), v);
-        // block for CTA (mt*4 + q): [NB rows][32 units] bf16; lane = unit.  Lane pairs exchange so that the even lane
-        // writes the (even, odd) unit pair of the even rows and the odd lane that of the odd rows.
-        uint8_t* dst = st + (mt * 4 + q) * SB + (lane & ~1) * 2 + (lane & 1) * 64;
+        tmem_ld_cols<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + (uint32_t)(mt * NB), v);
+        // block for CTA (mt*4 + q): [4 quarters][32 units][BQ rows] bf16; lane = unit
+        uint8_t* dst = st + (mt * 4 + q) * SB + lane * (BQ * 2);
 #pragma unroll
-        for (int b = 0; b < NB; b += 2) {
-          const float mine0 = __uint_as_float(v[b]), mine1 = __uint_as_float(v[b + 1]);
-          const float other = __shfl_xor_sync(0xffffffffu, (lane & 1) ? mine0 : mine1, 1);
-          *reinterpret_cast<uint32_t*>(dst + b * 64) = (lane & 1) ? pack_bf16x2(other, mine1) : pack_bf16x2(mine0, other);
+        for (int e4 = 0; e4 < 4; ++e4) {
+          if constexpr (BQ == 4) {
+            uint2 w;
+            w.x = pack_bf16x2(__uint_as_float(v[e4 * 4]), __uint_as_float(v[e4 * 4 + 1]));
+            w.y = pack_bf16x2(__uint_as_float(v[e4 * 4 + 2]), __uint_as_float(v[e4 * 4 + 3]));
+            *reinterpret_cast<uint2*>(dst + e4 * 32 * (BQ * 2)) = w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < BQ; i += 8) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(v[e4 * BQ + i]), __uint_as_float(v[e4 * BQ + i + 1]));
+              w.y = pack_bf16x2(__uint_as_float(v[e4 * BQ + i + 2]), __uint_as_float(v[e4 * BQ + i + 3]));
+              w.z = pack_bf16x2(__uint_as_float(v[e4 * BQ + i + 4]), __uint_as_float(v[e4 * BQ + i + 5]));
+              w.w = pack_bf16x2(__uint_as_float(v[e4 * BQ + i + 6]), __uint_as_float(v[e4 * BQ + i + 7]));
+              *reinterpret_cast<uint4*>(dst + e4 * 32 * (BQ * 2) + i * 2) = w;
+            }
+          }
         }
       }
       ptx::tc_fence_before();
@@ -905,11 +979,12 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       epi_bar_sync();
       if (tid == 0) ptx::mbar_arrive_expect_tx(&rbar[it & 1], (uint32_t)CS * SB);
-      if (tid < CS) ptx::bulk_copy_s2c(dst_r[it & 1], ptx::smem_u32(st) + src_off, SB, dst_bar[it & 1]);
+      if (sender) ptx::bulk_copy_s2c(dst_r[it & 1], ptx::smem_u32(st) + src_off, SB, dst_bar[it & 1]);
       if (tid == 0) GC_DBG(1, 2, it, 9);
-      // ---- off the recurrent chain: the rows the weight-gradient GEMMs and the projection below read
+      // ---- off the recurrent chain (hidden behind the exchange): the rows the weight-gradient GEMMs and the
+      // projection below read, then the saved rows of the next iteration
       {
-        const int64_t base = (int64_t)p.off[t] + m0;
+        const int64_t base = (int64_t)off_s[t] + m0;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
           const int bl = row0 + 16 * i;
@@ -924,7 +999,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
           }
         }
       }
-      sig_arrive(sig_ctr);
+      sig_arrive(sig_ctr);                  // (a release: issued BEFORE the loads below so that it does not wait for them)
+      if (t - 1 >= 0) prefetch(t - 1);
       if (t - 3 >= 0) prefetch_far(t - 3);
       if (tid == 0) GC_DBG(1, 2, it, 10);
     }
@@ -940,8 +1016,9 @@ struct ClusterPlan {
   int NB, nbt, CS, S_f, S_b, smem_f, smem_b;
 };
 
-static bool plan_cluster(int64_t d, int64_t bt0, int64_t nl, ClusterPlan* out) {
-  if (d % 128 != 0 || d < 128 || d > 512 || bt0 <= 0 || nl < 1 || nl > GC_MAXL) return false;
+static bool plan_cluster(int64_t d, int64_t bt0, int64_t nl, int64_t L, ClusterPlan* out) {
+  if (d % 128 != 0 || d < 128 || d > 512 || bt0 <= 0 || nl < 1 || nl > GC_MAXL || L < 1 || L > 4096) return false;
+  const int64_t meta = (2 * L * 4 + 1023) / 1024 * 1024;   // step table in shared memory
   const int CS = (int)(d / GC_DJ);
   if (CS > 16) return false;
   const int cand[3] = {16, 32, 64};
@@ -949,18 +1026,17 @@ static bool plan_cluster(int64_t d, int64_t bt0, int64_t nl, ClusterPlan* out) {
     const int NB = cand[i];
     const int nbt = (int)((bt0 + NB - 1) / NB);
     if (2 * nl * CS * nbt > kNumSMs) continue;
-    const int64_t lim = 227 * 1024 - 1024;       // alignment slack
-    const int64_t w = d / 64 * GC_WCH;
-    // forward
-    const int64_t rec_f = w + 2 * (int64_t)NB * d * 2 + 2 * NB * 64 + (int64_t)GC_GS * 96 * NB * 4 + (int64_t)NB * 100 * 4 + 256;
+    const int64_t lim = 227 * 1024 - 1024 - meta;       // alignment slack, step table
+    if (d / 2 + 2 * NB > 512 || (d / 128) * (48 + NB) > 512) continue;   // tensor memory: weight slice + accumulators
+    // forward (the weight slices live in tensor memory)
+    const int64_t rec_f = 2 * (int64_t)NB * d * 2 + 2 * NB * 64 + (int64_t)GC_GS * 96 * NB * 4 + (int64_t)NB * 100 * 4 + 256;
     const int64_t slot_f = d / 64 * NB * 128;
-    int64_t S_f = (lim - w - 256) / slot_f;
+    int64_t S_f = (lim - 256) / slot_f;
     if (S_f > 4) S_f = 4;
     if (S_f < 2 || rec_f > lim) continue;
-    int64_t proj_f = w + S_f * slot_f + 256;
-    if (proj_f < w + 4096 + 256) proj_f = w + 4096 + 256;
+    const int64_t proj_f = S_f * slot_f + 256;
     // backward
-    const int64_t rec_b = d * 192 + NB * 192 + 4 * (int64_t)CS * NB * 64 + (int64_t)GC_GS * 32 * NB * 4 + 256;
+    const int64_t rec_b = NB * 192 + 4 * (int64_t)CS * NB * 64 + (int64_t)GC_GS * 32 * NB * 4 + (int64_t)NB * 36 * 4 + 256;
     const int64_t wb = 3 * d / 64 * 4096;
     const int64_t slot_b = 3 * d / 64 * NB * 128;
     int64_t S_b = (lim - wb - 256) / slot_b;
@@ -968,8 +1044,8 @@ static bool plan_cluster(int64_t d, int64_t bt0, int64_t nl, ClusterPlan* out) {
     if (S_b < 2 || rec_b > lim || S_b * slot_b < 12288) continue;
     const int64_t proj_b = wb + S_b * slot_b + 256;
     out->NB = NB; out->nbt = nbt; out->CS = CS; out->S_f = (int)S_f; out->S_b = (int)S_b;
-    out->smem_f = (int)((rec_f > proj_f ? rec_f : proj_f) + 1024);
-    out->smem_b = (int)((rec_b > proj_b ? rec_b : proj_b) + 1024);
+    out->smem_f = (int)((rec_f > proj_f ? rec_f : proj_f) + 1024 + meta);
+    out->smem_b = (int)((rec_b > proj_b ? rec_b : proj_b) + 1024 + meta);
     return true;
   }
   return false;
@@ -1060,14 +1136,14 @@ extern "C" int ark_gru_cluster_debug_dump(int64_t* out_host, int64_t n_words) {
   return e == cudaSuccess ? 0 : fail((int)e, "gru_cluster_debug_dump: %s", cudaGetErrorString(e));
 }
 
-extern "C" int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl) {
+extern "C" int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl, int64_t L) {
   ClusterPlan pl;
-  if (!plan_cluster(d, bt0, nl, &pl)) return 0;
+  if (!plan_cluster(d, bt0, nl, L, &pl)) return 0;
   // the kernels spin on flags of other clusters: every cluster of the launch must be co-resident
-  static thread_local struct { int64_t d, bt0, nl; int ok; } memo[16];
+  static thread_local struct { int64_t d, bt0, nl, L; int ok; } memo[16];
   static thread_local int n_memo = 0;
   for (int i = 0; i < n_memo; ++i)
-    if (memo[i].d == d && memo[i].bt0 == bt0 && memo[i].nl == nl) return memo[i].ok ? pl.NB : 0;
+    if (memo[i].d == d && memo[i].bt0 == bt0 && memo[i].nl == nl && memo[i].L == L) return memo[i].ok ? pl.NB : 0;
   GruClFwdParams pf;
   GruClBwdParams pb;
   memset(&pf, 0, sizeof(pf));
@@ -1077,13 +1153,13 @@ extern "C" int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl) {
                        pl.smem_f, 0, "gru_cluster_fwd", true) == 0 &&
            dispatch_nb(pl.NB, gru_cluster_bwd_kernel<16>, gru_cluster_bwd_kernel<32>, gru_cluster_bwd_kernel<64>, pb, gb, pl.CS,
                        pl.smem_b, 0, "gru_cluster_bwd", true) == 0;
-  if (n_memo < 16) { memo[n_memo].d = d; memo[n_memo].bt0 = bt0; memo[n_memo].nl = nl; memo[n_memo].ok = ok; ++n_memo; }
+  if (n_memo < 16) { memo[n_memo].d = d; memo[n_memo].bt0 = bt0; memo[n_memo].nl = nl; memo[n_memo].L = L; memo[n_memo].ok = ok; ++n_memo; }
   return ok ? pl.NB : 0;
 }
 
 extern "C" int64_t ark_gru_cluster_workspace_bytes(int64_t L, int64_t bt0, int64_t d, int64_t nl) {
   ClusterPlan pl;
-  if (!plan_cluster(d, bt0, nl, &pl)) return 0;
+  if (!plan_cluster(d, bt0, nl, L, &pl)) return 0;
   // forward gi^T scratch (the backward dx^T scratch is a third of it and reuses the same buffer)
   return nl * L * (int64_t)pl.nbt * pl.NB * 3 * d * 4;
 }
@@ -1102,7 +1178,7 @@ extern "C" int ark_gru_cluster_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t
   ARK_REQUIRE(L > 0 && N > 0 && bt0 > 0, ARK_E_BADARG, "gru_cluster_fwd: bad sizes");
   ARK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, ARK_E_BADARG, "gru_cluster_fwd: dropout probability must be in [0,1)");
   ClusterPlan pl;
-  ARK_REQUIRE(plan_cluster(d, bt0, nl, &pl), ARK_E_SHAPE,
+  ARK_REQUIRE(plan_cluster(d, bt0, nl, L, &pl), ARK_E_SHAPE,
               "gru_cluster_fwd: unsupported shape d=%lld bt0=%lld nl=%lld (need d in {128,256,384,512}, nl <= 4 and "
               "2*nl*(d/32)*ceil(bt0/NB) <= 148 CTAs)", (long long)d, (long long)bt0, (long long)nl);
   ARK_REQUIRE(ws_bytes >= ark_gru_cluster_workspace_bytes(L, bt0, d, nl), ARK_E_BADARG, "gru_cluster_fwd: workspace too small");
@@ -1119,8 +1195,9 @@ extern "C" int ark_gru_cluster_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t
     const uint16_t* u = k == 0 ? x_b : out_b + (int64_t)(k - 1) * LS;
     if ((rc = make_tmap_kchunked_bf16(&prm.tmU[k], u, (uint64_t)d, (uint64_t)N, (uint64_t)d, pl.NB, (uint32_t)(d / 64)))) return rc;
     ARK_REQUIRE(Wih_b[k] && Whh_b[k] && b_ih[k] && b_hh[k], ARK_E_BADARG, "gru_cluster_fwd: null weight pointer (layer %d)", k);
-    if ((rc = make_tmap_2d_bf16(&prm.tmWih[k], Wih_b[k], (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, 64, GC_DJ))) return rc;
-    if ((rc = make_tmap_2d_bf16(&prm.tmWhh[k], Whh_b[k], (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, 64, GC_DJ))) return rc;
+    ARK_REQUIRE(aligned16(Wih_b[k]) && aligned16(Whh_b[k]), ARK_E_ALIGN, "gru_cluster_fwd: weights must be 16-byte aligned");
+    prm.wih[k] = Wih_b[k];
+    prm.whh[k] = Whh_b[k];
     prm.b_ih[k] = b_ih[k];
     prm.b_hh[k] = b_hh[k];
   }
@@ -1147,7 +1224,7 @@ extern "C" int ark_gru_cluster_bwd(const float* dy_top, const uint16_t* r, const
   ARK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, ARK_E_BADARG, "gru_cluster_bwd: dropout probability must be in [0,1)");
   ARK_REQUIRE(p_drop == 0.f || nl == 1 || mask, ARK_E_BADARG, "gru_cluster_bwd: dropout needs the forward keep mask");
   ClusterPlan pl;
-  ARK_REQUIRE(plan_cluster(d, bt0, nl, &pl), ARK_E_SHAPE, "gru_cluster_bwd: unsupported shape d=%lld bt0=%lld nl=%lld",
+  ARK_REQUIRE(plan_cluster(d, bt0, nl, L, &pl), ARK_E_SHAPE, "gru_cluster_bwd: unsupported shape d=%lld bt0=%lld nl=%lld",
               (long long)d, (long long)bt0, (long long)nl);
   ARK_REQUIRE(ws_bytes >= ark_gru_cluster_workspace_bytes(L, bt0, d, nl), ARK_E_BADARG, "gru_cluster_bwd: workspace too small");
   ARK_REQUIRE(aligned16(dy_top) && aligned16(dgi_b) && aligned16(dgh_b) && aligned16(ws) && (!dh0 || aligned16(dh0)), ARK_E_ALIGN,
@@ -1167,8 +1244,8 @@ extern "C" int ark_gru_cluster_bwd(const float* dy_top, const uint16_t* r, const
     if ((rc = make_tmap_kchunked_bf16(&prm.tmDgi[k], dgi_b + (int64_t)k * LS * 3, (uint64_t)(3 * d), (uint64_t)N,
                                       (uint64_t)(3 * d), pl.NB, (uint32_t)(3 * d / 64)))) return rc;
     ARK_REQUIRE(WhhT_b[k] && (k == 0 || WihT_b[k]), ARK_E_BADARG, "gru_cluster_bwd: null weight pointer (layer %d)", k);
-    if ((rc = make_tmap_2d_bf16_nosw(&prm.tmWhhT[k], WhhT_b[k], (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), 8, 128)))
-      return rc;
+    ARK_REQUIRE(aligned16(WhhT_b[k]), ARK_E_ALIGN, "gru_cluster_bwd: weights must be 16-byte aligned");
+    prm.whhT[k] = WhhT_b[k];
     if (k > 0 && (rc = make_tmap_2d_bf16(&prm.tmWihT[k], WihT_b[k], (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), 64,
                                          GC_DJ))) return rc;
   }

@@ -102,11 +102,11 @@ class SailEngine:
 
     # ------------------------------------------------------------------ GRU driver choice
     def _use_gru_cluster(self, d, b0, nl, L):
-        """The cluster kernel wins where the chain is long and the batch tile short (its DSMEM exchange costs
-        ~1 us per step whatever the tile; the wavefront kernel's global-memory exchange ~2.3 us)."""
+        """Batch-tile rows of the cluster kernel (0 = do not use it).  It wins where the chain is long and the batch
+        tile short (its DSMEM exchange costs ~0.8 us per step; the wavefront kernel's global-memory exchange ~2.3 us)."""
         if self.gru_mode != "cluster" and L < 32:
-            return False
-        return ops.gru_cluster_supported(d, b0, nl) > 0
+            return 0
+        return ops.gru_cluster_supported(d, b0, nl, L)
 
     def _cluster_ws(self, L, b0, d, nl):
         need = ops.gru_cluster_workspace_bytes(L, b0, d, nl)
@@ -203,10 +203,14 @@ class SailEngine:
         b0 = int(lay.bt[0])
         saved = []
         u_b = x_b
-        cluster = (use_tc and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru
-                   and self._use_gru_cluster(d, b0, nl, L))
-        wave = cluster or (use_tc and self.gru_mode in ("auto", "wave") and not self.force_unfused_gru
-                           and ops.gru_wave_supported(d, b0, nl) > 0)
+        cl_nb = (self._use_gru_cluster(d, b0, nl, L)
+                 if (use_tc and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru) else 0)
+        wave_ok = use_tc and not self.force_unfused_gru and ops.gru_wave_supported(d, b0, nl) > 0
+        cluster = cl_nb > 0
+        # the two stack kernels share every tensor of their contract, so the direction can be chosen separately: with
+        # 64-row batch tiles the cluster backward (16 work items per epilogue thread) is no faster than the wavefront's
+        cluster_bwd = cluster and (cl_nb <= 32 or self.gru_mode == "cluster" or not wave_ok)
+        wave = cluster or (self.gru_mode in ("auto", "wave") and wave_ok)
         persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru and not wave
         gh_ws = None if (persist or wave) else new(b0, d3)
         sync_ws = new(2 * nl * ((b0 + 15) // 16), dtype=torch.int32) if (persist or wave) else None
@@ -301,12 +305,12 @@ class SailEngine:
                 if k > 0:
                     ops.transpose_bf16(self._w(f"dec.gru.weight_ih_l{k}"), w_t[nl + k])
             dgi_all, dgh_all = new(nl, N, d3, dtype=bf), new(nl, N, d3, dtype=bf)
-            with self._timed("gru_cluster_bwd" if cluster else "gru_wave_bwd", flops=4.0 * N * d * d3 * nl - 2.0 * N * d * d3):
+            with self._timed("gru_cluster_bwd" if cluster_bwd else "gru_wave_bwd", flops=4.0 * N * d * d3 * nl - 2.0 * N * d * d3):
                 bwd_args = (dy, wave_gates, hp_all, wave_mask, self.p_drop if wave_mask is not None else 0.0,
                             [w_t[k] for k in range(nl)], [None] + [w_t[nl + k] for k in range(1, nl)],
                             lay.bt_dev, lay.off_dev, L, b0, d, dgi_all, dgh_all, dh0 if self.has_enc else None,
                             sync_ws)
-                if cluster:
+                if cluster_bwd:
                     ops.gru_cluster_bwd(*bwd_args, cl_ws)
                 else:
                     ops.gru_wave_bwd(*bwd_args)

@@ -300,9 +300,9 @@ def gru_wave_bwd(dy_top, gates, hp_b, mask, p_drop, WhhT, WihT, bt_dev, off_dev,
                   _ptr(sync_ws, torch.int32), _stream())
 
 
-def gru_cluster_supported(d, bt0, nl) -> int:
+def gru_cluster_supported(d, bt0, nl, L) -> int:
     """Batch-tile rows (16/32/64) of the cluster GRU stack kernel (csrc/gru_cluster.cu) or 0."""
-    return int(_C.lib().raw("ark_gru_cluster_supported")(int(d), int(bt0), int(nl)))
+    return int(_C.lib().raw("ark_gru_cluster_supported")(int(d), int(bt0), int(nl), int(L)))
 
 
 def gru_cluster_workspace_bytes(L, bt0, d, nl) -> int:

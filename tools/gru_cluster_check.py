@@ -26,7 +26,7 @@ def main():
               for _ in range(B)]
     tri, seq = O.build_batch(graphs, layv)
     cfg = dict(layv, model_type="SAIL", d_model=d, d_latent=16, n_heads=2, n_layers=nl, dec_dropout=p_drop)
-    print("cluster supported NB =", ops.gru_cluster_supported(d, B, nl), " wave dj =", ops.gru_wave_supported(d, B, nl), flush=True)
+    print("cluster supported NB =", ops.gru_cluster_supported(d, B, nl, seq.shape[1] - 1), " wave dj =", ops.gru_wave_supported(d, B, nl), flush=True)
     eps = torch.from_numpy(rng.standard_normal((B, 16)).astype(np.float32)).cuda()
     seq_t = torch.from_numpy(seq)
     lay = pack_layout(seq_t).to("cuda")
