@@ -80,6 +80,21 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const T* __restrict__ X, i
   if (col < N) {
     const int64_t stride = (int64_t)gridDim.y * 8;
     int64_t r = (int64_t)blockIdx.y * 8 + ty;
+    for (; r + 3 * stride < M; r += 4 * stride) {   // four independent loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if constexpr (sizeof(T) == 2) {
+          const uint2 ua = *reinterpret_cast<const uint2*>(X + (r + u * stride) * ld + col);
+          const float2 a0 = unpack_bf16x2(ua.x), a1 = unpack_bf16x2(ua.y);
+          v[u] = make_float4(a0.x, a0.y, a1.x, a1.y);
+        } else {
+          v[u] = *reinterpret_cast<const float4*>(X + (r + u * stride) * ld + col);
+        }
+      }
+      acc.x += (v[0].x + v[1].x) + (v[2].x + v[3].x); acc.y += (v[0].y + v[1].y) + (v[2].y + v[3].y);
+      acc.z += (v[0].z + v[1].z) + (v[2].z + v[3].z); acc.w += (v[0].w + v[1].w) + (v[2].w + v[3].w);
+    }
     for (; r + stride < M; r += 2 * stride) {       // two independent loads in flight
       float4 a, b;
       if constexpr (sizeof(T) == 2) {
@@ -114,8 +129,10 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const T* __restrict__ X, i
     for (int k = 1; k < 8; ++k) {
       s4.x += part[k][tx].x; s4.y += part[k][tx].y; s4.z += part[k][tx].z; s4.w += part[k][tx].w;
     }
-    atomicAdd(out + col, s4.x); atomicAdd(out + col + 1, s4.y);
-    atomicAdd(out + col + 2, s4.z); atomicAdd(out + col + 3, s4.w);
+    atomicAdd(out + col, s4.x);
+    if (col + 1 < N) atomicAdd(out + col + 1, s4.y);    // N % 4 != 0: the last thread's tail columns are row padding
+    if (col + 2 < N) atomicAdd(out + col + 2, s4.z);
+    if (col + 3 < N) atomicAdd(out + col + 3, s4.w);
   }
 }
 
@@ -276,17 +293,19 @@ extern "C" int ark_colsum(const void* X, int dtype, int64_t M, int64_t N, int64_
   ARK_REQUIRE(X && out, ARK_E_BADARG, "colsum: null pointer");
   ARK_REQUIRE(M >= 0 && N > 0 && ld >= N, ARK_E_BADARG, "colsum: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
-  if (!accumulate) {
+  if (accumulate != 1) {
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s);
     if (e != cudaSuccess) return fail((int)e, "colsum: memset: %s", cudaGetErrorString(e));
   }
   if (M == 0) return 0;
-  const bool vec = (N % 4 == 0) && (ld % 4 == 0) && aligned16(X);
+  // vector path: 4 columns per thread; a ragged N is fine when the row padding up to the next multiple of 4 exists
+  const bool vec = (ld % 4 == 0) && aligned16(X) && ((N + 3) / 4 * 4 <= ld);
   const int64_t gx = vec ? (N + 127) / 128 : (N + 31) / 32;
   int64_t gy = (M + 63) / 64;
   const int64_t want = 4 * kNumSMs;  // enough CTAs to cover the machine, few enough atomics
   if (gx * gy > want) gy = (want + gx - 1) / gx;
   if (gy < 1) gy = 1;
+  if (accumulate == 2) gy = 1;       // deterministic: one CTA per column strip, fixed summation order (no cross-CTA atomics)
   dim3 grid((unsigned)gx, (unsigned)gy);
   if (dtype == ARK_BF16) {
     if (vec) colsum4_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)X, M, (int)N, ld, out);

@@ -1084,7 +1084,11 @@ static int launch_cluster(Kern kern, const Params& prm, dim3 grid, int cs, int s
               grid.y, grid.z, cs, smem, n, need);
     return n >= need ? 0 : fail(ARK_E_SHAPE, "%s: only %d of %lld clusters can be co-resident", who, n, need);
   }
-  cfg.numAttrs = 2;
+  // ARK_GRU_CLUSTER_NO_COOP=1 drops the cooperative attribute (Nsight Compute refuses cooperative cluster launches);
+  // co-residency was established by the occupancy query of ark_gru_cluster_supported
+  static int no_coop = -1;
+  if (no_coop < 0) { const char* ev = getenv("ARK_GRU_CLUSTER_NO_COOP"); no_coop = ev ? atoi(ev) : 0; }
+  cfg.numAttrs = no_coop ? 1 : 2;
   e = cudaLaunchKernelEx(&cfg, kern, prm);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();

@@ -82,6 +82,11 @@ class SailEngine:
                                          # wavefront stack kernel when it fits, else per-layer persistent;
                                          # "wave": never the cluster kernel; "layer": neither (tests / A-B timing)
         self._gru_cluster_ws = None      # scratch of the cluster GRU kernels (gi^T / dx^T slices), grown on demand
+        self.dp_factor_gather = True     # data parallel: all-gather the [B, 3d] FACTORS of the encoder-MLP weight
+                                         # gradients (dW = dY^T X, rank <= global batch) instead of all-reducing dW
+        self.dp_emb_min_bytes = None     # ... and (opt-in: a byte threshold) of the entity-embedding gradient of a large
+                                         # table.  Off by default: the scatter's atomics make the ranks' results differ
+                                         # in the last bits, so replicas would drift apart without a periodic re-sync
         self.stats = torch.zeros(4, device=dev)  # [ce, kl, steps, unused] accumulated on device
         self.refresh_shadow()
         if hasattr(model, "_attach_engine"):
@@ -179,6 +184,25 @@ class SailEngine:
                            bias=f.p(f"enc.mlp.{2 * k}.bias"), epilogue=ops.EPI_GELU, aux=pre)
                 acts.append(a_next)
                 pres.append(pre)
+            # data parallel: dW_k = dY_k^T X_k has rank <= global batch << 3d, so the ranks exchange the FACTORS
+            # ([B, 3d] bf16 each) instead of all-reducing the [3d, 3d] fp32 gradient: X_k now (hidden behind the whole
+            # decoder), dY_k at the end of backward; every rank then forms the global dW_k with one K = world*B GEMM
+            fg = (train and self.world > 1 and self.dp_factor_gather and (batch_global is None or batch_global == self.world * B))
+            # the entity-embedding gradient is a scatter of B x T rows into a [nE, d] table: when the table is large and
+            # the global batch touches few of its rows, every rank gathers the [B, 3d] upstream gradient + the triples
+            # of all ranks and runs the scatter over the GLOBAL batch instead of all-reducing the (mostly zero) table
+            nE_rows = f.p("enc.e_emb.weight").shape[0]
+            fg_emb = (fg and self.dp_emb_min_bytes is not None and nE_rows * d * 4 >= self.dp_emb_min_bytes
+                      and self.world * B * triples.shape[1] <= nE_rows)
+            if fg:
+                x_all = [new(self.world * B, d3, dtype=bf) for _ in range(self.n_mlp)]
+                gathers = [("gather", x_all[k], acts[k]) for k in range(self.n_mlp)]
+                if fg_emb:
+                    tri_p = triples.index_select(0, lay.perm_dev.long()).contiguous()      # rows in packed order
+                    tri_all = torch.empty((self.world * B,) + tuple(triples.shape[1:]), device=dev, dtype=triples.dtype)
+                    inv_all = new(self.world * B)
+                    gathers += [("gather", tri_all, tri_p), ("gather", inv_all, inv_cnt)]
+                self._comm_actions(gathers)
             w_heads = f.fused(f.shadow, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
             b_heads = f.fused(f.param, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
             heads = new(B, 2 * dz)
@@ -386,31 +410,60 @@ class SailEngine:
         self._grad_ready("dec.z_proj.weight", "enc.logv.bias")
 
         # ---------------- encoder MLP + pooled gather backward
+        dp_all = [None] * self.n_mlp
         for k in range(self.n_mlp - 1, -1, -1):
             dp_b = new(B, d3, dtype=bf)
             ops.gelu_bwd(da, pres[k], None, dp_b)
-            self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B, tag="enc_mlp_bwd")
-            ops.colsum(dp_b, B, d3, f.g(f"enc.mlp.{2 * k}.bias"))
+            if fg:
+                dp_all[k] = new(self.world * B, d3, dtype=bf)
+                self._comm_action(("gather", dp_all[k], dp_b))       # overlaps the rest of the chain
+            else:
+                self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B, tag="enc_mlp_bwd")
+                ops.colsum(dp_b, B, d3, f.g(f"enc.mlp.{2 * k}.bias"))
             da = new(B, d3)
             self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3, tag="enc_mlp_bwd")
-            self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
+            if not fg:
+                self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
         gE, gR = f.g("enc.e_emb.weight"), f.g("enc.r_emb.weight")
-        with self._timed("gather_pool_bwd", nbytes=gE.numel() * 4.0 + B * d3 * 4 + 3.0 * lay.n_triples * d * 8):
-            gR.zero_()
-            gE.zero_()
-            ops.gather_pool_bwd(da, triples, lay.perm_dev, inv_cnt, self.pad_rid, self.pad_eid, gE, gR)
-        self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight")
+        if fg and fg_emb:
+            da_all = new(self.world * B, d3)
+            self._comm_action(("gather", da_all, da))
+        else:
+            with self._timed("gather_pool_bwd", nbytes=gE.numel() * 4.0 + B * d3 * 4 + 3.0 * lay.n_triples * d * 8):
+                gR.zero_()
+                gE.zero_()
+                ops.gather_pool_bwd(da, triples, lay.perm_dev, inv_cnt, self.pad_rid, self.pad_eid, gE, gR)
+            self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight")
+        if fg:
+            self._flush_bucket()                    # the embedding gradients go first: their all-reduce overlaps the GEMMs below
+            self._comm_action(("join",))            # every rank's factors have arrived
+            wb = self.world * B
+            if fg_emb:
+                with self._timed("gather_pool_bwd", nbytes=gE.numel() * 4.0 + wb * d3 * 4 + 3.0 * lay.n_triples * self.world * d * 8):
+                    gR.zero_()
+                    gE.zero_()
+                    ops.gather_pool_bwd(da_all, tri_all, None, inv_all, self.pad_rid, self.pad_eid, gE, gR)
+                self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight", reduced=True)
+            for k in range(self.n_mlp - 1, -1, -1):
+                self._gemm(dp_all[k], MN, x_all[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, wb, tag="enc_mlp_dW_global")
+                ops.colsum(dp_all[k], wb, d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks must agree bitwise
+                self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias", reduced=True)
         return out
 
     # ------------------------------------------------------------------ gradient exchange + bucketed update
-    def _grad_ready(self, first, last):
+    def _grad_ready(self, first, last, reduced=False):
         """Gradient slots first..last (contiguous in the flat layout) are final AND their weights are no longer read
         by the rest of this backward pass.  They are merged into buckets; a full bucket is handed to the side stream,
         which (data parallel) sums it over ranks with NCCL and (inside a train step) applies Adam to exactly that
-        slice of the flat buffers — both overlap the remaining backward kernels on the main stream."""
+        slice of the flat buffers — both overlap the remaining backward kernels on the main stream.
+        reduced=True: the slots already hold the GLOBAL gradient (factor all-gather): Adam only, no all-reduce."""
         if self.world == 1 and self._upd is None:
             return
         s, e = self.flat.span(first, last)
+        if reduced:
+            self._flush_bucket()
+            self._comm_action(("bucket", [(s, e)], False))
+            return
         if self._pending and self._pending[-1][1] >= s - 64:
             self._pending[-1] = (self._pending[-1][0], e)
         else:
@@ -422,15 +475,42 @@ class SailEngine:
         if not self._pending:
             return
         spans, self._pending = self._pending, []
-        if self._capturing and self.world > 1:
-            # graph mode under data parallelism: end the graph segment here; the replay loop runs the bucket's NCCL
-            # all-reduce and Adam eagerly on the side stream while the NEXT segment runs (NCCL kernels are never
-            # captured: capturing them next to the cooperative GRU kernels hung at 2 ranks)
-            self._segment_break(spans)
-            return
-        self._bucket_async(spans)
+        self._comm_action(("bucket", spans, True))
 
-    def _bucket_async(self, spans, upd=None):
+    def _comm_action(self, action):
+        """Side-stream work that may contain NCCL calls: ("bucket", spans, allreduce) | ("gather", out, inp) |
+        ("join",).  Graph mode under data parallelism ends the graph segment here; the replay loop runs the action
+        eagerly while the NEXT segment runs (NCCL kernels are never captured: capturing them next to the cooperative
+        GRU kernels hung at 2 ranks)."""
+        if self._capturing and self.world > 1:
+            self._segment_break([action])
+            return
+        self._run_action(action, self._upd)
+
+    def _comm_actions(self, actions):
+        if self._capturing and self.world > 1:
+            self._segment_break(list(actions))      # one segment break for all of them
+            return
+        for a in actions:
+            self._run_action(a, self._upd)
+
+    def _run_action(self, action, upd):
+        kind = action[0]
+        if kind == "bucket":
+            self._bucket_async(action[1], upd, allreduce=action[2])
+        elif kind == "gather":      # all ranks' [B, n] rows -> [world * B, n], on the side stream
+            ev = torch.cuda.Event()
+            ev.record()
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                with self._timed("nccl_all_gather", nbytes=float(action[1].numel() * action[1].element_size())):
+                    torch.distributed.all_gather_into_tensor(action[1], action[2], group=self.group)
+        elif kind == "join":        # the main stream needs what the side stream produced
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            raise ValueError(kind)
+
+    def _bucket_async(self, spans, upd=None, allreduce=True):
         """On the side stream, ordered after everything queued on the current stream: all-reduce (world > 1) and,
         inside a train step, Adam over the slices."""
         upd = self._upd if upd is None else upd
@@ -440,8 +520,9 @@ class SailEngine:
         f = self.flat
         with torch.cuda.stream(self.comm_stream):
             for (s, e) in spans:
-                if self.world > 1:
-                    torch.distributed.all_reduce(f.grad[s:e], group=self.group)
+                if self.world > 1 and allreduce:
+                    with self._timed("nccl_all_reduce", nbytes=4.0 * (e - s)):
+                        torch.distributed.all_reduce(f.grad[s:e], group=self.group)
                 if upd is not None:
                     with self._timed("adam_flat", nbytes=30.0 * (e - s)):
                         if upd[0] == "dyn":     # graph replay: lr / bias corrections live in device memory
@@ -516,9 +597,9 @@ class SailEngine:
                 cur["g"] = torch.cuda.CUDAGraph()
                 cur["g"].capture_begin(pool=pool)
 
-            def brk(spans):
+            def brk(actions):
                 cur["g"].capture_end()
-                segs.append((cur["g"], list(spans)))
+                segs.append((cur["g"], list(actions)))
                 begin()
 
             # warm-up outside capture is NOT wanted (it would apply an extra optimiser step): capture directly
@@ -557,10 +638,10 @@ class SailEngine:
             ent["seq"].copy_(seq, non_blocking=True)
             ent["lay"].perm_dev.copy_(lay.perm_dev, non_blocking=True)
         segs = ent["segs"]
-        for g, spans in segs:
+        for g, actions in segs:
             g.replay()
-            if spans:
-                self._bucket_async(spans, ("dyn", None))
+            for a in actions:
+                self._run_action(a, ("dyn", None))
         if self.world > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)     # the next forward needs every updated weight
         self.launches_replayed += ent["n_launch"]

@@ -183,9 +183,10 @@ def tanh_bwd(dh, h, dpre=None, dpre_bf16=None):
                   _ptr(dpre, torch.float32), _ptr(dpre_bf16, torch.bfloat16), _stream())
 
 
-def colsum(X, M, N, out, accumulate=False):
-    _C.lib().call("ark_colsum", _ptr(X), _DT[X.dtype], M, N, X.stride(0), _ptr(out, torch.float32), int(accumulate),
-                  _stream())
+def colsum(X, M, N, out, accumulate=False, deterministic=False):
+    """deterministic: fixed summation order (ranks that redo the same sum must agree bitwise)."""
+    _C.lib().call("ark_colsum", _ptr(X), _DT[X.dtype], M, N, X.stride(0), _ptr(out, torch.float32),
+                  2 if deterministic else int(accumulate), _stream())
 
 
 def add_(a, b, y=None, y_bf16=None):

@@ -287,7 +287,7 @@ def main():
         f_ = fam.setdefault(k, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
         for kk in f_:
             f_[kk] += a[kk]
-    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    top = max(((k, v) for k, v in fam.items() if not k.startswith("nccl_")), key=lambda kv: kv[1]["ms"])   # our kernels only
     name, a = top
     if a["flops"] > 0:
         ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
@@ -298,6 +298,14 @@ def main():
         ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
         roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"]}
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` captures (profiles/), where one exists
+    # for this workload: dram__bytes_read.sum + dram__bytes_write.sum
+    ncu_traffic = {("syn-types", "gru_persist_bwd"): (44.08e6 + 3.47e6, "profiles/r01_ncu_summary.md"),
+                   ("syn-types", "gru_persist_fwd"): (39.37e6 + 2.27e6, "profiles/r01_ncu_summary.md"),
+                   ("wd-articles", "gru_cluster_bwd"): (99.65e6 + 90.60e6, "profiles/r01c_ncu_summary.md"),
+                   ("wd-articles", "gru_cluster_fwd"): (54.30e6 + 225.63e6, "profiles/r01c_ncu_summary.md")}
+    if mt == "SAIL" and not args.dense and args.batch == 0 and (args.workload, name) in ncu_traffic:
+        roof["traffic"], roof["traffic_src"] = ncu_traffic[(args.workload, name)]
     roof["share_of_step"] = a["ms"] / max(tot_ms, 1e-9)
     roof["avg_launch_ms"] = a["ms"] / max(a["calls"], 1)
     breakdown = {t: {"ms_per_step": v["ms"] / n_prof, "calls_per_step": v["calls"] / n_prof,

@@ -291,7 +291,8 @@ int ark_relu_bwd(const float* d, const uint16_t* out, int64_t n, float scale, ui
 int ark_gelu_bwd(const float* dact, const float* pre, int64_t n, float* dpre, uint16_t* dpre_bf16, void* stream);
 /* dpre = dh * (1 - h^2) */
 int ark_tanh_bwd(const float* dh, const float* h, int64_t n, float* dpre, uint16_t* dpre_bf16, void* stream);
-/* out[N] (+)= column sums of X[M, ld] (f32 or bf16) — bias gradients */
+/* out[N] (+)= column sums of X[M, ld] (f32 or bf16) — bias gradients.  accumulate: 0 = overwrite, 1 = add to out,
+ * 2 = overwrite with a fixed summation order (bitwise reproducible: one CTA per column strip, no cross-CTA atomics) */
 int ark_colsum(const void* X, int dtype, int64_t M, int64_t N, int64_t ld, float* out, int accumulate, void* stream);
 /* y = a + b (f32), optional bf16 copy; y may alias a */
 int ark_add_f32(const float* a, const float* b, int64_t n, float* y, uint16_t* y_bf16, void* stream);

@@ -257,6 +257,15 @@ def test_elementwise_helpers():
     Xb = X.to(torch.bfloat16)
     ops.colsum(Xb, 777, 130, cs)
     torch.testing.assert_close(cs, Xb.float().sum(0), rtol=1e-4, atol=1e-4)
+    # ragged N inside a padded row (the [N_tok, ceil(V/8)*8] logits): vector path, NaN padding must not leak
+    Xp = torch.full((1500, 136), float("nan"), device=DEV)
+    Xp[:, :131] = torch.randn(1500, 131, device=DEV)
+    cs = torch.empty(131, device=DEV)
+    ops.colsum(Xp, 1500, 131, cs)
+    torch.testing.assert_close(cs, Xp[:, :131].sum(0), rtol=1e-4, atol=1e-4)
+    Xpb = Xp.to(torch.bfloat16)
+    ops.colsum(Xpb, 1500, 131, cs)
+    torch.testing.assert_close(cs, Xpb[:, :131].float().sum(0), rtol=1e-4, atol=2e-4)
     y = torch.empty(n, device=DEV)
     m = torch.empty(n, device=DEV, dtype=torch.uint8)
     ops.dropout_fwd(a, 0.25, 1234, 0, y, None, m)
