@@ -314,13 +314,23 @@ class SailEngine:
             return out
 
         # ---------------- decoder backward
-        g_wout = f.g("dec.tok_emb.weight") if self.tied else f.g("dec.out.weight")
-        self._gemm(logits, MN, u_b, MN, g_wout, V, d, N, tag="vocab_dW")                      # dW = dLogits^T . Y
-        ops.colsum(logits, N, V, f.g("dec.out.bias"))
+        # Order of the backward pass: the CHAIN first (dY -> GRU backward -> dX -> embedding scatter -> encoder), the
+        # LEAVES (weight-gradient GEMMs nothing in this pass consumes) after it, so that the two large late buckets
+        # (token / entity embedding tables: all-reduce + dense Adam on the side stream) overlap the leaf GEMMs.
+        deferred = []
         dy = new(N, d)
         self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")                         # dY = dLogits . W
+
+        def vocab_weight_grads(logits=logits):
+            g_wout = f.g("dec.tok_emb.weight") if self.tied else f.g("dec.out.weight")
+            # dW = dLogits^T . Y; tied weights: on top of the embedding scatter already in the slot
+            self._gemm(logits, MN, u_b, MN, g_wout, V, d, N, tag="vocab_dW", accumulate=self.tied)
+            ops.colsum(logits, N, V, f.g("dec.out.bias"))
+            self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
+            if self.tied:
+                self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+        deferred.append(vocab_weight_grads)
         del logits
-        self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
         dh0 = new(b0, d)
         if wave:
             w_t = new(2 * nl, d, d3, dtype=bf)
@@ -338,16 +348,19 @@ class SailEngine:
                     ops.gru_cluster_bwd(*bwd_args, cl_ws)
                 else:
                     ops.gru_wave_bwd(*bwd_args)
-            for k in range(nl - 1, -1, -1):
-                u_in = x_b if k == 0 else out_all[k - 1]
-                self._gemm(dgi_all[k], MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
-                self._gemm(dgh_all[k], MN, hp_all[k], MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
-                ops.colsum(dgi_all[k], N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
-                ops.colsum(dgh_all[k], N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
-                if k > 0:
-                    self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+            # the chain first: dX feeds the embedding scatter and the encoder backward, whose (large, late) gradient
+            # buckets then reduce / update on the side stream WHILE the GRU weight-gradient GEMMs below run
             self._gemm(dgi_all[0], K, self._w("dec.gru.weight_ih_l0"), MN, dy, N, d, d3, tag="gru_dX")
-            self._grad_ready("dec.gru.weight_ih_l0", "dec.gru.bias_hh_l0")    # W_ih^0 was still read by the dX GEMM
+
+            def gru_weight_grads():
+                for k in range(nl - 1, -1, -1):
+                    u_in = x_b if k == 0 else out_all[k - 1]
+                    self._gemm(dgi_all[k], MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
+                    self._gemm(dgh_all[k], MN, hp_all[k], MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
+                    ops.colsum(dgi_all[k], N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
+                    ops.colsum(dgh_all[k], N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
+                    self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+            deferred.append(gru_weight_grads)
         else:
             dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
             if persist:
@@ -377,17 +390,19 @@ class SailEngine:
             ops.colsum(dgh, N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
             self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3, tag="gru_dX")   # grad w.r.t. layer input
             self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
-        if not self.tied:
-            f.g("dec.tok_emb.weight").zero_()
+        f.g("dec.tok_emb.weight").zero_()
         with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
             ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
-        self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+        if not self.tied:             # (tied: final once the deferred vocabulary dW has been added)
+            self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
 
         if not self.has_enc:
             g_pos = f.g("dec.pos_emb.weight")
             g_pos.zero_()
             ops.tok_scatter_add(dy, row_t, g_pos)      # d pos_emb[t] = sum of dX over the rows of step t
             self._grad_ready("dec.pos_emb.weight", "dec.pos_emb.weight")
+            for fn in deferred:
+                fn()
             return out
 
         # ---------------- h0 = tanh(W_z z + b_z), reparameterisation, KL
@@ -448,6 +463,8 @@ class SailEngine:
                 self._gemm(dp_all[k], MN, x_all[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, wb, tag="enc_mlp_dW_global")
                 ops.colsum(dp_all[k], wb, d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks must agree bitwise
                 self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias", reduced=True)
+        for fn in deferred:
+            fn()
         return out
 
     # ------------------------------------------------------------------ gradient exchange + bucketed update
@@ -464,7 +481,7 @@ class SailEngine:
             self._flush_bucket()
             self._comm_action(("bucket", [(s, e)], False))
             return
-        if self._pending and self._pending[-1][1] >= s - 64:
+        if self._pending and s - 64 <= self._pending[-1][1] <= s:     # directly behind the previous slots: one slice
             self._pending[-1] = (self._pending[-1][0], e)
         else:
             self._pending.append((s, e))
