@@ -839,6 +839,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
       const int Bt = bt_s[t < 0 ? 0 : t];
       const int B_next = (t + 1 <= L - 1) ? bt_s[t + 1] : 0;
       if (tid == 0) GC_DBG(1, 2, it, 0);
+      const int s = it % GC_GS;
+      const float* dxs = reinterpret_cast<const float*>(dx_sm + s * DXB);   // [NB][32]
+      // (the projection runs ahead: this wait is normally over at once and its latency hides behind the exchange)
+      if (t >= 0 && !top) ptx::mbar_wait(&dx_full[s], (it / GC_GS) & 1);
       if (it > 0) {                                         // partial sums of dgh_{t+1} W_hh from every CTA of the cluster
         const int e = it - 1;
         ptx::mbar_wait_cluster(&rbar[e & 1], (e >> 1) & 1);
@@ -881,10 +885,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
         if (it > 0) v = *reinterpret_cast<const float4*>(recT + (row0 + 16 * i) * RT + quad * 4);
         rec[i][0] = v.x; rec[i][1] = v.y; rec[i][2] = v.z; rec[i][3] = v.w;
       }
-      const int s = it % GC_GS;
-      const float* dxs = reinterpret_cast<const float*>(dx_sm + s * DXB);   // [NB][32]
       if (tid == 0) GC_DBG(1, 2, it, 2);
-      if (t >= 0 && !top) ptx::mbar_wait(&dx_full[s], (it / GC_GS) & 1);
       if (tid == 0) GC_DBG(1, 2, it, 3);
       float dar[NI][4], daz[NI][4], dan[NI][4], danr[NI][4];
 #pragma unroll

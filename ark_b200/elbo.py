@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .flat import FlatParams, ark_param_order, sail_param_order
+from .flat import FlatParams, ark_param_order, merge_span, sail_param_order
 from .layout import PackedLayout, pack_layout
 
 K, MN = ops.MAJOR_K, ops.MAJOR_MN
@@ -481,10 +481,7 @@ class SailEngine:
             self._flush_bucket()
             self._comm_action(("bucket", [(s, e)], False))
             return
-        if self._pending and s - 64 <= self._pending[-1][1] <= s:     # directly behind the previous slots: one slice
-            self._pending[-1] = (self._pending[-1][0], e)
-        else:
-            self._pending.append((s, e))
+        merge_span(self._pending, s, e)
         if sum(b - a for a, b in self._pending) >= self.bucket_elems:
             self._flush_bucket()
 

@@ -63,6 +63,17 @@ def ark_param_order(model):
     return groups
 
 
+def merge_span(pending, s, e, gap=64):
+    """Append the slot range [s, e) of the flat buffer to `pending` (a list of (start, end)); a range that begins
+    directly behind the last one (within the alignment gap) extends it, anything else — including ranges that arrive
+    out of layout order — starts a new entry."""
+    if pending and s - gap <= pending[-1][1] <= s:
+        pending[-1] = (pending[-1][0], e)
+    else:
+        pending.append((s, e))
+    return pending
+
+
 class FlatParams:
     def __init__(self, groups, device):
         self.slots = {}  # name -> (offset, numel, shape)

@@ -167,3 +167,63 @@ def test_two_rank_gloo_gradient_sum_equals_whole_batch(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("OK") == 2
+
+
+def test_merge_span_handles_adjacent_and_out_of_order_slots():
+    """Gradient slots arrive in the order the backward pass finishes them, which is NOT the layout order once the
+    leaf weight-gradient GEMMs are deferred behind the critical chain: only a slot directly behind the previous one
+    may extend it; everything else is its own slice (nothing is dropped, nothing overlaps)."""
+    from ark_b200.flat import merge_span
+    p = []
+    merge_span(p, 0, 100)
+    merge_span(p, 128, 300)          # behind the 64-element alignment gap: same slice
+    assert p == [(0, 300)]
+    merge_span(p, 1000, 1200)        # a hole: new slice
+    merge_span(p, 400, 600)          # out of order (earlier in the layout): new slice, never a negative range
+    merge_span(p, 640, 700)
+    assert p == [(0, 300), (1000, 1200), (400, 700)]
+    assert all(e > s for s, e in p)
+    covered = sorted(p)
+    assert all(covered[i][1] <= covered[i + 1][0] for i in range(len(covered) - 1))
+
+
+_FACTOR_WORKER = r'''
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = torch.Generator().manual_seed(100 + rank)
+B, n = 6, 40                                        # B << n: dW = dY^T X has rank <= world * B
+X = torch.randn(B, n, generator=g, dtype=torch.float64)
+dY = torch.randn(B, n, generator=g, dtype=torch.float64)
+# what the engine used to do: all-reduce the [n, n] weight gradient (and the bias gradient)
+dW = dY.t() @ X
+db = dY.sum(0)
+dist.all_reduce(dW)
+dist.all_reduce(db)
+# what it does now (ark_b200/elbo.py, dp_factor_gather): all-gather the two [B, n] factors, ONE K = world*B product
+X_all, dY_all = torch.empty(world * B, n, dtype=torch.float64), torch.empty(world * B, n, dtype=torch.float64)
+dist.all_gather_into_tensor(X_all, X)
+dist.all_gather_into_tensor(dY_all, dY)
+assert torch.allclose(dY_all.t() @ X_all, dW, rtol=1e-12, atol=1e-12)
+assert torch.allclose(dY_all.sum(0), db, rtol=1e-12, atol=1e-12)
+# every rank computed the SAME bits from the same gathered operands (no drift between replicas)
+ref = (dY_all.t() @ X_all).clone()
+dist.broadcast(ref, 0)
+assert torch.equal(ref, dY_all.t() @ X_all)
+assert 2 * world * B * n < n * n                   # and it moves fewer numbers than the all-reduce
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_two_rank_gloo_factor_gather_equals_weight_gradient_all_reduce(tmp_path):
+    script = tmp_path / "factor_worker.py"
+    script.write_text(_FACTOR_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29633", str(script)],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == 2
