@@ -14,6 +14,8 @@
 #include "ptx.cuh"
 #include "tmap.cuh"
 #include "gemm_tc.cuh"
+#include <string.h>
+#include <stdlib.h>
 
 namespace ark {
 
@@ -52,7 +54,8 @@ __device__ __forceinline__ float apply_act(float v, int epilogue) {
 //                  drain tile i — no per-tile launch / TMEM alloc / barrier init, no idle tensor pipe during stores.
 template <int BN, bool A_MN, bool B_MN, int STAGES, bool PERSIST>
 __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmC, const EpiParams ep,
                                                       const int M, const int N, const int K,
                                                       const int a_row0, const int b_row0) {
   using L = TcSmem<BN, STAGES, PERSIST>;
@@ -191,10 +194,59 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       int m0, n0;
       tile_origin(tile, m0, n0);
       const int acc = PERSIST ? (lt & 1) : 0;
+      const bool full_tile = (m0 + TC_BM <= M) && (n0 + BN <= N);
+      if constexpr (PERSIST && BN == 128) {
+        if (ep.tma_store) {
+          // the staging tile may still be the source of the previous tile's TMA store: its issuers wait, then all meet
+          if (lane == 0 && q == 0) ptx::bulk_wait_group_read0();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
       // bias for the tile's columns: ONE coalesced global load per tile, issued before the MMA wait
       if (tid < BN) bias_s[tid] = (ep.bias && n0 + tid < N && kb0 == 0) ? __ldg(ep.bias + n0 + tid) : 0.f;
       ptx::mbar_wait(&tmem_full_bar[acc], PERSIST ? ((lt >> 1) & 1) : 0);
       ptx::tc_fence_after();
+      if constexpr (PERSIST && BN == 128) {
+        if (ep.tma_store && plain && full_tile && ep.c_bf16) {
+          // ---- full bf16 tile: TMEM -> registers (+ bias) -> bf16 -> 128B-swizzled staging -> ONE TMA store per
+          // 64-column half.  A thread owns one row: its 64 columns are exactly one 128-byte swizzle row.
+          asm volatile("bar.sync 1, 256;" ::: "memory");      // bias_s visible
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N);
+          uint8_t* half_sm = reinterpret_cast<uint8_t*>(stage) + half * (TC_BM * 128);
+          uint8_t* row_sm = half_sm + r_loc * 128;
+          const float* bs = bias_s + half * HALF_N;
+          uint32_t r[HALF_N / 16][16];
+#pragma unroll
+          for (int c = 0; c < HALF_N / 16; ++c) ptx::tmem_ld_32x32b_x16(t_addr + (uint32_t)(c * 16), r[c]);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < HALF_N / 16; ++c) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              uint4 pk;
+              const int b0 = c * 16 + h8 * 8;
+              const float4 ba = *reinterpret_cast<const float4*>(bs + b0), bb = *reinterpret_cast<const float4*>(bs + b0 + 4);
+              pk.x = pack_bf16x2(__uint_as_float(r[c][h8 * 8 + 0]) + ba.x, __uint_as_float(r[c][h8 * 8 + 1]) + ba.y);
+              pk.y = pack_bf16x2(__uint_as_float(r[c][h8 * 8 + 2]) + ba.z, __uint_as_float(r[c][h8 * 8 + 3]) + ba.w);
+              pk.z = pack_bf16x2(__uint_as_float(r[c][h8 * 8 + 4]) + bb.x, __uint_as_float(r[c][h8 * 8 + 5]) + bb.y);
+              pk.w = pack_bf16x2(__uint_as_float(r[c][h8 * 8 + 6]) + bb.z, __uint_as_float(r[c][h8 * 8 + 7]) + bb.w);
+              const int chunk = (c * 2 + h8) ^ (r_loc & 7);           // 128B swizzle: 16-byte chunk index ^ (row % 8)
+              *reinterpret_cast<uint4*>(row_sm + chunk * 16) = pk;
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);   // accumulator back to the MMA warp
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+          else asm volatile("bar.sync 3, 128;" ::: "memory");
+          if (lane == 0 && q == 0) {
+            ptx::tma_store_2d(&tmC, half_sm, n0 + half * HALF_N, m0);
+            ptx::bulk_commit_group();
+          }
+          continue;
+        }
+      }
       // Phase 1: raw accumulators TMEM -> smem; all of this warp's loads are in flight before the single wait
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N);
       float* sp = stage + r_loc * LD + half * HALF_N;
@@ -216,7 +268,6 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // Phase 2: bias (+ activation, aux) + stores, row-contiguous.
-      const bool full_tile = (m0 + TC_BM <= M) && (n0 + BN <= N);
       if (plain && full_tile) {
         // fast path (every large GEMM of the step): 8 columns per thread, no bounds checks, no activation
         if (ep.c_bf16) {
@@ -321,6 +372,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       }
       if (PERSIST) asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile free for the next drain
     }
+    if constexpr (PERSIST && BN == 128) {
+      if (ep.tma_store && lane == 0 && q == 0) ptx::bulk_wait_group0();   // the last tiles' TMA stores are complete
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -358,8 +412,18 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiPa
     cudaError_t e = cudaMemset2DAsync(ep.C, (size_t)ep.ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, s);
     if (e != cudaSuccess) return fail((int)e, "gemm_bf16_tc: split-K memset: %s", cudaGetErrorString(e));
   }
+  // persistent kernel, plain bf16 output: full tiles leave through TMA stores (the thread-written epilogue took
+  // ~2.6 us per 128x128 tile, longer than the main loop of a K = 512 product)
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  ep2.tma_store = 0;
+  if (PERSIST && BN == 128 && ep.c_bf16 && ep.epilogue == ARK_EPI_NONE && !ep.aux && ep.ldc % 8 == 0 && aligned16(ep.C)) {
+    static int want = -1;
+    if (want < 0) { const char* ev = getenv("ARK_GEMM_TMA_STORE"); want = ev ? atoi(ev) : 1; }
+    if (want && make_tmap_2d_bf16(&tmC, ep.C, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldc, 64, TC_BM) == 0) ep2.tma_store = 1;
+  }
   dim3 grid((unsigned)(PERSIST ? (tiles < kNumSMs ? tiles : kNumSMs) : tiles), (unsigned)splits);
-  kern<<<grid, TC_THREADS, L::TOTAL, s>>>(tmA, tmB, ep2, M, N, K, a_row0, b_row0);
+  kern<<<grid, TC_THREADS, L::TOTAL, s>>>(tmA, tmB, tmC, ep2, M, N, K, a_row0, b_row0);
   return launched("gemm_bf16_tc");
 }
 

@@ -16,6 +16,7 @@ struct EpiParams {
   int swap_raster;   // set by the launcher
   int kb_per_split;  // set by the launcher: k-blocks per blockIdx.y slice (split-K: partial sums meet through f32 atomics)
   int atomic;        // set by the launcher: C += via red.global.add (split-K)
+  int tma_store;     // set by the launcher: full bf16 tiles leave through a TMA store (persistent kernel)
 };
 
 int tc_pick_bn(int64_t M, int64_t N);

@@ -73,6 +73,27 @@ def test_gemm_tc_epilogues(epi, c_dtype):
         assert _rel(aux, pre) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,with_bias", [(2048, 4736, True), (1100, 9000, False)])
+def test_gemm_tc_persistent_bf16_tma_store_epilogue(M, N, with_bias):
+    """>= 2 waves of 128x128 tiles with a plain bf16 output (the vocabulary projection): the persistent kernel whose
+    full tiles leave through 128B-swizzled staging + TMA stores; ragged edges (M, N not multiples of 128) take the
+    thread-written path inside the same launch."""
+    K = 192
+    g = torch.Generator(device=DEV).manual_seed(5)
+    A = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=DEV, generator=g) * 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV, generator=g) if with_bias else None
+    ldc = (N + 7) // 8 * 8
+    C = torch.full((M, ldc), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, ops.MAJOR_K, B, ops.MAJOR_K, C, M, N, K, bias=bias, backend="tc")
+    ref = A.float() @ B.float().t()
+    if with_bias:
+        ref = ref + bias
+    torch.testing.assert_close(C[:, :N].float(), ref.to(torch.bfloat16).float(), rtol=2e-2, atol=2e-2)
+    if ldc > N:
+        assert (C[:, N:] == 7.0).all()          # the row padding is never written
+
+
 def test_gemm_tc_accumulate_and_simt_agree():
     M, N, K = 130, 70, 1000
     torch.manual_seed(5)
