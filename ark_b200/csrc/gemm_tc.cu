@@ -400,8 +400,11 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiPa
   int splits = 1;
   // split-K: few output tiles, long K (dW = dY^T X of the recurrent / attention weights: M,N = O(d), K = N_tok).
   // Only for a plain f32 output; C is zeroed (unless accumulating) and the partial sums meet through red.add.
-  if (!PERSIST && !ep.c_bf16 && ep.epilogue == ARK_EPI_NONE && !ep.aux && tiles * 2 <= kNumSMs && num_kb >= 8) {
-    splits = (int)(kNumSMs / tiles);
+  if (!PERSIST && !ep.c_bf16 && ep.epilogue == ARK_EPI_NONE && !ep.aux && num_kb >= 8 &&
+      (tiles * 2 <= kNumSMs || (tiles <= kNumSMs && num_kb >= 24))) {
+    // up to one CTA per SM; a long K with 75..148 tiles (dX of the encoder MLP: M = batch, K = 3d) goes to two
+    // co-resident CTAs per SM so that the weight panel streams from all SMs at once
+    splits = (int)((tiles * 2 <= kNumSMs ? kNumSMs : 2 * kNumSMs) / tiles);
     if (splits > num_kb / 4) splits = num_kb / 4;
     if (splits < 1) splits = 1;
   }
