@@ -67,9 +67,13 @@ class SailEngine:
         self.group = dist_group
         self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self.comm_stream = torch.cuda.Stream(device=dev)   # gradient all-reduce + per-bucket Adam, overlapping backward
+        # gradient all-reduce + per-bucket Adam, overlapping backward.  High priority: its (few) NCCL CTAs must not queue
+        # behind the full grids of the main stream's GEMMs
+        import os as _os
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1 if _os.environ.get("ARK_COMM_PRIORITY", "1") != "0" else 0)
         self._upd = None                 # (mode, lr) while a train step is in flight: buckets are updated as they finish
         self._pending = []
+        self._hold_comm, self._held = False, []   # see _comm_action: no NCCL next to the 128-CTA cooperative GRU kernels
         self.prof = None
         self._capturing = False
         self._segment_break = None
@@ -84,6 +88,7 @@ class SailEngine:
         self._gru_cluster_ws = None      # scratch of the cluster GRU kernels (gi^T / dx^T slices), grown on demand
         self.dp_factor_gather = True     # data parallel: all-gather the [B, 3d] FACTORS of the encoder-MLP weight
                                          # gradients (dW = dY^T X, rank <= global batch) instead of all-reducing dW
+        self.dp_hold_comm = _os.environ.get("ARK_DP_HOLD_COMM", "0") != "0"   # opt-in: see _release_comm
         self.dp_emb_min_bytes = None     # ... and (opt-in: a byte threshold) of the entity-embedding gradient of a large
                                          # table.  Off by default: the scatter's atomics make the ranks' results differ
                                          # in the last bits, so replicas would drift apart without a periodic re-sync
@@ -169,6 +174,12 @@ class SailEngine:
         out = torch.zeros(2, device=dev) if stats_out is None else stats_out
         self._drop_calls = 0
         use_tc = 1 if self.backend == "tc" else 0
+        self._hold_comm, self._held = False, []
+        if train and self.world > 1 and use_tc and not self.force_unfused_gru and self.dp_hold_comm:
+            b0_ = int(lay.bt[0])
+            stack = ((self.gru_mode in ("auto", "cluster") and self._use_gru_cluster(d, b0_, nl, L) > 0)
+                     or (self.gru_mode in ("auto", "wave") and ops.gru_wave_supported(d, b0_, nl) > 0))
+            self._hold_comm = (not stack) and ops.gru_persist_supported(d, b0_) > 0
         new = lambda *s, dtype=f32: torch.empty(*s, device=dev, dtype=dtype)  # noqa: E731
 
         # ---------------- encoder forward (models.py:46-64)
@@ -390,6 +401,7 @@ class SailEngine:
             ops.colsum(dgh, N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
             self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3, tag="gru_dX")   # grad w.r.t. layer input
             self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+        self._release_comm()          # (no-op unless collectives were held back for the persistent GRU kernels)
         f.g("dec.tok_emb.weight").zero_()
         with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
             ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
@@ -496,17 +508,35 @@ class SailEngine:
         ("join",).  Graph mode under data parallelism ends the graph segment here; the replay loop runs the action
         eagerly while the NEXT segment runs (NCCL kernels are never captured: capturing them next to the cooperative
         GRU kernels hung at 2 ranks)."""
+        if self._hold_comm:
+            self._held.append(action)
+            return
         if self._capturing and self.world > 1:
             self._segment_break([action])
             return
         self._run_action(action, self._upd)
 
     def _comm_actions(self, actions):
+        if self._hold_comm:
+            self._held.extend(actions)
+            return
         if self._capturing and self.world > 1:
             self._segment_break(list(actions))      # one segment break for all of them
             return
         for a in actions:
             self._run_action(a, self._upd)
+
+    def _release_comm(self):
+        """End of the stretch of per-layer persistent GRU kernels: everything that was held back goes out at once.
+        Those kernels are cooperative launches of 128 CTAs; an NCCL kernel that holds a few SMs keeps them from
+        starting, so a collective issued between two of them is serialised with the recurrence (and with the
+        slowest rank) instead of overlapping it — measured at 8 GPUs on syn-types: 7 bucket all-reduces took
+        1.5 ms and stretched gru_persist_bwd 0.41 -> 1.08 ms.  Held back, the same gradients leave in one or two
+        large all-reduces that overlap the (non-cooperative) encoder backward."""
+        self._hold_comm = False
+        held, self._held = self._held, []
+        if held:
+            self._comm_actions(held)
 
     def _run_action(self, action, upd):
         kind = action[0]

@@ -1,11 +1,17 @@
-TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-n=8
-for ctas in 16 8; do
-for w in syn-types wd-articles; do
-  NCCL_MAX_CTAS=$ctas timeout 240 $TR --nproc-per-node $n --master-port 2952$ctas bench.py --gpus $n --workload $w --steps 20 --warmup 5 > gpurun_out/n${n}k${ctas}_$w.log 2> gpurun_out/n${n}k${ctas}_$w.err; echo "N=$n ctas=$ctas $w rc=$?"
-  tail -1 gpurun_out/n${n}k${ctas}_$w.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N=$n ctas=$ctas', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), 'e2e', round(d['e2e']['value']))"
-  cp gpurun_out/bench_breakdown_${w}_n${n}.json gpurun_out/bench_breakdown_${w}_n${n}_k${ctas}.json 2>/dev/null
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+i=0
+for hold in 0 1; do
+  i=$((i+1))
+  ARK_DP_HOLD_COMM=$hold timeout 200 $TR --master-port 2953$i bench.py --gpus 8 --workload syn-types --steps 20 --warmup 5 --no-e2e > gpurun_out/n8p_$hold.log 2> gpurun_out/n8p_$hold.err; echo "hold=$hold rc=$?"
+  tail -1 gpurun_out/n8p_$hold.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N=8 hold=$hold', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']))"
+  python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_breakdown_syn-types_n8.json'))
+for k,v in d.items():
+    if isinstance(v,dict):
+        print("   ", {kk: round(vv['ms_per_step'],3) for kk,vv in v.items() if 'nccl' in kk or 'gru_persist' in kk or 'adam' in kk})
+        break
+PY
 done
-done
-NCCL_MAX_CTAS=16 timeout 240 $TR --nproc-per-node 8 --master-port 29533 bench.py --gpus 8 --workload wd-articles --batch 256 --steps 10 --warmup 3 > gpurun_out/n8_wda256.log 2> gpurun_out/n8_wda256.err; echo "N=8 b256 rc=$?"
-tail -1 gpurun_out/n8_wda256.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N=8 b256', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), 'e2e', round(d['e2e']['value']))"
+timeout 200 $TR --master-port 29539 bench.py --gpus 8 --workload wd-articles --steps 20 --warmup 5 > gpurun_out/n8p_wda.log 2> gpurun_out/n8p_wda.err; echo "wda rc=$?"
+tail -1 gpurun_out/n8p_wda.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N=8', d['config']['workload'], round(d['ms_per_step'],4), round(d['value']), 'e2e', round(d['e2e']['value']))"
