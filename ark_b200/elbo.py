@@ -17,6 +17,7 @@ producing kernel), fp32 accumulation, fp32 master weights / recurrent state / ga
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -69,8 +70,7 @@ class SailEngine:
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         # gradient all-reduce + per-bucket Adam, overlapping backward.  High priority: its (few) NCCL CTAs must not queue
         # behind the full grids of the main stream's GEMMs
-        import os as _os
-        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1 if _os.environ.get("ARK_COMM_PRIORITY", "1") != "0" else 0)
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get("ARK_COMM_PRIORITY", "1") != "0" else 0)
         self._upd = None                 # (mode, lr) while a train step is in flight: buckets are updated as they finish
         self._pending = []
         self._hold_comm, self._held = False, []   # see _comm_action: no NCCL next to the 128-CTA cooperative GRU kernels
@@ -88,7 +88,7 @@ class SailEngine:
         self._gru_cluster_ws = None      # scratch of the cluster GRU kernels (gi^T / dx^T slices), grown on demand
         self.dp_factor_gather = True     # data parallel: all-gather the [B, 3d] FACTORS of the encoder-MLP weight
                                          # gradients (dW = dY^T X, rank <= global batch) instead of all-reducing dW
-        self.dp_hold_comm = _os.environ.get("ARK_DP_HOLD_COMM", "0") != "0"   # opt-in: see _release_comm
+        self.dp_hold_comm = os.environ.get("ARK_DP_HOLD_COMM", "0") != "0"   # opt-in: see _release_comm
         self.dp_emb_min_bytes = None     # ... and (opt-in: a byte threshold) of the entity-embedding gradient of a large
                                          # table.  Off by default: the scatter's atomics make the ranks' results differ
                                          # in the last bits, so replicas would drift apart without a periodic re-sync
