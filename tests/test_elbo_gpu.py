@@ -307,6 +307,52 @@ def test_gru_cluster_kernel_agrees_with_wavefront_and_per_layer(spec, p_drop):
         assert rel < 2e-2, (other, rel)
 
 
+def test_gru_cluster_kernel_decoder_only_eval_and_graph_replay():
+    """Paths of the cluster GRU kernel the SAIL training test does not reach: decoder-only ARK (no initial state: h0 =
+    NULL, position embeddings) against the numpy oracle; forward-only evaluation (no saved gates: r/z/n/ghn = NULL);
+    and the captured + replayed step (scratch allocated before capture) against the eager one."""
+    from ark_b200 import ops
+    cfg, tri, seq, rng = _random_case(29, nE=300, nR=6, lo=2, hi=14, pad=True, d=128, dz=16, nl=3, B=20)
+    L = seq.shape[1] - 1
+    assert ops.gru_cluster_supported(128, 20, 3, L) > 0
+    # --- decoder-only model, cluster kernel forced, vs the oracle
+    acfg = dict(cfg, model_type="ARK")
+    torch.manual_seed(1)
+    ark = ARK(dict(acfg)).to(DEV)
+    params = {k: v.detach().double().cpu().numpy() for k, v in ark.state_dict().items()}
+    losses, g_ref, _ = O.ark_step(params, acfg, seq)
+    ark.engine().gru_mode = "cluster"
+    ce = ark.ce_backward(torch.from_numpy(seq))[0].item()
+    assert abs(ce - losses["ce"]) <= LOSS_RTOL * abs(losses["ce"])
+    _check_grads(ark.engine(), g_ref)
+    # --- SAIL: evaluation pass (forward only) agrees between the cluster and the per-layer kernels
+    eps = torch.from_numpy(rng.standard_normal((20, 16)).astype(np.float32)).to(DEV)
+    seq_t = torch.from_numpy(seq)
+    lay = pack_layout(seq_t).to(DEV)
+    tri_d, seq_d = torch.from_numpy(tri).to(DEV), seq_t.to(DEV)
+    ev = {}
+    for mode in ("cluster", "layer"):
+        torch.manual_seed(4)
+        eng = SAIL(dict(cfg)).to(DEV).engine(seed=3)
+        eng.gru_mode = mode
+        ev[mode] = eng.eval_step(tri_d, seq_d, lay, eps, 0.5).clone()
+    torch.testing.assert_close(ev["cluster"], ev["layer"], rtol=5e-3, atol=1e-5)
+    # --- graph replay of the training step with the cluster kernels == eager
+    res = []
+    for graphed in (False, True):
+        torch.manual_seed(6)
+        eng = SAIL(dict(cfg)).to(DEV).engine(lr=3e-3)
+        eng.gru_mode = "cluster"
+        outs = []
+        for s_ in range(3):
+            fn = eng.train_step_graphed if graphed else eng.train_step
+            outs.append(fn(tri_d, seq_d, lay, eps, 0.5).clone())
+        res.append((torch.stack(outs), eng.flat.param.clone()))
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=5e-3, atol=1e-5)
+    bad = (res[0][1] - res[1][1]).abs() > 0.25 * 3e-3
+    assert bad.float().mean().item() < 0.02
+
+
 def test_cuda_graph_step_matches_eager_step():
     """Replaying the captured step (device-resident Adam scalars / Philox offset) == launching it eagerly."""
     cfg, tri, seq, rng = _random_case(21, nE=60, nR=4, lo=4, hi=4, pad=False, d=64, dz=8, nl=2, B=40)
