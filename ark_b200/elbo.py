@@ -39,6 +39,11 @@ class SailEngine:
     ``gemm_backend``: "tc" (tcgen05/TMA, default, the product path) or "simt" (fp32-FMA kernel with the same
     bf16 operands — a debugging cross-check, never chosen automatically for TMA-eligible shapes).
     """
+    # defaults of the data-parallel / GRU-driver switches, also for subclasses with their own __init__
+    # (ark_b200.tsail: the Transformer engines reuse the bucket machinery below)
+    _hold_comm, _held = False, ()
+    dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
+    _gru_cluster_ws = None
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gemm_backend="tc", dist_group=None,
                  bucket_mb=16.0, seed=0):
@@ -78,8 +83,10 @@ class SailEngine:
         self._capturing = False
         self._segment_break = None
         self._graphs = {}
-        self.dyn_f = torch.zeros(2, device=dev)                      # [lr/(1-b1^t), 1/sqrt(1-b2^t)] for graph replay
-        self.dyn_i = torch.zeros(1, device=dev, dtype=torch.int64)   # running Philox offset for graph replay
+        # per-step scalars of a replayed graph, ONE 16-byte device buffer (one H2D copy per step):
+        self._dyn_raw = torch.zeros(16, device=dev, dtype=torch.uint8)
+        self.dyn_f = self._dyn_raw[:8].view(torch.float32)           # [lr/(1-b1^t), 1/sqrt(1-b2^t)]
+        self.dyn_i = self._dyn_raw[8:].view(torch.int64)             # running Philox offset
         self.launches_replayed = 0       # kernels of libarkb200 executed through graph replays
         self.force_unfused_gru = False   # tests: compare the persistent GRU kernel with the per-step path
         self.gru_mode = "auto"           # "auto": cluster stack kernel (long chains of short batch tiles), else the
@@ -622,9 +629,10 @@ class SailEngine:
         lr = self.lr if lr is None else float(lr)
         b1, b2 = self.betas
         # pageable sources: the driver stages them at call time, so the next step may overwrite nothing in flight
-        self.dyn_f.copy_(torch.tensor([lr / (1.0 - b1 ** self.step_count), 1.0 / math.sqrt(1.0 - b2 ** self.step_count)],
-                                      dtype=torch.float32))
-        self.dyn_i.copy_(torch.tensor([self.philox_offset], dtype=torch.int64))
+        host = np.empty(16, dtype=np.uint8)
+        host[:8].view(np.float32)[:] = (lr / (1.0 - b1 ** self.step_count), 1.0 / math.sqrt(1.0 - b2 ** self.step_count))
+        host[8:].view(np.int64)[0] = self.philox_offset
+        self._dyn_raw.copy_(torch.from_numpy(host))
         if ent is None:
             dev = self.device
             st = {"triples": None if triples is None else triples.to(dev, copy=True), "seq": seq.to(dev, copy=True),

@@ -33,10 +33,32 @@ class PackedLayout:
     off_dev: torch.Tensor = None
 
     def to(self, device):
+        device = torch.device(device)
+        if self.perm_dev is not None and self.perm_dev.device == device:
+            return self                 # (the cached uniform layouts of fixed-length datasets: nothing to copy again)
         self.perm_dev = torch.from_numpy(self.perm).to(device, non_blocking=True)
         self.bt_dev = torch.from_numpy(self.bt).to(device, non_blocking=True)
         self.off_dev = torch.from_numpy(self.off[:-1].copy()).to(device, non_blocking=True)
         return self
+
+
+# Fixed-length datasets (syn-*: every graph has the same number of triples): the layout depends on (B, len) only —
+# identity permutation, B active graphs at every step.  Deriving it again for every batch (argsort, per-step counts,
+# three small H2D copies) is ~70 us of exposed host time in front of a ~1.5 ms step, so it is built once.  The device
+# tensors of a cached layout are read-only for every consumer (the graph replay copies perm_dev OUT of it).
+_UNIFORM = {}
+
+
+def _uniform_layout(B: int, n: int) -> PackedLayout:
+    lay = _UNIFORM.get((B, n))
+    if lay is None:
+        if len(_UNIFORM) > 64:
+            _UNIFORM.clear()
+        lay = PackedLayout(perm=np.arange(B, dtype=np.int32), lens=np.full(B, n, dtype=np.int32),
+                           bt=np.full(n, B, dtype=np.int32), off=(np.arange(n + 1, dtype=np.int64) * B).astype(np.int32),
+                           n_tok=B * n, n_triples=B * ((n - 1) // 3), L=n)
+        _UNIFORM[(B, n)] = lay
+    return lay
 
 
 def pack_layout(seq_cpu: torch.Tensor) -> PackedLayout:
@@ -46,6 +68,8 @@ def pack_layout(seq_cpu: torch.Tensor) -> PackedLayout:
     s = seq_cpu.numpy()
     B, seq_len = s.shape
     lens = (s[:, 1:] != PAD).sum(1).astype(np.int32)          # targets that are not PAD
+    if B and lens[0] > 0 and (lens == lens[0]).all():
+        return _uniform_layout(B, int(lens[0]))
     perm = np.argsort(-lens, kind="stable").astype(np.int32)
     L = int(lens.max()) if B else 0
     steps = np.arange(L, dtype=np.int32)

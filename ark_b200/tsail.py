@@ -113,9 +113,10 @@ class TSailEngine(SailEngine):
         self.group = dist_group
         self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
         self._upd = None
         self._pending = []
+        self._hold_comm, self._held = False, []
         self.prof = None
         self._capturing = False
         self._segment_break = None
