@@ -278,6 +278,7 @@ def test_gru_kernels_agree_wavefront_vs_per_layer_vs_per_step(spec, p_drop):
     dict(nE=300, nR=6, lo=2, hi=40, pad=True, d=256, dz=16, nl=2, B=12),     # 8-CTA clusters, one 16-row tile, long chain
     dict(nE=300, nR=6, lo=2, hi=30, pad=True, d=512, dz=16, nl=3, B=16),     # wd-articles shape: 16-CTA clusters
     dict(nE=50, nR=4, lo=6, hi=6, pad=False, d=256, dz=8, nl=4, B=16),       # four layers, fixed length
+    dict(nE=300, nR=6, lo=1, hi=12, pad=True, d=128, dz=16, nl=3, B=100),    # 32-row batch tiles (4 ragged tiles)
 ])
 @pytest.mark.parametrize("p_drop", [0.0, 0.1])
 def test_gru_cluster_kernel_agrees_with_wavefront_and_per_layer(spec, p_drop):
@@ -288,7 +289,8 @@ def test_gru_cluster_kernel_agrees_with_wavefront_and_per_layer(spec, p_drop):
     cfg, tri, seq, rng = _random_case(13, **spec)
     cfg["dec_dropout"] = p_drop
     B, d, nl = spec["B"], spec["d"], spec["nl"]
-    assert ops.gru_cluster_supported(d, B, nl, seq.shape[1] - 1) > 0
+    nb = ops.gru_cluster_supported(d, B, nl, seq.shape[1] - 1)
+    assert nb > 0 and (B != 100 or nb == 32)
     eps = torch.from_numpy(rng.standard_normal((B, spec["dz"])).astype(np.float32)).to(DEV)
     seq_t = torch.from_numpy(seq)
     lay = pack_layout(seq_t).to(DEV)
