@@ -180,6 +180,27 @@ __global__ void __launch_bounds__(256) dropout_bf16_kernel(const uint16_t* __res
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
   const float scale = 1.f / (1.f - p);
+  if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 7) == 0 &&
+      (!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0)) {
+    // vector path: one 8-byte load / store of the four bf16 values and one 4-byte store of their keep flags
+    const uint2 xv = *reinterpret_cast<const uint2*>(x + i);
+    const float2 a = unpack_bf16x2(xv.x), b = unpack_bf16x2(xv.y);
+    const float xs[4] = {a.x, a.y, b.x, b.y};
+    uint16_t o[4];
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool keep = (float)(rr[k] >> 8) * (1.f / 16777216.f) >= p;
+      m |= (keep ? 1u : 0u) << (8 * k);
+      o[k] = keep ? f32_to_bf16_bits(xs[k] * scale) : (uint16_t)0;
+    }
+    if (mask) *reinterpret_cast<uint32_t*>(mask + i) = m;
+    uint2 yv;
+    yv.x = (uint32_t)o[0] | ((uint32_t)o[1] << 16);
+    yv.y = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
+    *reinterpret_cast<uint2*>(y + i) = yv;
+    return;
+  }
   for (int k = 0; k < 4 && i + k < n; ++k) {
     const float u = (float)(rr[k] >> 8) * (1.f / 16777216.f);
     const bool keep = u >= p;
@@ -193,6 +214,20 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restric
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   dx[i] = mask[i] ? dy[i] * scale : 0.f;
+}
+// four elements per thread: 16-byte gradient accesses, one 4-byte load of the keep flags (n % 4 == 0, aligned bases)
+__global__ void __launch_bounds__(256) dropout_bwd4_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                                           int64_t n4, float scale, float* __restrict__ dx) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n4) return;
+  const float4 g = *reinterpret_cast<const float4*>(dy + 4 * q);
+  const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + 4 * q);
+  float4 o;
+  o.x = (m & 0xffu) ? g.x * scale : 0.f;
+  o.y = (m & 0xff00u) ? g.y * scale : 0.f;
+  o.z = (m & 0xff0000u) ? g.z * scale : 0.f;
+  o.w = (m & 0xff000000u) ? g.w * scale : 0.f;
+  *reinterpret_cast<float4*>(dx + 4 * q) = o;
 }
 
 // Adam: 16 B p + 16 B g + 16 B m + 16 B v read, 16+16+16 written (+8 B bf16 shadow) per 4 parameters.
@@ -358,7 +393,10 @@ extern "C" int ark_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, 
   ARK_REQUIRE(dy && mask && dx, ARK_E_BADARG, "dropout_bwd: null pointer");
   ARK_REQUIRE(p >= 0.f && p < 1.f, ARK_E_BADARG, "dropout_bwd: p must be in [0,1)");
   if (n <= 0) return 0;
-  dropout_bwd_kernel<<<blocks_for(n, 256, 0), 256, 0, (cudaStream_t)stream>>>(dy, mask, n, 1.f / (1.f - p), dx);
+  if (n % 4 == 0 && aligned16(dy) && aligned16(dx) && (reinterpret_cast<uintptr_t>(mask) & 3) == 0)
+    dropout_bwd4_kernel<<<blocks_for(n / 4, 256, 0), 256, 0, (cudaStream_t)stream>>>(dy, mask, n / 4, 1.f / (1.f - p), dx);
+  else
+    dropout_bwd_kernel<<<blocks_for(n, 256, 0), 256, 0, (cudaStream_t)stream>>>(dy, mask, n, 1.f / (1.f - p), dx);
   return launched("dropout_bwd");
 }
 

@@ -297,6 +297,11 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tmem_empty[par]);     // all 128 epilogue threads arrive
+        // The signaller counts arrivals in aggregate (128 per step).  Without this barrier the four warps could drift a
+        // step apart (the accumulator is double buffered), three fast warps' arrivals for step t+1 would complete the
+        // count of step t and the stage counter would announce a gi slice whose last 32 rows are not stored yet.  With
+        // it, an arrival for step t+1 implies that every thread's rows of step t are stored.
+        epi_bar_sync();
         sig_arrive(sig_ctr);
         if (tid == 0) GC_DBG(0, 2, t, 2);
       }

@@ -296,6 +296,24 @@ def test_elementwise_helpers():
     dx = torch.empty(n, device=DEV)
     ops.dropout_bwd(b, m, 0.25, dx)
     torch.testing.assert_close(dx, torch.where(keep, b / 0.75, torch.zeros_like(b)))
+    # vector paths (n % 4 == 0, aligned): the bf16 dropout draws the SAME mask as the f32 kernel (shared Philox
+    # stream: the fused GRU epilogues rely on it) and the 4-wide backward agrees with the scalar one
+    n4 = 4096
+    a4, b4 = torch.randn(n4, device=DEV), torch.randn(n4, device=DEV)
+    m32 = torch.empty(n4, device=DEV, dtype=torch.uint8)
+    ops.dropout_fwd(a4, 0.25, 99, 7, torch.empty(n4, device=DEV), None, m32)
+    xb = a4.to(torch.bfloat16)
+    yb = torch.empty_like(xb)
+    mb = torch.empty(n4, device=DEV, dtype=torch.uint8)
+    ops.dropout_bf16(xb, 0.25, 99, 7, yb, mb)
+    assert torch.equal(mb, m32)
+    ref = torch.where(mb.bool(), (xb.float() / 0.75).to(torch.bfloat16), torch.zeros_like(xb))
+    torch.testing.assert_close(yb.float(), ref.float(), rtol=1e-2, atol=1e-3)
+    ops.dropout_bf16(xb[:1001], 0.25, 99, 7, yb[:1001], mb[:1001])          # ragged tail: scalar path, same draw
+    assert torch.equal(mb[:1001], m32[:1001])
+    dx4 = torch.empty(n4, device=DEV)
+    ops.dropout_bwd(b4, mb, 0.25, dx4)
+    torch.testing.assert_close(dx4, torch.where(mb.bool(), b4 / 0.75, torch.zeros_like(b4)))
 
 
 def test_adam_flat_matches_torch():
