@@ -47,7 +47,7 @@ struct GruClFwdParams {
   const float* b_hh[GC_MAXL];
   const int32_t* bt;
   const int32_t* off;
-  int32_t* sync;               // [2][nl][nbt]: iterations finished by the recurrence / projection stage; zeroed
+  int32_t* sync;               // [2][nl][nbt][16]: iterations finished by every recurrence / projection CTA; zeroed
   const float* h0;             // [bt0, d] fp32 or null
   float* git;                  // scratch [nl][L][nbt][CS][96][NB] fp32: gi^T slices (b_ih + b_hh(r,z) included)
   uint16_t* hp_b;              // [nl, N, d] bf16 h_prev rows (block 0 pre-filled with bf16(h0) by the caller)
@@ -70,7 +70,7 @@ struct GruClBwdParams {
   CUtensorMap tmWihT[GC_MAXL];    // W_ih^k^T [d,3d] bf16, box {64, 32}                   (read by projection k-1)
   const int32_t* bt;
   const int32_t* off;
-  int32_t* sync;                  // [2][nl][nbt]
+  int32_t* sync;                  // [2][nl][nbt][16]
   const float* dy_top;            // [N, d] fp32
   const uint16_t *r, *z, *n, *ghn, *hp_b;   // [nl, N, d]
   const uint8_t* mask;            // [nl-1, N, d] or null
@@ -153,6 +153,30 @@ __device__ __forceinline__ void signaller_loop(uint32_t* ctr, uint32_t per_iter,
     }
   }
 }
+// Stage counters are PER CTA (one int32 per slice of a (stage, batch tile): [.][GC_MAXCS]).  A consumer needs all CS
+// slices of an iteration; one summed counter would let a CTA that runs an iteration ahead (the DSMEM exchange does not
+// wait for the peers' global stores) complete the count of a slower peer's iteration.
+constexpr int GC_MAXCS = 16;
+__device__ __forceinline__ void wait_all_counters(const int32_t* p, int n, int target) {
+  for (uint32_t spin = 0;; ++spin) {
+    int v[GC_MAXCS];
+#pragma unroll
+    for (int c = 0; c < GC_MAXCS; ++c) {      // all loads in flight together (one 64-byte line)
+      v[c] = target;
+      if (c < n) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v[c]) : "l"(p + c) : "memory");
+    }
+    int m = v[0];
+#pragma unroll
+    for (int c = 1; c < GC_MAXCS; ++c) m = min(m, v[c]);
+    if (m >= target) break;
+    if (spin > (1u << 22)) {
+      printf("arkb200: gru_cluster stage counters timed out (block %d,%d,%d want %d have %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, target, m);
+      __trap();
+    }
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Copy rows {g*d + j0 + lane} (g = TMEM lane quadrant q < 3) of a [3d, d] bf16 weight matrix into TMEM columns
@@ -199,8 +223,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
   const bool is_proj = (int)blockIdx.z >= nl;
   const int k = is_proj ? (int)blockIdx.z - nl : (int)blockIdx.z;
   const int j0 = c * GC_DJ, m0 = bi * NB;
-  int32_t* rec_done = p.sync + k * nbt + bi;
-  int32_t* proj_done = p.sync + (nl + k) * nbt + bi;
+  int32_t* rec_done = p.sync + (k * nbt + bi) * GC_MAXCS;            // [CS] iterations finished by each recurrence CTA
+  int32_t* proj_done = p.sync + ((nl + k) * nbt + bi) * GC_MAXCS;    // ... by each projection CTA
   const uint16_t* W = is_proj ? p.wih[k] : p.whh[k];
   const uint32_t A_COLS = (uint32_t)d / 2;    // TMEM columns of the resident weight slice [128 lanes x d bf16]
   const int q = warp & 3;                     // TMEM lane quadrant of an epilogue warp
@@ -238,10 +262,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
     ptx::cluster_sync_all();
     if (warp == 0) {
       if (ptx::elect_one()) {
-        const int32_t* below = p.sync + (k - 1) * nbt + bi;
+        const int32_t* below = p.sync + ((k - 1) * nbt + bi) * GC_MAXCS;
         for (int t = 0; t < n_steps; ++t) {
           GC_DBG(0, 0, t, 0);
-          if (k > 0) { wait_counter(below, (t + 1) * CS); fence_proxy_async_all(); }
+          if (k > 0) { wait_all_counters(below, CS, t + 1); fence_proxy_async_all(); }
           GC_DBG(0, 0, t, 1);
           const int s = t % S;
           ptx::mbar_wait(&empty_bar[s], ((t / S) & 1) ^ 1);
@@ -306,7 +330,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
         if (tid == 0) GC_DBG(0, 2, t, 2);
       }
     } else if (warp == 6) {
-      if (ptx::elect_one()) signaller_loop(sig_ctr, 128, (uint32_t)n_steps, proj_done);
+      if (ptx::elect_one()) signaller_loop(sig_ctr, 128, (uint32_t)n_steps, proj_done + c);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -355,7 +379,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
         GC_DBG(0, 0, t, 0);
         ptx::mbar_wait(&gi_empty[s], ((t / GC_GS) & 1) ^ 1);
         GC_DBG(0, 0, t, 1);
-        wait_counter(proj_done, (t + 1) * CS);
+        wait_all_counters(proj_done, CS, t + 1);
         fence_proxy_async_all();
         GC_DBG(0, 0, t, 2);
         ptx::mbar_arrive_expect_tx(&gi_full[s], GB);
@@ -387,7 +411,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const __
       }
     }
   } else if (warp == 6) {
-    if (ptx::elect_one()) signaller_loop(sig_ctr, 128, (uint32_t)n_steps, rec_done);
+    if (ptx::elect_one()) signaller_loop(sig_ctr, 128, (uint32_t)n_steps, rec_done + c);
   } else {
     const uint32_t me = (uint32_t)c;
     const int64_t LS = p.layer_stride;
@@ -562,8 +586,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
   const bool is_proj = (int)blockIdx.z >= nl;
   const int k = is_proj ? (int)blockIdx.z - nl : (int)blockIdx.z;    // projection k feeds layer k from layer k+1
   const int j0 = c * GC_DJ, m0 = bi * NB;
-  int32_t* rec_done = p.sync + k * nbt + bi;
-  int32_t* proj_done = p.sync + (nl + k) * nbt + bi;
+  int32_t* rec_done = p.sync + (k * nbt + bi) * GC_MAXCS;            // [CS] iterations finished by each recurrence CTA
+  int32_t* proj_done = p.sync + ((nl + k) * nbt + bi) * GC_MAXCS;    // ... by each projection CTA
   const int q = warp & 3;
   const int tid = threadIdx.x - 64;
   const int t_first = active_steps(p.bt, L, m0) - 1;      // last step at which this batch tile is alive
@@ -603,11 +627,11 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(w_bar, w_bytes);
         for (int kc = 0; kc < nkc; ++kc) ptx::tma_load_2d(w_sm + kc * 4096, &p.tmWihT[k + 1], w_bar, kc * 64, j0);
-        const int32_t* above = p.sync + (k + 1) * nbt + bi;
+        const int32_t* above = p.sync + ((k + 1) * nbt + bi) * GC_MAXCS;
         for (int it = 0; it <= t_first; ++it) {
           const int t = t_first - it, s = it % S;
           GC_DBG(1, 0, it, 0);
-          wait_counter(above, (it + 1) * CS);               // every slice of dgi^{k+1}_t is in global memory
+          wait_all_counters(above, CS, it + 1);             // every slice of dgi^{k+1}_t is in global memory
           fence_proxy_async_all();
           GC_DBG(1, 0, it, 1);
           ptx::mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
@@ -663,7 +687,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
         }
       }
     } else if (warp == 6) {
-      if (ptx::elect_one()) signaller_loop(sig_ctr, 32, (uint32_t)(t_first + 1), proj_done);
+      if (ptx::elect_one()) signaller_loop(sig_ctr, 32, (uint32_t)(t_first + 1), proj_done + c);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -734,7 +758,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
           GC_DBG(1, 0, it, 0);
           ptx::mbar_wait(&dx_empty[s], ((it / GC_GS) & 1) ^ 1);
           GC_DBG(1, 0, it, 1);
-          wait_counter(proj_done, (it + 1) * CS);
+          wait_all_counters(proj_done, CS, it + 1);
           fence_proxy_async_all();
           GC_DBG(1, 0, it, 2);
           ptx::mbar_arrive_expect_tx(&dx_full[s], DXB);
@@ -763,7 +787,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const __
       }
     }
   } else if (warp == 6) {
-    if (ptx::elect_one()) signaller_loop(sig_ctr, 128, (uint32_t)(t_first + 1), rec_done);
+    if (ptx::elect_one()) signaller_loop(sig_ctr, 128, (uint32_t)(t_first + 1), rec_done + c);
   } else {
     const uint32_t me = (uint32_t)c;
     const int quad = tid & 7, row0 = tid >> 3;
@@ -1195,7 +1219,7 @@ extern "C" int ark_gru_cluster_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t
   ARK_REQUIRE(aligned16(x_b) && aligned16(hp_b) && aligned16(out_b) && aligned16(ws) && (!h0 || aligned16(h0)), ARK_E_ALIGN,
               "gru_cluster_fwd: 16-byte alignment");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * 2 * pl.nbt * nl, s);
+  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * 2 * pl.nbt * nl * GC_MAXCS, s);
   if (e != cudaSuccess) return fail((int)e, "gru_cluster_fwd: memset: %s", cudaGetErrorString(e));
   GruClFwdParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -1240,7 +1264,7 @@ extern "C" int ark_gru_cluster_bwd(const float* dy_top, const uint16_t* r, const
   ARK_REQUIRE(aligned16(dy_top) && aligned16(dgi_b) && aligned16(dgh_b) && aligned16(ws) && (!dh0 || aligned16(dh0)), ARK_E_ALIGN,
               "gru_cluster_bwd: 16-byte alignment");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * 2 * pl.nbt * nl, s);
+  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * 2 * pl.nbt * nl * GC_MAXCS, s);
   if (e != cudaSuccess) return fail((int)e, "gru_cluster_bwd: memset: %s", cudaGetErrorString(e));
   if (dh0) {
     e = cudaMemsetAsync(dh0, 0, sizeof(float) * bt0 * d, s);

@@ -255,7 +255,7 @@ class SailEngine:
         wave = cluster or (self.gru_mode in ("auto", "wave") and wave_ok)
         persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru and not wave
         gh_ws = None if (persist or wave) else new(b0, d3)
-        sync_ws = new(2 * nl * ((b0 + 15) // 16), dtype=torch.int32) if (persist or wave) else None
+        sync_ws = new(32 * nl * ((b0 + 15) // 16), dtype=torch.int32) if (persist or wave) else None   # cluster: 2*nl*tiles*16
         cl_ws = self._cluster_ws(L, b0, d, nl) if cluster else None
         if wave:
             # the whole stack in ONE cooperative launch: layers run as a diagonal wavefront (L+nl-1 dependent

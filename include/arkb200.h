@@ -208,7 +208,7 @@ int ark_gru_wave_bwd(const float* dy_top, const uint16_t* r, const uint16_t* z, 
  * ark_gru_cluster_supported returns the batch-tile rows NB (16/32/64) or 0 (needs d in {128,256,384,512}, nl <= 4,
  * 2*nl*(d/32)*ceil(bt0/NB) <= 148 co-resident CTAs, L <= 4096; queries the device).  ws: scratch of
  * ark_gru_cluster_workspace_bytes(L, bt0, d, nl) bytes (16-byte aligned; the same buffer may serve fwd and bwd);
- * sync_ws int32 [2*nl*ceil(bt0/NB)]. */
+ * sync_ws int32 [2*nl*ceil(bt0/NB)*16] (one counter per CTA of every stage). */
 int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl, int64_t L);
 /* debugging aid: with ARK_GRU_CLUSTER_DBG=<first iteration> in the environment the cluster kernels record a clock64
  * timeline [2 dir][8 blockIdx.z][3 thread roles][4 iterations][16 points] of CTA (0,0) of every stage */
