@@ -5,7 +5,11 @@
 //
 // One thread-block CLUSTER of CS = d/32 CTAs owns (layer, batch tile); CTA c owns hidden units j0 = 32c .. 32c+31.
 // Operands are swapped w.r.t. gru_wave: the resident WEIGHT slice is the UMMA A operand (M = gate rows), the batch
-// rows are the B operand (N = NB in {16,32,64} rows), so TMEM lanes = gate rows, TMEM columns = batch rows.
+// rows are the B operand (N = NB in {16,32,64} rows), so TMEM lanes = gate rows, TMEM columns = batch rows.  The
+// weight slice is copied ONCE into TENSOR MEMORY (tcgen05.st) and the MMAs take A from TMEM (tcgen05.mma [d],[a],bdesc):
+// with A in shared memory every step re-read the whole slice (4 KB per 128x16x16 MMA, ~37 cycles each); from TMEM the
+// 32 MMAs of a step take ~440 cycles.  (The backward projection keeps its [32 x 3d] slice in shared memory: it does
+// not fit the 512 TMEM columns.)
 //
 //   forward, recurrence CTA (layer k): A = rows {g*d + j0..j0+32} (g = r,z,n) of W_hh^k, resident.  Step t:
 //     D[96 x NB] = W_hh_slice . h_{t-1}^T  (h_{t-1} [NB x d] bf16 lives in THIS CTA's shared memory),
@@ -23,7 +27,8 @@
 //   backward, projection CTA: dx_t = dgi^{k+1}_t W_ih^{k+1} for the layer below (pipelined, K = 3d).
 //
 // Layers run as a wavefront exactly as in gru_wave.cu (L + nl - 1 dependent steps); the clock two layers
-// synchronise on is "iterations of this batch tile done" (one release/acquire counter per (stage, batch tile)).
+// synchronise on is "iterations of this batch tile done", one release/acquire counter PER CTA of a (stage, batch
+// tile) (see wait_all_counters), bumped by a signaller warp so that the release fence is never on the chain.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
