@@ -227,3 +227,36 @@ def test_two_rank_gloo_factor_gather_equals_weight_gradient_all_reduce(tmp_path)
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("OK") == 2
+
+
+def test_bf16_partial_sum_reduce_scatter_error_is_operand_rounding_sized():
+    """Numerical contract of the cluster GRU backward (ark_b200/csrc/gru_cluster.cu): every CTA multiplies its 96 gate
+    columns (fp32 accumulate over K = 96 from bf16 operands), ROUNDS its partial sum to bf16 for the exchange through
+    distributed shared memory, and the owner adds the CS partials in fp32.  The extra error w.r.t. one fp32
+    accumulation over K = 3d stays of the order of the bf16 rounding of the operands themselves (so the 3e-2
+    gradient tolerance of the parity tests is not consumed by it)."""
+    rng = np.random.default_rng(0)
+    d, nb, cs = 512, 16, 16
+
+    def bf16(x):
+        x = np.asarray(x, dtype=np.float32)
+        u = x.view(np.uint32)
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000       # round to nearest even
+        return u.view(np.float32)
+
+    W = bf16(rng.standard_normal((3 * d, d)) / np.sqrt(d))     # W_hh [3d, d]
+    dgh = bf16(rng.standard_normal((nb, 3 * d)) * 1e-2)        # dgh_t [NB, 3d]
+    exact = dgh.astype(np.float64) @ W.astype(np.float64)       # what one long accumulation of the bf16 operands gives
+    # CTA c owns gate rows {g*d + 32c .. 32c+31}: its partial, rounded to bf16 before the exchange
+    total = np.zeros((nb, d), dtype=np.float32)
+    for c in range(cs):
+        rows = np.concatenate([g * d + 32 * c + np.arange(32) for g in range(3)])
+        part = (dgh[:, rows].astype(np.float64) @ W[rows].astype(np.float64)).astype(np.float32)
+        total += bf16(part)
+    rel = np.linalg.norm(total - exact) / np.linalg.norm(exact)
+    # reference point: the error the bf16 rounding of the OPERANDS already causes w.r.t. fp32 operands
+    W32 = rng.standard_normal((3 * d, d)).astype(np.float32) / np.sqrt(d)
+    g32 = (rng.standard_normal((nb, 3 * d)) * 1e-2).astype(np.float32)
+    op_rel = (np.linalg.norm(bf16(g32).astype(np.float64) @ bf16(W32).astype(np.float64) - g32.astype(np.float64) @ W32)
+              / np.linalg.norm(g32.astype(np.float64) @ W32))
+    assert rel < 4e-3 and rel < 2.0 * op_rel, (rel, op_rel)
