@@ -165,10 +165,12 @@ __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(
 
 __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(
     const float* __restrict__ heads, int ld_heads, const float* __restrict__ eps, const int32_t* __restrict__ perm,
-    const float* __restrict__ dz_in, int B, int dz, int clamp_logv, float bk, float* __restrict__ dheads,
+    const float* __restrict__ dz_in, int B, int dz, int clamp_logv, float bk, const float* __restrict__ beta_dev,
+    const float* __restrict__ dmu_ext, const float* __restrict__ dlogv_ext, float* __restrict__ dheads,
     uint16_t* __restrict__ dheads_bf16, int ld_dh) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dz) return;
+  if (beta_dev) bk *= *beta_dev;      // replayed CUDA graphs: beta lives in device memory (changes every epoch)
   const int b = i / dz, j = i - b * dz;
   const float mu = heads[(int64_t)b * ld_heads + j];
   const float raw = heads[(int64_t)b * ld_heads + dz + j];
@@ -178,10 +180,13 @@ __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(
     lv = fminf(fmaxf(raw, -10.f), 10.f);
     pass = (raw >= -10.f) && (raw <= 10.f);  // torch.clamp passes the gradient on the closed interval
   }
-  const float e = eps[(int64_t)(perm ? perm[b] : b) * dz + j];
+  const int64_t src = (int64_t)(perm ? perm[b] : b) * dz + j;
+  const float e = eps[src];
   const float dzv = dz_in[i];
-  const float dmu = fmaf(bk, mu, dzv);
+  float dmu = fmaf(bk, mu, dzv);
   float dlv = 0.5f * dzv * e * expf(0.5f * lv) + 0.5f * bk * (expf(lv) - 1.f);
+  if (dmu_ext) dmu += dmu_ext[src];          // upstream gradients of the returned (mu, logv) (autograd forward())
+  if (dlogv_ext) dlv += dlogv_ext[src];
   if (!pass) dlv = 0.f;
   const int64_t o = (int64_t)b * ld_dh;
   if (dheads) {
@@ -259,12 +264,13 @@ extern "C" int ark_reparam_kl_fwd(const float* heads, int64_t ld_heads, const fl
 
 extern "C" int ark_reparam_kl_bwd(const float* heads, int64_t ld_heads, const float* eps, const int32_t* perm,
                                   const float* dz_in, int64_t B, int64_t dz, int clamp_logv, float beta_kl_scale,
+                                  const float* beta_dev, const float* dmu_ext, const float* dlogv_ext,
                                   float* dheads, uint16_t* dheads_bf16, int64_t ld_dh, void* stream) {
   ARK_REQUIRE(heads && eps && dz_in && (dheads || dheads_bf16), ARK_E_BADARG, "reparam_kl_bwd: null pointer");
   ARK_REQUIRE(B > 0 && dz > 0 && ld_heads >= 2 * dz && ld_dh >= 2 * dz, ARK_E_BADARG, "reparam_kl_bwd: bad sizes");
   const int n = (int)(B * dz);
   reparam_kl_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      heads, (int)ld_heads, eps, perm, dz_in, (int)B, (int)dz, clamp_logv, beta_kl_scale, dheads, dheads_bf16,
-      (int)ld_dh);
+      heads, (int)ld_heads, eps, perm, dz_in, (int)B, (int)dz, clamp_logv, beta_kl_scale, beta_dev, dmu_ext, dlogv_ext,
+      dheads, dheads_bf16, (int)ld_dh);
   return launched("reparam_kl_bwd");
 }

@@ -29,6 +29,7 @@
 // Layers run as a wavefront exactly as in gru_wave.cu (L + nl - 1 dependent steps); the clock two layers
 // synchronise on is "iterations of this batch tile done", one release/acquire counter PER CTA of a (stage, batch
 // tile) (see wait_all_counters), bumped by a signaller warp so that the release fence is never on the chain.
+#include <vector>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -144,17 +145,17 @@ __device__ __forceinline__ void sig_arrive(uint32_t* ctr) {
 }
 __device__ __forceinline__ void signaller_loop(uint32_t* ctr, uint32_t per_iter, uint32_t n_iters, int32_t* flag) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; done < n_iters; ++spin) {
+  for (ptx::SpinGuard g; done < n_iters;) {
     uint32_t v;
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(ctr)) : "memory");
     v /= per_iter;
     if (v > done) {
       red_release_add(flag, (int)(v - done));
       done = v;
-      spin = 0;
+      g = ptx::SpinGuard();
     } else {
       __nanosleep(64);
-      if (spin > (1u << 24)) { printf("arkb200: gru_cluster signaller timed out (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z); __trap(); }
+      if (g.expired()) { printf("arkb200: gru_cluster signaller timed out (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z); __trap(); }
     }
   }
 }
@@ -163,7 +164,7 @@ __device__ __forceinline__ void signaller_loop(uint32_t* ctr, uint32_t per_iter,
 // wait for the peers' global stores) complete the count of a slower peer's iteration.
 constexpr int GC_MAXCS = 16;
 __device__ __forceinline__ void wait_all_counters(const int32_t* p, int n, int target) {
-  for (uint32_t spin = 0;; ++spin) {
+  for (ptx::SpinGuard g;;) {
     int v[GC_MAXCS];
 #pragma unroll
     for (int c = 0; c < GC_MAXCS; ++c) {      // all loads in flight together (one 64-byte line)
@@ -174,7 +175,7 @@ __device__ __forceinline__ void wait_all_counters(const int32_t* p, int n, int t
 #pragma unroll
     for (int c = 1; c < GC_MAXCS; ++c) m = min(m, v[c]);
     if (m >= target) break;
-    if (spin > (1u << 22)) {
+    if (g.expired()) {
       printf("arkb200: gru_cluster stage counters timed out (block %d,%d,%d want %d have %d)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, target, m);
       __trap();
@@ -1122,9 +1123,32 @@ static int launch_cluster(Kern kern, const Params& prm, dim3 grid, int cs, int s
   // ARK_GRU_CLUSTER_NO_COOP=1 drops the cooperative attribute (Nsight Compute refuses cooperative cluster launches);
   // co-residency was established by the occupancy query of ark_gru_cluster_supported
   static int no_coop = -1;
-  if (no_coop < 0) { const char* ev = getenv("ARK_GRU_CLUSTER_NO_COOP"); no_coop = ev ? atoi(ev) : 0; }
+  if (no_coop < 0) {
+    const char* ev = getenv("ARK_GRU_CLUSTER_NO_COOP");
+    no_coop = ev ? atoi(ev) : 0;
+    // Nsight Compute's injection does not survive a cooperative cluster launch (the profiler exits with rc 9 and
+    // takes the process with it, so there is no error to retry on): recognise a profiled process by the variables
+    // its launcher exports
+    extern char** environ;
+    for (char** e = environ; !ev && e && *e; ++e)
+      if (!strncmp(*e, "NV_NSIGHT", 9) || !strncmp(*e, "NV_COMPUTE_PROFILER", 19) || !strncmp(*e, "CUDA_INJECTION64_PATH", 21) ||
+          !strncmp(*e, "NVTX_INJECTION64_PATH", 21))
+        no_coop = 1;
+  }
   cfg.numAttrs = no_coop ? 1 : 2;
   e = cudaLaunchKernelEx(&cfg, kern, prm);
+  if (e != cudaSuccess && cfg.numAttrs == 2) {
+    // a profiler / sanitizer that refuses cooperative cluster launches: the plain cluster launch is equivalent here
+    // (co-residency of every cluster was established by ark_gru_cluster_supported's occupancy query)
+    (void)cudaGetLastError();
+    cudaStreamCaptureStatus cs_ = cudaStreamCaptureStatusNone;
+    (void)cudaStreamIsCapturing(s, &cs_);
+    if (cs_ == cudaStreamCaptureStatusNone) {
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, kern, prm);
+      if (e == cudaSuccess) no_coop = 1;
+    }
+  }
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     return fail((int)e, "%s: launch grid=(%u,%u,%u) cluster=%d smem=%d: %s", who, grid.x, grid.y, grid.z, cs, smem,
@@ -1179,10 +1203,13 @@ extern "C" int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl, int
   ClusterPlan pl;
   if (!plan_cluster(d, bt0, nl, L, &pl)) return 0;
   // the kernels spin on flags of other clusters: every cluster of the launch must be co-resident
-  static thread_local struct { int64_t d, bt0, nl, L; int ok; } memo[16];
-  static thread_local int n_memo = 0;
-  for (int i = 0; i < n_memo; ++i)
-    if (memo[i].d == d && memo[i].bt0 == bt0 && memo[i].nl == nl && memo[i].L == L) return memo[i].ok ? pl.NB : 0;
+  // memoised on what the launch configuration depends on (d, layers, tile rows / count, shared-memory sizes): ragged
+  // batches change L every step but hit the same handful of plans
+  struct Memo { int64_t d, nl; ClusterPlan pl; int ok; };
+  static thread_local std::vector<Memo> memo;
+  for (const Memo& m : memo)
+    if (m.d == d && m.nl == nl && m.pl.NB == pl.NB && m.pl.nbt == pl.nbt && m.pl.smem_f == pl.smem_f && m.pl.smem_b == pl.smem_b)
+      return m.ok ? pl.NB : 0;
   GruClFwdParams pf;
   GruClBwdParams pb;
   memset(&pf, 0, sizeof(pf));
@@ -1192,7 +1219,7 @@ extern "C" int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl, int
                        pl.smem_f, 0, "gru_cluster_fwd", true) == 0 &&
            dispatch_nb(pl.NB, gru_cluster_bwd_kernel<16>, gru_cluster_bwd_kernel<32>, gru_cluster_bwd_kernel<64>, pb, gb, pl.CS,
                        pl.smem_b, 0, "gru_cluster_bwd", true) == 0;
-  if (n_memo < 16) { memo[n_memo].d = d; memo[n_memo].bt0 = bt0; memo[n_memo].nl = nl; memo[n_memo].L = L; memo[n_memo].ok = ok; ++n_memo; }
+  memo.push_back(Memo{d, nl, pl, ok});
   return ok ? pl.NB : 0;
 }
 

@@ -15,8 +15,8 @@ __device__ __forceinline__ void red_release_add(int32_t* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void wait_counter(const int32_t* p, int target) {
-  for (uint32_t spin = 0; ld_acquire(p) < target; ++spin) {
-    if (spin > (1u << 24)) {
+  for (ptx::SpinGuard g; ld_acquire(p) < target;) {
+    if (g.expired()) {
       printf("arkb200: gru_persist tile counter timed out (block %d,%d want %d have %d)\n", blockIdx.x, blockIdx.y,
              target, ld_acquire(p));
       __trap();

@@ -48,10 +48,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (the launch fails with an error) instead of hanging the GPU.
+// Bounded waits: a protocol bug must trap (the launch fails with an error) instead of hanging the GPU.  The bound is
+// WALL-CLOCK (%globaltimer, checked every 4096 polls), not a poll count: a run that is legitimately slowed down
+// (compute-sanitizer, time-slicing, a debugger) keeps polling; only ~20 s without progress on one wait traps.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct SpinGuard {
+  uint64_t t0 = 0;
+  uint32_t n = 0;
+  __device__ __forceinline__ bool expired() {
+    if ((++n & 0xFFFu) != 0) return false;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > 20000000000ull;
+  }
+};
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) {
+  for (SpinGuard g; !mbar_try_wait(bar, parity);) {
+    if (g.expired()) {
       printf("arkb200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
@@ -228,8 +245,8 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 }
 // wait on a barrier completed by peers of the cluster (complete_tx of their bulk copies)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait_cluster(bar, parity); ++spin) {
-    if (spin > (1u << 26)) {
+  for (SpinGuard g; !mbar_try_wait_cluster(bar, parity);) {
+    if (g.expired()) {
       printf("arkb200: cluster mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x);
       __trap();

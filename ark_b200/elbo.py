@@ -44,6 +44,8 @@ class SailEngine:
     _hold_comm, _held = False, ()
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
+    max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
+    keep = None                      # tests: a dict that receives references to the GRU stack's internal tensors
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gemm_backend="tc", dist_group=None,
                  bucket_mb=16.0, seed=0):
@@ -83,10 +85,11 @@ class SailEngine:
         self._capturing = False
         self._segment_break = None
         self._graphs = {}
-        # per-step scalars of a replayed graph, ONE 16-byte device buffer (one H2D copy per step):
-        self._dyn_raw = torch.zeros(16, device=dev, dtype=torch.uint8)
+        # per-step scalars of a replayed graph, ONE 24-byte device buffer (one H2D copy per step):
+        self._dyn_raw = torch.zeros(24, device=dev, dtype=torch.uint8)
         self.dyn_f = self._dyn_raw[:8].view(torch.float32)           # [lr/(1-b1^t), 1/sqrt(1-b2^t)]
-        self.dyn_i = self._dyn_raw[8:].view(torch.int64)             # running Philox offset
+        self.dyn_i = self._dyn_raw[8:16].view(torch.int64)           # running Philox offset
+        self.dyn_beta = self._dyn_raw[16:20].view(torch.float32)     # beta of the ELBO (changes every epoch: NOT a graph key)
         self.launches_replayed = 0       # kernels of libarkb200 executed through graph replays
         self.force_unfused_gru = False   # tests: compare the persistent GRU kernel with the per-step path
         self.gru_mode = "auto"           # "auto": cluster stack kernel (long chains of short batch tiles), else the
@@ -140,7 +143,12 @@ class SailEngine:
 
         def __enter__(self):
             if self.eng.prof is not None:
-                self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                # inside a stream capture the events become EXTERNAL event-record nodes of the graph: every replay
+                # re-records them, so elapsed_time() after a replay is the kernel's time inside the replayed graph
+                # (no host launch gaps — what bench.py's per-kernel list is built from)
+                ext = bool(self.eng._capturing)
+                self.e0 = torch.cuda.Event(enable_timing=True, external=ext)
+                self.e1 = torch.cuda.Event(enable_timing=True, external=ext)
                 self.e0.record()
 
         def __exit__(self, *exc):
@@ -153,11 +161,12 @@ class SailEngine:
         pass); free otherwise."""
         return SailEngine._Timer(self, tag, flops, nbytes)
 
-    def profile_summary(self):
-        """tag -> dict(ms, calls, flops, bytes) from the recorded events (synchronises)."""
+    def profile_summary(self, prof=None, agg=None):
+        """tag -> dict(ms, calls, flops, bytes) from the recorded events (synchronises).  `prof`: the event list of a
+        captured profiling graph (train_step_graphed with self.prof set), read after EACH replay; `agg` accumulates."""
         torch.cuda.synchronize()
-        agg = {}
-        for tag, e0, e1, fl, nb in self.prof:
+        agg = {} if agg is None else agg
+        for tag, e0, e1, fl, nb in (self.prof if prof is None else prof):
             a = agg.setdefault(tag, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
             a["ms"] += e0.elapsed_time(e1)
             a["calls"] += 1
@@ -171,6 +180,24 @@ class SailEngine:
         """One ELBO forward+backward over a device-resident batch.  Gradients land in ``self.flat.grad``
         (overwritten, never accumulated).  Returns a device tensor [ce, kl] (already globally normalised when
         the *_global normalisers are given; the caller sums them over ranks)."""
+        gen = self._fb_gen(triples, seq, lay, eps, beta, n_tok_global, batch_global, train, stats_out)
+        try:
+            next(gen)
+        except StopIteration as stop:
+            return stop.value
+        raise RuntimeError("forward_backward: the fused step must not suspend")
+
+    def _fb_gen(self, triples, seq, lay: PackedLayout, eps, beta, n_tok_global=None, batch_global=None,
+                train=True, stats_out=None, dropout=None, autograd=False):
+        """The step as a GENERATOR.  Fused mode (autograd=False) runs to completion on the first next().  With
+        autograd=True it suspends once, between forward and backward: it yields {"logits": bf16 [N, ldv] packed
+        time-major rows, "heads": f32 [B, 2dz] = (mu | raw logv)} and is resumed with
+        {"dmu": f32 [B, dz] | None, "dlogv": ...} AFTER the caller has overwritten `logits` in place with
+        d(loss)/d(logits) — the activations of the forward pass stay alive in the suspended frame exactly as long as
+        the autograd node that owns the generator (kgvae.model.models._ForwardFn: the differentiable
+        SAIL.forward / ARK.forward of the reference interface, models.py:317-320,395-405).
+        `dropout` (default: `train`) switches the inter-layer GRU dropout independently of running the backward."""
+        dropout = train if dropout is None else bool(dropout)
         f, dev, d, dz, V, ldv, nl = self.flat, self.device, self.d, self.dz, self.V, self.ldv, self.nl
         B = seq.shape[0]
         N, L = lay.n_tok, lay.L
@@ -265,7 +292,7 @@ class SailEngine:
             ops.cast_bf16(h0[:b0], h0_b)
             hp_all[:, :b0].copy_(h0_b)
             wave_gates = tuple(new(nl, N, d, dtype=bf) for _ in range(4))
-            dropping = train and self.p_drop > 0 and nl > 1
+            dropping = dropout and self.p_drop > 0 and nl > 1
             wave_mask = new(nl - 1, N, d, dtype=torch.uint8) if dropping else None
             stride = (N * d + 3) // 4
             with self._timed("gru_cluster_fwd" if cluster else "gru_wave_fwd", flops=4.0 * N * d * d3 * nl):
@@ -310,7 +337,7 @@ class SailEngine:
                     ops.gru_layer_fwd(hp_b, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
                                       lay.bt, lay.off, L, d, y, y_b, gates, gh_ws, use_tc)
             mask = None
-            if train and self.p_drop > 0 and k < nl - 1:
+            if dropout and self.p_drop > 0 and k < nl - 1:
                 mask = new(N, d, dtype=torch.uint8)
                 if self._capturing:   # replayed graphs read the running Philox offset from device memory
                     ops.dropout_bf16(y_b, self.p_drop, self.seed, self._drop_calls * ((N * d + 3) // 4), y_b, mask,
@@ -326,8 +353,15 @@ class SailEngine:
         w_out = self._w("dec.tok_emb.weight") if self.tied else self._w("dec.out.weight")
         self._gemm(u_b, K, w_out, K, logits, N, V, d, tag="vocab_fwd", bias=f.p("dec.out.bias"))
         # CE forward+backward in place (ablation_study.py:64-69): logits -> (softmax-onehot)/N_tok
-        with self._timed("softmax_ce", nbytes=2.0 * N * V * 2 + 12.0 * N):
-            ops.softmax_ce(logits, V, tgt, 1.0 / n_tok_g, True, out[0:1], None)
+        ext = None
+        if autograd:
+            # hand the logits out; the caller turns the buffer into d(loss)/d(logits) in place and resumes us
+            ext = yield {"logits": logits, "heads": heads if self.has_enc else None}
+            ext = ext or {}
+            beta = 0.0                       # the KL term (if any) arrives through dmu / dlogv
+        else:
+            with self._timed("softmax_ce", nbytes=2.0 * N * V * 2 + 12.0 * N):
+                ops.softmax_ce(logits, V, tgt, 1.0 / n_tok_g, True, out[0:1], None)
         if not train:
             return out
 
@@ -366,6 +400,8 @@ class SailEngine:
                     ops.gru_cluster_bwd(*bwd_args, cl_ws)
                 else:
                     ops.gru_wave_bwd(*bwd_args)
+            if self.keep is not None:
+                self.keep.update(gru_out=out_all, gru_dgi=dgi_all, gru_dgh=dgh_all, gru_dh0=dh0)
             # the chain first: dX feeds the embedding scatter and the encoder backward, whose (large, late) gradient
             # buckets then reduce / update on the side stream WHILE the GRU weight-gradient GEMMs below run
             self._gemm(dgi_all[0], K, self._w("dec.gru.weight_ih_l0"), MN, dy, N, d, d3, tag="gru_dX")
@@ -434,7 +470,13 @@ class SailEngine:
         ld_dh = _up8(2 * dz)
         dheads = torch.zeros(B, ld_dh, device=dev)
         dheads_b = torch.zeros(B, ld_dh, device=dev, dtype=bf)
-        ops.reparam_kl_bwd(heads, eps, lay.perm_dev, dz_in, dz, True, beta / (b_g * dz), dheads, dheads_b)
+        if self._capturing:      # replayed graphs read beta from device memory (ablation_study.py:589-591: per-epoch schedule)
+            ops.reparam_kl_bwd(heads, eps, lay.perm_dev, dz_in, dz, True, 1.0 / (b_g * dz), dheads, dheads_b,
+                               beta_dev=self.dyn_beta)
+        else:
+            ops.reparam_kl_bwd(heads, eps, lay.perm_dev, dz_in, dz, True, beta / (b_g * dz), dheads, dheads_b,
+                               dmu_ext=None if ext is None else ext.get("dmu"),
+                               dlogv_ext=None if ext is None else ext.get("dlogv"))
         g_wh = f.fused(f.grad, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
         g_bh = f.fused(f.grad, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
         self._gemm(dheads_b[:, :2 * dz], MN, acts[-1], MN, g_wh, 2 * dz, d3, B, tag="enc_heads_bwd")
@@ -615,23 +657,25 @@ class SailEngine:
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def train_step_graphed(self, triples, seq, lay, eps, beta, lr=None, n_tok_global=None, batch_global=None):
         """Same as train_step, but the ~190 launches of the step are captured ONCE per batch layout
-        (B, T, per-step row counts, normalisers, beta) into CUDA graphs and replayed: the host cost of a step
+        (B, T, per-step row counts, normalisers — NOT beta, lr or the Philox offset: those live in a small device
+        buffer refreshed by one H2D copy per step) into CUDA graphs and replayed: the host cost of a step
         drops to a few small input copies + a handful of graph launches.  Layouts that never repeat (ragged real
         data) should use train_step.
         Single GPU: the per-bucket Adam launches are a parallel branch of the one captured graph.  Under data
         parallelism the step is captured as a CHAIN of graph segments cut at the gradient-bucket boundaries; between
         two segments the replay loop issues that bucket's NCCL all-reduce + Adam eagerly on the side stream, so they
         overlap the following segment of backward exactly as in the eager step."""
-        key = (None if triples is None else tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(), float(beta),
-               n_tok_global, batch_global)
+        key = (None if triples is None else tuple(triples.shape), tuple(seq.shape), lay.bt.tobytes(),
+               n_tok_global, batch_global, self.prof is not None)     # (a profiling capture carries event nodes)
         ent = self._graphs.get(key)
         self.step_count += 1
         lr = self.lr if lr is None else float(lr)
         b1, b2 = self.betas
         # pageable sources: the driver stages them at call time, so the next step may overwrite nothing in flight
-        host = np.empty(16, dtype=np.uint8)
+        host = np.zeros(24, dtype=np.uint8)
         host[:8].view(np.float32)[:] = (lr / (1.0 - b1 ** self.step_count), 1.0 / math.sqrt(1.0 - b2 ** self.step_count))
-        host[8:].view(np.int64)[0] = self.philox_offset
+        host[8:16].view(np.int64)[0] = self.philox_offset
+        host[16:20].view(np.float32)[0] = beta
         self._dyn_raw.copy_(torch.from_numpy(host))
         if ent is None:
             dev = self.device
@@ -682,6 +726,10 @@ class SailEngine:
             st["out"], st["segs"] = out, segs
             st["philox_per_step"] = self._drop_calls * ((lay.n_tok * self.d + 3) // 4)
             st["n_launch"] = _C.lib().launch_count() - n0
+            if self.prof is not None:
+                st["prof"], self.prof = list(self.prof), []
+            if len(self._graphs) >= self.max_graphs:       # bounded: every entry pins a private pool of activations
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent = st
         else:
             if triples is not None:
@@ -698,6 +746,7 @@ class SailEngine:
             torch.cuda.current_stream().wait_stream(self.comm_stream)     # the next forward needs every updated weight
         self.launches_replayed += ent["n_launch"]
         self.philox_offset += ent["philox_per_step"]
+        self.last_graph = ent
         return ent["out"]
 
     def eval_step(self, triples, seq, lay, eps, beta):

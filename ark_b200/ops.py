@@ -99,14 +99,16 @@ def reparam_kl_fwd(heads, eps, perm, dz, clamp, kl_scale, z, z_bf16, kl_acc):
                   _ptr(kl_acc, torch.float32), _stream())
 
 
-def reparam_kl_bwd(heads, eps, perm, dz_in, dz, clamp, beta_kl_scale, dheads, dheads_bf16):
+def reparam_kl_bwd(heads, eps, perm, dz_in, dz, clamp, beta_kl_scale, dheads, dheads_bf16, beta_dev=None, dmu_ext=None,
+                   dlogv_ext=None):
     B = heads.shape[0]
-    _contig(eps, perm, dz_in)
+    _contig(eps, perm, dz_in, dmu_ext, dlogv_ext)
     ld = dheads.stride(0) if dheads is not None else dheads_bf16.stride(0)
     if dheads is not None and dheads_bf16 is not None and dheads.stride(0) != dheads_bf16.stride(0):
         raise _C.ArkError("dheads and dheads_bf16 must share a row stride")
     _C.lib().call("ark_reparam_kl_bwd", _ptr(heads, torch.float32), heads.stride(0), _ptr(eps, torch.float32),
                   _ptr(perm, torch.int32), _ptr(dz_in, torch.float32), B, dz, int(clamp), float(beta_kl_scale),
+                  _ptr(beta_dev, torch.float32), _ptr(dmu_ext, torch.float32), _ptr(dlogv_ext, torch.float32),
                   _ptr(dheads, torch.float32), _ptr(dheads_bf16, torch.bfloat16), ld, _stream())
 
 

@@ -14,9 +14,16 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, **engine_kw):
         self.engine = model.engine(lr=lr, betas=betas, eps=eps, **engine_kw)
         self.engine.lr, self.engine.betas, self.engine.eps = float(lr), tuple(betas), float(eps)
-        names = self.engine.flat.order
-        named = dict(model.named_parameters())
-        params = [named[n] for n in names]
+        # parameters are registered in MODULE order (model.parameters()), exactly like the reference's
+        # Adam(model.parameters()) (ablation_study.py:571): torch indexes optimizer_state_dict entries by position, so
+        # reference checkpoints load into FusedAdam and vice versa.  The flat buffers are ordered differently
+        # (gradient-readiness order); the per-parameter views below do not care.
+        named = list(model.named_parameters())
+        names = [n for n, _ in named]
+        params = [p for _, p in named]
+        missing = set(names) ^ set(self.engine.flat.order)
+        if missing:
+            raise RuntimeError(f"optimizer / flat-buffer parameter mismatch: {sorted(missing)}")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False))
         f = self.engine.flat
         for n, p in zip(names, params):   # expose the flat Adam state through the usual per-parameter dicts

@@ -7,16 +7,25 @@
 
 A step = zero_grad + ELBO forward + backward (+ NCCL gradient all-reduce) + Adam over one synthetic
 IntelliGraphs-shaped batch per GPU (weak scaling: the YAML batch_size on every GPU).  `value` = real (non-PAD)
-triples per second, whole job, device-timed with CUDA events, max over ranks, inputs resident in HBM.
+triples per second, whole job, device-timed with CUDA events, max over ranks, inputs resident in HBM; the MEDIAN of
+`--windows` (default 5) timed windows of exactly `--steps` steps each (every window is bracketed by barrier +
+synchronize; all window times are in `windows_ms`).
 `e2e` = the same through the public call `SAIL.elbo_step(host tensors)`: host-side packing, pinned H2D copies
 and a device->host read of (ce, kl) every step inside the timed region.
-One JSON line on stdout (rank 0).  Per-op breakdown goes to stderr / gpurun_out/bench_breakdown.json.
+`kernels` = per-kernel time INSIDE the replayed CUDA graph (external event-record nodes around every op of a
+profiling capture of the same step; no host launch gaps), with each kernel's algorithmic FLOP / bytes and roofline
+fraction; `roofline` = the single kernel of that list with the largest time per step.
+`library_baseline` = the reference's modules on device='cuda' in torch eager (cuDNN GRU, cuBLASLt, ATen, torch Adam),
+fp32 with TF32 off and on — the existing-library bar on the same GPU.  `also` = the other BASELINE workloads in the
+same invocation.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
+import statistics
 import sys
 import threading
 import time
@@ -28,6 +37,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ELBO train triples/sec (SAIL fwd+bwd+Adam, synthetic IntelliGraphs-shaped batches)"
 UNIT = "triples/s"
+WORKLOADS = ["syn-paths", "syn-types", "syn-tipr", "wd-movies", "wd-articles"]
 
 
 def parse():
@@ -35,17 +45,21 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps steps; the median is reported")
     ap.add_argument("--impl", default="ark", choices=["ark", "reference"])
-    ap.add_argument("--workload", default="syn-types",
-                    choices=["syn-paths", "syn-types", "syn-tipr", "wd-movies", "wd-articles"])
+    ap.add_argument("--workload", default="syn-types", choices=WORKLOADS)
     ap.add_argument("--model", default="SAIL", choices=["SAIL", "t-SAIL", "ARK", "t-ARK"],
                     help="SAIL = the KG-VAE ELBO path (headline); t-SAIL = Transformer KG-VAE; ARK = decoder-only GRU")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the YAML batch_size)")
     ap.add_argument("--dense", action="store_true", help="every graph at max_edges (what the reference pays for)")
     ap.add_argument("--backend", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE workloads (`also` array)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: YAML batch_size per GPU; strong: YAML batch_size split over the GPUs")
     return ap.parse_args()
 
 
@@ -91,7 +105,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def result(self):
         self.stop_flag = True
@@ -126,7 +140,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     train_steps(model, opt, [hb[0][:2]], 0.5)
     first = time.perf_counter() - t0
-    W = max(0, min(args.warmup, 1) - 1)      # the probe step above already is the warm-up
+    W = max(0, min(args.warmup, max(1, int(30.0 / max(first, 1e-3)))) - 1)      # the probe step above is warm-up #1
     K = int(max(1, min(args.steps, 120.0 / max(first, 1e-3))))
     for i in range(W):
         train_steps(model, opt, [hb[i % 2][:2]], 0.5)
@@ -141,13 +155,212 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": 1 + W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"autoreg_{args.workload} SAIL", "batch_per_step": batch, "dense": args.dense,
-                   "note": "reference CPU path = torch-CPU port of the reference step (same ATen/MKL calls); "
-                           "steps capped so the run ends within minutes"},
+        "config": {"workload": f"autoreg_{args.workload} SAIL", "graphs_per_gpu": batch, "global_batch": batch,
+                   "dense": bool(args.dense),
+                   "note": "reference CPU path = torch-CPU port of the reference step (same ATen/MKL calls), all host "
+                           "threads; steps/warm-up capped so the run ends within minutes"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{K} full train steps of the workload batch, {dt:.1f} s wall"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
+# under profiles/, keyed by (workload, kernel tag)
+NCU_TRAFFIC = {
+    ("syn-types", "gru_persist_bwd"): (44.08e6 + 3.47e6, "profiles/r01_ncu_summary.md"),
+    ("syn-types", "gru_persist_fwd"): (39.37e6 + 2.27e6, "profiles/r01_ncu_summary.md"),
+    ("wd-articles", "gru_cluster_bwd"): (99.65e6 + 90.60e6, "profiles/r01c_ncu_summary.md"),
+    ("wd-articles", "gru_cluster_fwd"): (54.30e6 + 225.63e6, "profiles/r01c_ncu_summary.md"),
+}
+try:    # later captures of this round override / extend the table (written by tools/ncu_summary.py)
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
+        for _k, _v in json.load(_f).items():
+            NCU_TRAFFIC[tuple(_k.split("|"))] = (_v["bytes"], _v["src"])
+except (OSError, ValueError):
+    pass
+
+
+class Workload:
+    """One (workload, model type, batch) on this rank: model + engine + resident synthetic batches + step closures."""
+
+    def __init__(self, args, workload, model_type, batch, dense, dev, group, world, rank, use_graph):
+        from ark_b200.layout import pack_tlayout
+        from ark_b200.synthetic import DeviceBatch, model_config
+        from kgvae.model.models import ARK, SAIL
+        self.cfg = cfg = model_config(workload, model_type=model_type)
+        self.workload, self.mt, self.dense, self.dev, self.world, self.rank = workload, model_type, dense, dev, world, rank
+        self.batch = batch or cfg["batch_size"]
+        if args.scaling == "strong" and not batch:
+            self.batch = max(1, cfg["batch_size"] // world)
+        self.dec_only = model_type in ("ARK", "t-ARK")
+        self.use_graph = use_graph and model_type in ("SAIL", "ARK")
+        torch.manual_seed(0)                       # identical initial weights on every rank
+        self.model = (ARK if self.dec_only else SAIL)(cfg).to(dev)
+        self.eng = self.model.engine(lr=1e-3, gemm_backend=args.backend, dist_group=group, seed=rank)
+        self.n_params = sum(p.numel() for p in self.model.parameters())
+        self.NB = NB = 4
+        self.host = make_host_batches(cfg, self.batch, rank, NB, dense)
+        self.dbs = [DeviceBatch(t, s, n, dev, 1234 + 1000 * rank + i) for i, (t, s, n) in enumerate(self.host)]
+        if model_type in ("t-SAIL", "t-ARK"):      # graph-major ragged rows instead of time-major packed rows
+            for b_, (t, s, _) in zip(self.dbs, self.host):
+                b_.layout = pack_tlayout(t, s, cfg.get("pad_rid")).to(dev)
+        self.eps = [b.eps(cfg["d_latent"], dev) if not self.dec_only else None for b in self.dbs]
+        # global normalisers (SURVEY.md §8e): the sampler knows every rank's lengths, so no per-step collective
+        ntok = torch.tensor([b.layout.n_tok for b in self.dbs], device=dev, dtype=torch.float64)
+        ntri = torch.tensor([b.n_triples for b in self.dbs], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ntok)
+            torch.distributed.all_reduce(ntri)
+        self.ntok_g, self.ntri_g = ntok.tolist(), ntri.tolist()
+        self.bg = self.batch * world
+        self.beta = 0.5
+
+    def step(self, i, graph=None):
+        j = i % self.NB
+        graph = self.use_graph if graph is None else graph
+        eng, d = self.eng, self.dbs[j]
+        fn = eng.train_step_graphed if graph else eng.train_step
+        return fn(d.triples if not self.dec_only else None, d.seq, d.layout, self.eps[j],
+                  self.beta if not self.dec_only else 0.0, n_tok_global=self.ntok_g[j],
+                  batch_global=self.bg if not self.dec_only else None)
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def window(self, steps, step_fn=None):
+        """Exactly `steps` steps bracketed by barrier + synchronize; device time, max over ranks (ms)."""
+        step_fn = step_fn or self.step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    def triples_in(self, steps):
+        return sum(self.ntri_g[i % self.NB] for i in range(steps))
+
+    def measure(self, steps, warmup, windows):
+        for i in range(max(warmup, 3) + (self.NB if self.use_graph else 0)):   # graph mode: first visit of a layout captures
+            self.step(i)
+        times = [self.window(steps) for _ in range(max(1, windows))]
+        med = statistics.median(times)
+        return med, times
+
+    def measure_e2e(self, steps, windows):
+        """The public API with HOST (pinned) buffers: packing, H2D and the D2H read of (ce, kl) inside the timed region."""
+        pinned = [b.host for b in self.dbs]
+        model, dec_only = self.model, self.dec_only
+        lay0 = self.dbs[0].layout
+        meta_bytes = (self.batch + 2 * lay0.L) * 4 if hasattr(lay0, "L") else \
+            (lay0.idx.nbytes + lay0.tok.nbytes * 3 + lay0.enc.cu.nbytes * 2 + lay0.enc.sq_off.nbytes * 2 + lay0.enc.graph.nbytes
+             + lay0.dec.graph.nbytes)
+        h2d = (0 if dec_only else pinned[0][0].numel() * 8) + pinned[0][1].numel() * 8 + meta_bytes + 24
+
+        def api_step(i):
+            j = i % self.NB
+            if dec_only:
+                out = model.ce_step(pinned[j][1], n_tok_global=self.ntok_g[j])
+            else:
+                out = model.elbo_step(pinned[j][0], pinned[j][1], self.beta, n_tok_global=self.ntok_g[j],
+                                      batch_global=self.bg, graph=self.use_graph)
+            return out.tolist()                      # device->host read of the step's (ce, kl)
+
+        for i in range(3):
+            api_step(i)
+        times = []
+        for _ in range(max(1, windows)):
+            self.barrier()
+            t0 = time.perf_counter()
+            dev_ms = self.window(steps, api_step)
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            times.append(max(dev_ms, wall_ms) if self.world == 1 else dev_ms)
+        med = statistics.median(times)
+        return {"value": self.triples_in(steps) / (med / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 8, "ms_per_step": med / steps, "windows_ms": times,
+                "api": "kgvae.model.models.ARK.ce_step(seq_cpu)" if dec_only else
+                       "kgvae.model.models.SAIL.elbo_step(triples_cpu, seq_cpu, beta)"}
+
+    def kernel_profile(self, n_replays=6):
+        """Per-kernel time inside the REPLAYED graph: a second capture of the same step with external event-record
+        nodes around every op (SailEngine._timed), read back after each replay.  Falls back to eager per-op events
+        (which include host launch gaps) for engines without a graphed step."""
+        eng = self.eng
+        agg, mode = {}, "graph-replay event nodes"
+        eng.prof = []
+        try:
+            if self.use_graph:
+                for i in range(self.NB):               # capture the profiling twin of every layout
+                    self.step(i, graph=True)
+                torch.cuda.synchronize()
+                eng.prof = []
+                n = 0
+                for i in range(n_replays):
+                    self.step(i, graph=True)
+                    eng.profile_summary(prof=eng.last_graph["prof"], agg=agg)
+                    n += 1
+                if eng.prof:                            # eager side-stream work between graph segments (NCCL under DP)
+                    eng.profile_summary(agg=agg)
+            else:
+                mode = "eager per-op events (host launch gaps included)"
+                n = n_replays
+                for i in range(n):
+                    self.step(i, graph=False)
+                eng.profile_summary(agg=agg)
+        finally:
+            eng.prof = None
+        return agg, n, mode
+
+    def close(self):
+        self.eng._graphs.clear()
+        del self.eng, self.model, self.dbs, self.eps
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def kernel_table(agg, n_steps, step_ms, pk, workload):
+    rows = []
+    for tag, a in agg.items():
+        if a["ms"] <= 0:
+            continue
+        ms_step = a["ms"] / n_steps
+        row = {"name": tag, "launches_per_step": a["calls"] / n_steps, "ms_per_step": ms_step,
+               "avg_launch_ms": a["ms"] / max(a["calls"], 1), "share_of_step": ms_step / max(step_ms, 1e-9)}
+        if a["flops"] > 0:
+            ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                       frac=ach / pk["bf16_tflops_sustained"], algorithmic_per_launch=a["flops"] / a["calls"])
+        elif a["bytes"] > 0:
+            ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+            row.update(bound="nvlink" if tag.startswith("nccl_") else "hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s",
+                       frac=None if tag.startswith("nccl_") else ach / pk["hbm_gbs"],
+                       algorithmic_per_launch=a["bytes"] / a["calls"])
+        t = NCU_TRAFFIC.get((workload, tag.split(":")[-1])) or NCU_TRAFFIC.get((workload, tag))
+        if t:
+            row["traffic"], row["traffic_src"] = t
+        rows.append(row)
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
+
+
+def roofline_from(rows, pk, mode):
+    ours = [r for r in rows if not r["name"].startswith("nccl_") and "bound" in r]
+    if not ours:
+        return None
+    top = ours[0]
+    return {"kernel": top["name"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+            "unit": top["unit"], "frac": top["frac"], "traffic": top.get("traffic"), "traffic_src": top.get("traffic_src"),
+            "avg_launch_ms": top["avg_launch_ms"], "launches_per_step": top["launches_per_step"],
+            "share_of_step": top["share_of_step"], "algorithmic_per_launch": top.get("algorithmic_per_launch"),
+            "timing": mode, "peak_src": pk["src"] + (" (sustained: timed inside a long step)" if top["bound"] == "tensor" else "")}
 
 
 def main():
@@ -169,183 +382,123 @@ def main():
         group = torch.distributed.group.WORLD
 
     from ark_b200 import _C
-    from ark_b200.layout import pack_tlayout
-    from ark_b200.synthetic import DeviceBatch, model_config
-    from kgvae.model.models import ARK, SAIL
-
-    cfg = model_config(args.workload, model_type=args.model)
-    mt = args.model
-    batch = args.batch or cfg["batch_size"]
-    torch.manual_seed(0)                       # identical initial weights on every rank
-    dec_only = mt in ("ARK", "t-ARK")
-    model = (ARK if dec_only else SAIL)(cfg).to(dev)
-    eng = model.engine(lr=1e-3, gemm_backend=args.backend, dist_group=group)
-    n_params = sum(p.numel() for p in model.parameters())
-
-    NB = 4
-    host = make_host_batches(cfg, batch, rank, NB, args.dense)
-    dbs = [DeviceBatch(t, s, n, dev, 1234 + 1000 * rank + i) for i, (t, s, n) in enumerate(host)]
-    if mt in ("t-SAIL", "t-ARK"):               # graph-major ragged rows instead of time-major packed rows
-        for b_, (t, s, _) in zip(dbs, host):
-            b_.layout = pack_tlayout(t, s, cfg.get("pad_rid")).to(dev)
-    eps = [b.eps(cfg["d_latent"], dev) if not dec_only else None for b in dbs]
-    # global normalisers: the sampler knows every rank's lengths, so no per-step collective
-    ntok = torch.tensor([b.layout.n_tok for b in dbs], device=dev, dtype=torch.float64)
-    ntri = torch.tensor([b.n_triples for b in dbs], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(ntok)
-        torch.distributed.all_reduce(ntri)
-    ntok_g, ntri_g = ntok.tolist(), ntri.tolist()
-    bg = batch * world
-    beta = 0.5
-
+    lib = _C.lib()
+    pk = peaks()
     use_graph = not args.no_graph      # N>1: graph segments cut at the gradient buckets, NCCL eager in between
 
-    def step(i, graph=use_graph):
-        j = i % NB
-        fn = eng.train_step_graphed if graph else eng.train_step
-        return fn(dbs[j].triples if not dec_only else None, dbs[j].seq, dbs[j].layout, eps[j], beta if not dec_only else 0.0,
-                  n_tok_global=ntok_g[j], batch_global=bg if not dec_only else None)
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3) + (NB if use_graph else 0)):   # graph mode: first visit of a layout captures
-        step(i)
-    barrier()
-    lib = _C.lib()
+    w = Workload(args, args.workload, args.model, args.batch, args.dense, dev, group, world, rank, use_graph)
+    for i in range(max(args.warmup, 3) + (w.NB if w.use_graph else 0)):
+        w.step(i)
+    w.barrier()
     sampler = ClockSampler(local)
     sampler.start()
     lib.reset_launch_count()
-    replayed0 = eng.launches_replayed
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    launches = lib.launch_count() + (eng.launches_replayed - replayed0)   # eager launches + kernels inside replayed graphs
+    replayed0 = w.eng.launches_replayed
+    times = [w.window(args.steps) for _ in range(max(1, args.windows))]
+    launches = (lib.launch_count() + (w.eng.launches_replayed - replayed0)) // max(1, args.windows)
     clocks = sampler.result()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    total_ms = ms.item()
-    triples_done = sum(ntri_g[i % NB] for i in range(args.steps))
+    total_ms = statistics.median(times)
+    triples_done = w.triples_in(args.steps)
     value = triples_done / (total_ms / 1e3)
-    final = eng.read_stats(beta)
+    final = w.eng.read_stats(w.beta)
 
-    # ---------------- e2e: public API with HOST buffers, H2D + D2H inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        pinned = [b.host for b in dbs]
-        lay0 = dbs[0].layout
-        meta_bytes = (batch + 2 * lay0.L) * 4 if hasattr(lay0, "L") else \
-            (lay0.idx.nbytes + lay0.tok.nbytes * 3 + lay0.enc.cu.nbytes * 2 + lay0.enc.sq_off.nbytes * 2 + lay0.enc.graph.nbytes
-             + lay0.dec.graph.nbytes)
-        h2d = pinned[0][0].numel() * 8 + pinned[0][1].numel() * 8 + meta_bytes
-        def api_step(j):
-            if dec_only:
-                return model.ce_step(pinned[j][1], n_tok_global=ntok_g[j])
-            return model.elbo_step(pinned[j][0], pinned[j][1], beta, n_tok_global=ntok_g[j], batch_global=bg, graph=use_graph)
+    e2e = None if args.no_e2e else w.measure_e2e(args.steps, min(args.windows, 3))
 
-        for i in range(2):
-            api_step(i % NB).tolist()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        f0.record()
-        for i in range(args.steps):
-            j = i % NB
-            out = api_step(j)
-            out.tolist()                                    # device->host read of the step's (ce, kl)
-        f1.record()
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ems = torch.tensor([max(f0.elapsed_time(f1), wall_ms)], device=dev, dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
-        e2e = {"value": triples_done / (ems.item() / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": 8, "ms_per_step": ems.item() / args.steps,
-               "api": "kgvae.model.models.ARK.ce_step(seq_cpu)" if dec_only else
-                      "kgvae.model.models.SAIL.elbo_step(triples_cpu, seq_cpu, beta)"}
+    agg, n_prof, mode = w.kernel_profile()
+    step_ms = total_ms / args.steps
+    rows = kernel_table(agg, n_prof, step_ms, pk, args.workload if (args.model == "SAIL" and not args.dense and not args.batch) else "-")
+    roof = roofline_from(rows, pk, mode)
 
-    # ---------------- roofline pass: CUDA events around every op of the same steps (rank 0 reports)
-    eng.prof = []
-    for i in range(min(args.steps, 8)):
-        step(i, graph=False)          # events cannot be recorded inside a replayed graph: eager launches
-    agg = eng.profile_summary()
-    n_prof = min(args.steps, 8)
-    eng.prof = None
-    pk = peaks()
-    tot_ms = sum(a["ms"] for a in agg.values())
-    fam = {}
-    for tag, a in agg.items():
-        k = tag.split(":")[0]
-        f_ = fam.setdefault(k, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
-        for kk in f_:
-            f_[kk] += a[kk]
-    top = max(((k, v) for k, v in fam.items() if not k.startswith("nccl_")), key=lambda kv: kv[1]["ms"])   # our kernels only
-    name, a = top
-    if a["flops"] > 0:
-        ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
-        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
-                "peak_src": pk["src"] + " (sustained: timed inside a long step)"}
-    else:
-        ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
-        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"]}
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` captures (profiles/), where one exists
-    # for this workload: dram__bytes_read.sum + dram__bytes_write.sum
-    ncu_traffic = {("syn-types", "gru_persist_bwd"): (44.08e6 + 3.47e6, "profiles/r01_ncu_summary.md"),
-                   ("syn-types", "gru_persist_fwd"): (39.37e6 + 2.27e6, "profiles/r01_ncu_summary.md"),
-                   ("wd-articles", "gru_cluster_bwd"): (99.65e6 + 90.60e6, "profiles/r01c_ncu_summary.md"),
-                   ("wd-articles", "gru_cluster_fwd"): (54.30e6 + 225.63e6, "profiles/r01c_ncu_summary.md")}
-    if mt == "SAIL" and not args.dense and args.batch == 0 and (args.workload, name) in ncu_traffic:
-        roof["traffic"], roof["traffic_src"] = ncu_traffic[(args.workload, name)]
-    roof["share_of_step"] = a["ms"] / max(tot_ms, 1e-9)
-    roof["avg_launch_ms"] = a["ms"] / max(a["calls"], 1)
-    breakdown = {t: {"ms_per_step": v["ms"] / n_prof, "calls_per_step": v["calls"] / n_prof,
-                     "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None,
-                     "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] and v["ms"] else None}
-                 for t, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    cpu = lib_base = None
+    if rank == 0 and world == 1 and args.model == "SAIL":
+        hb = [(t, s) for t, s, _ in w.host]
+        nt = [n for _, _, n in w.host]
+        if not args.no_library_baseline:
+            from oracle.torch_cpu_port import time_cuda_library_baseline   # baseline leg: the checker's modules on cuda
+            lib_base = {}
+            for tf32 in (False, True):
+                r = time_cuda_library_baseline(w.cfg, hb, nt, beta=w.beta, steps=10, warmup=3, tf32=tf32, device=dev)
+                r["speedup_of_this_repo"] = r["ms_per_step"] / step_ms
+                lib_base["tf32" if tf32 else "fp32"] = r
+            torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            from oracle.torch_cpu_port import time_cpu_baseline   # the checker/baseline, never the product
+            cpu = time_cpu_baseline(w.cfg, hb, nt, beta=w.beta, budget_s=20.0, max_steps=8)
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and mt == "SAIL":
-        from oracle.torch_cpu_port import time_cpu_baseline   # the checker/baseline, never the product
-        cpu = time_cpu_baseline(cfg, [(t, s) for t, s, _ in host], [n for _, _, n in host], beta=beta,
-                                budget_s=20.0, max_steps=8)
+    cfg, mt, batch, bg = w.cfg, w.mt, w.batch, w.bg
+    tokens0 = w.dbs[0].layout.n_tok
+    n_params = w.n_params
+    cuda_graph = bool(w.use_graph)
+    w.close()
+
+    # ---------------- the other BASELINE workloads, same invocation (N = 1 only: keeps the multi-rank runs short)
+    also = []
+    if rank == 0 and world == 1 and not args.no_also and args.model == "SAIL" and not args.dense and not args.batch:
+        extra = [(x, 0) for x in WORKLOADS if x != args.workload] + [("wd-articles", 256)]
+        for wl, b_ in extra:
+            try:
+                o = Workload(args, wl, "SAIL", b_, False, dev, None, 1, 0, use_graph)
+                med, ts = o.measure(args.steps, args.warmup, 3)
+                ag, npf, md = o.kernel_profile(4)
+                rws = kernel_table(ag, npf, med / args.steps, pk, wl if not b_ else "-")
+                ent = {"workload": f"autoreg_{wl} SAIL", "graphs_per_gpu": o.batch, "value": o.triples_in(args.steps) / (med / 1e3),
+                       "unit": UNIT, "ms_per_step": med / args.steps, "windows_ms": ts, "steps": args.steps,
+                       "tokens_per_step": o.dbs[0].layout.n_tok, "roofline": roofline_from(rws, pk, md),
+                       "kernels": [{k: r.get(k) for k in ("name", "ms_per_step", "launches_per_step", "bound", "achieved", "unit", "frac")}
+                                   for r in rws[:8]]}
+                if o.cfg.get("use_padding"):
+                    ent["note"] = ("ragged workload: the timed steps replay CUDA graphs captured for 4 fixed batch layouts; "
+                                   "`eager_fresh` draws a NEW ragged batch every step (no graph)")
+                    from ark_b200.synthetic import DeviceBatch, synth_batch
+                    fresh = [synth_batch(o.cfg, o.batch, 9000 + i) for i in range(args.steps)]
+                    fdb = [DeviceBatch(t, s, n, dev, 9000 + i) for i, (t, s, n) in enumerate(fresh)]
+                    feps = [b.eps(o.cfg["d_latent"], dev) for b in fdb]
+
+                    def fstep(i):
+                        d = fdb[i % len(fdb)]
+                        return o.eng.train_step(d.triples, d.seq, d.layout, feps[i % len(fdb)], o.beta)
+                    for i in range(3):
+                        fstep(i)
+                    fms = statistics.median([o.window(args.steps, fstep) for _ in range(3)])
+                    ent["eager_fresh"] = {"value": sum(n for _, _, n in fresh) / (fms / 1e3), "ms_per_step": fms / args.steps}
+                    del fdb, feps
+                also.append(ent)
+                o.close()
+            except Exception as e:     # an extra workload must never take the headline line down
+                also.append({"workload": f"autoreg_{wl} SAIL", "graphs_per_gpu": b_, "error": f"{type(e).__name__}: {e}"[:300]})
 
     if rank == 0:
-        print(json.dumps({"breakdown_ms_per_step": breakdown, "sum_ms": tot_ms / n_prof}, indent=1), file=sys.stderr)
         try:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            with open(os.path.join(ROOT, "gpurun_out", f"bench_breakdown_{args.workload}_n{world}.json"), "w") as f:
-                json.dump({"breakdown": breakdown, "families": fam, "profiled_steps": n_prof}, f, indent=1)
+            with open(os.path.join(ROOT, "gpurun_out", f"bench_kernels_{args.workload}_n{world}.json"), "w") as f:
+                json.dump({"kernels": rows, "profiled_steps": n_prof, "timing": mode, "also": also}, f, indent=1)
         except OSError:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "windows_ms": times, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"autoreg_{args.workload} {mt}", "graphs_per_gpu": batch, "global_batch": bg,
                        "d_model": cfg["d_model"], "d_latent": cfg["d_latent"], "n_layers": cfg["n_layers"],
                        "vocab_size": cfg["vocab_size"], "seq_len": cfg["seq_len"], "params": n_params,
-                       "triples_per_step": triples_done / args.steps, "tokens_per_step_rank0": dbs[0].layout.n_tok,
+                       "triples_per_step": triples_done / args.steps, "tokens_per_step_rank0": tokens0,
                        "dense": bool(args.dense), "parallelism": f"dp{world}",
                        "l2": "per-step working set (params+grads+Adam state+activations) exceeds the 126 MB L2; "
-                             "no explicit flush", "gemm_backend": args.backend, "cuda_graph": bool(use_graph),
-                       "precision": "bf16 GEMM operands, fp32 accumulate/master/state"},
+                             "no explicit flush", "gemm_backend": args.backend, "cuda_graph": cuda_graph,
+                       "precision": "bf16 GEMM operands, fp32 accumulate/master/state",
+                       "timing": f"median of {len(times)} windows of {args.steps} steps"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "roofline": roof, "final_loss": {"loss": final[0], "ce": final[1], "kl": final[2]},
+            "roofline": roof, "kernels": rows[:16],
+            "final_loss": {"loss": final[0], "ce": final[1], "kl": final[2]},
         }
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if lib_base is not None:
+            line["library_baseline"] = lib_base
+        if also:
+            line["also"] = also
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -94,9 +94,13 @@ int ark_tok_scatter_add(const float* dX, const int32_t* tok, int64_t N, int64_t 
 int ark_reparam_kl_fwd(const float* heads, int64_t ld_heads, const float* eps, const int32_t* perm,
                        int64_t B, int64_t dz, int clamp_logv, float kl_scale,
                        float* z, uint16_t* z_bf16, int64_t ld_zb, float* kl_acc, void* stream);
-/* dheads [B,2dz] = [dz + bk*mu | clampmask*(0.5*dz*eps*sigma + 0.5*bk*(e^logv-1))], bk = beta*kl_scale */
+/* dheads [B,2dz] = [dz + bk*mu + dmu_ext | clampmask*(0.5*dz*eps*sigma + 0.5*bk*(e^logv-1) + dlogv_ext)],
+ * bk = beta_kl_scale * (beta_dev ? *beta_dev : 1)   (beta_dev: device scalar, so a replayed CUDA graph follows the
+ * per-epoch beta schedule of ablation_study.py:589-591).  dmu_ext / dlogv_ext (NULL or f32 [B,dz], ORIGINAL graph
+ * order like eps): upstream gradients of the mu / logv tensors SAIL.forward returns (models.py:317-320). */
 int ark_reparam_kl_bwd(const float* heads, int64_t ld_heads, const float* eps, const int32_t* perm,
                        const float* dz_in, int64_t B, int64_t dz, int clamp_logv, float beta_kl_scale,
+                       const float* beta_dev, const float* dmu_ext, const float* dlogv_ext,
                        float* dheads, uint16_t* dheads_bf16, int64_t ld_dh, void* stream);
 
 /* ---- K7: fused softmax cross-entropy forward+backward (ablation_study.py:64-69) ----

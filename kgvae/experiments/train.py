@@ -2,7 +2,12 @@
 
 Same CLI, YAML schema, epoch flow, logged keys and checkpoint dictionary as the reference trainer
 (/root/reference/kgvae/experiments/train.py:241-624), with the SAIL / ELBO branches the reference keeps in
-ablation_study.py:59-81,589-591 merged in (SURVEY.md finding 3), and underneath:
+ablation_study.py:59-81,589-591 merged in (SURVEY.md finding 3).  Kept: 1-based `epoch` in logs and checkpoints,
+`dataset_meta = {dataset, n_entities, n_relations}`, `save_every` default 10, `objective` = best posterior
+compression bits updated every `compression_log_every` epochs (`val/compression_*` keys), the final evaluation on
+the validation (and, with `use_test_for_final_eval`, test) split logged as `final_val/*` / `final_test/*`.
+NOT reproduced (needs the `intelligraphs` verifiers, which cannot be installed here): the `verify_every` semantic
+validity / novelty evaluation of generated graphs and its `verification/*` keys.  Underneath:
 
   * the train step is the fused ark_b200 ELBO engine (no autograd graph, no [B,L,V] probabilities);
   * the optimiser is the fused flat Adam (same `optimizer_state_dict` layout);
@@ -28,7 +33,8 @@ import yaml
 from ark_b200.optim import FusedAdam
 from ark_b200.synthetic import DATASET_SHAPES
 from kgvae.model.models import ARK, SAIL
-from kgvae.model.utils import GraphSeqDataset, build_batch, canonical_graph_string, ints_to_labels, seq_to_triples
+from kgvae.model.utils import (GraphSeqDataset, build_batch, canonical_graph_string, canonicalize, ints_to_labels,
+                               seq_to_triples)
 
 SPECIAL = {"PAD": 0, "BOS": 1, "EOS": 2}
 
@@ -108,7 +114,10 @@ class BatchLoader:
     """
 
     def __init__(self, graphs, vocab, batch_size, rank=0, world=1, shuffle=False, drop_last=True, permute=False,
-                 seed=0):
+                 seed=0, triple_order="keep", i2e=None, i2r=None):
+        if triple_order != "keep":       # reference: GraphSeqDataset canonicalises every graph (utils.py:96-99,115)
+            graphs = [canonicalize(g, i2e, i2r, triple_order) for g in graphs]
+        self.graphs = graphs             # (posterior_bits iterates a GraphSeqDataset over the same canonical graphs)
         self.v, self.B, self.rank, self.world = vocab, batch_size, rank, world
         self.shuffle, self.drop_last, self.permute, self.epoch, self.seed = shuffle, drop_last, permute, 0, seed
         self.G = len(graphs)
@@ -216,6 +225,15 @@ def validate(model, dataloader, config, device, b=1.0):
     return ce + b * kl, ce, kl
 
 
+@torch.no_grad()
+def posterior_compression(model, dataset, config, device):
+    """Posterior compression bits of `sample_frac` of a split (reference: validate(compute_compression=True),
+    ablation_study.py:151-186 -> SAIL/ARK.posterior_bits, models.py:218-260,488-520)."""
+    model.eval()
+    return model.posterior_bits(dataset, device, pad_id=SPECIAL["PAD"], sample_frac=float(config.get("sample_frac", 0.1)),
+                                desc="Posterior compression")
+
+
 def cosine_lr(base, epoch, t_max, eta_min):
     return eta_min + (base - eta_min) * (1 + math.cos(math.pi * epoch / t_max)) / 2
 
@@ -244,13 +262,18 @@ def main(argv=None):
     log = _Log(args.wandb_project, args.wandb_entity or os.getenv("WANDB_ENTITY"), config,
                config.get("experiment_name", "ARK_experiment"), rank)
     config.update(log.config)                                   # sweep overrides (reference train.py:273)
+    if world > 1:       # wandb runs on rank 0 only: every rank must train with rank 0's effective hyper-parameters
+        box = [config]
+        torch.distributed.broadcast_object_list(box, src=0)
+        config = box[0]
     config["learning_rate"] = float(config.get("learning_rate", 1e-3))
     run_dir = os.path.join(args.checkpoint_dir, str(log.run.id))
     if rank == 0:
         os.makedirs(run_dir, exist_ok=True)
         with open(os.path.join(run_dir, "effective_config.yaml"), "w") as f:
             yaml.safe_dump(config, f)
-    log.log({"objective": 1e12})
+    best_comp_bits = 1e12
+    log.log({"objective": best_comp_bits})
     if config.get("use_test_for_final_eval", False) and rank == 0:
         warnings.warn("Test set evaluation ENABLED! Only use for final evaluation, NOT for hyperparameter tuning!",
                       UserWarning, stacklevel=2)
@@ -275,17 +298,27 @@ def main(argv=None):
                    "ENT_BASE": ent_base, "REL_BASE": rel_base})
 
     B = config["batch_size"]
+    order = config.get("triple_order", "keep")
     train_loader = BatchLoader(train_g, vocab, B, rank, world, shuffle=config["shuffle_train"], drop_last=True,
-                               permute=config.get("permute_triples", False))
-    val_loader = BatchLoader(val_g, vocab, B, 0, 1, drop_last=False)
+                               permute=config.get("permute_triples", False), triple_order=order, i2e=i2e, i2r=i2r)
+    val_loader = BatchLoader(val_g, vocab, B, 0, 1, drop_last=False, triple_order=order, i2e=i2e, i2r=i2r)
+    test_loader = BatchLoader(test_g, vocab, B, 0, 1, drop_last=False, triple_order=order, i2e=i2e, i2r=i2r)
+
+    def seq_dataset(loader):     # what the reference hands to posterior_bits: dataloader.dataset (ablation_study.py:151-157)
+        return GraphSeqDataset(loader.graphs, i2e, i2r, triple_order="keep", permute=False, use_padding=use_padding,
+                               pad_eid=pad_eid, pad_rid=pad_rid, max_triples=max_edges, special_tokens=SPECIAL,
+                               ent_base=ent_base, rel_base=rel_base, seq_len=vocab["seq_len"])
     if rank == 0:
         print(f"Dataset: {config['dataset']}  Entities: {n_ent}, Relations: {n_rel}")
         print(f"Train batches: {len(train_loader)}, Val batches: {len(val_loader)}  world={world}")
 
-    torch.manual_seed(0)
+    torch.manual_seed(0)                                       # identical initial weights on every rank
     model = (ARK if model_type in ("ARK", "t-ARK") else SAIL)(config).to(device)
+    # ... but independent noise per rank: eps (torch's CUDA generator) and the Philox dropout stream.  With one common
+    # seed every rank would draw the SAME eps / masks for its different shard, which no single-process run does
+    torch.manual_seed(1 + rank)
     optimizer = FusedAdam(model, lr=config["learning_rate"], dist_group=group,
-                          bucket_mb=float(config.get("ddp_bucket_mb", 32)))
+                          bucket_mb=float(config.get("ddp_bucket_mb", 32)), seed=rank)
     scheduler = None
     if config.get("lr_scheduler", False):
         scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=config["num_epochs"],
@@ -303,25 +336,42 @@ def main(argv=None):
         if rank == 0:
             print(f"\nEpoch {epoch + 1}/{config['num_epochs']}  loss {tr[0]:.4f} ce {tr[1]:.4f} kl {tr[2]:.4f}  "
                   f"val {va[0]:.4f}  {n_tri / dt:,.0f} triples/s")
-            log.log({"epoch": epoch, "train/loss": tr[0], "train/reconstruction_loss": tr[1], "train/kl_loss": tr[2],
+            if (epoch + 1) % int(config.get("compression_log_every", 5)) == 0:     # ablation_study.py:595-621
+                stats = posterior_compression(model, seq_dataset(val_loader), config, device)
+                log.log({"val/compression_bits": stats["avg_total_bits"], "val/compression_kl_bits": stats["avg_kl_bits"],
+                         "val/compression_edge_bits": stats["avg_ar_bits"], "val/compression_entity_bits": stats["avg_ar_bits"]})
+                if math.isfinite(stats["avg_total_bits"]) and stats["avg_total_bits"] < best_comp_bits:
+                    best_comp_bits = stats["avg_total_bits"]
+            log.log({"objective": best_comp_bits})
+            log.log({"epoch": epoch + 1, "train/loss": tr[0], "train/reconstruction_loss": tr[1], "train/kl_loss": tr[2],
                      "val/loss": va[0], "val/reconstruction_loss": va[1], "val/kl_loss": va[2], "beta": b,
                      "learning_rate": optimizer.param_groups[0]["lr"], "triples_per_sec": n_tri / dt,
                      "step_ms": 1e3 * dt / max(len(train_loader), 1)})
         if scheduler is not None:
             scheduler.step()
         if rank == 0:
-            ckpt = {"epoch": epoch, "model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+            ckpt = {"epoch": epoch + 1, "model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
                     "optimizer_state_dict": optimizer.state_dict(),
                     "scheduler_state_dict": scheduler.state_dict() if scheduler else None, "val_loss": va[0],
                     "config": config, "vocabs": {"e2i": e2i, "i2e": i2e, "r2i": r2i, "i2r": i2r},
-                    "dataset_meta": {"min_edges": min_edges, "max_edges": max_edges}}
+                    "dataset_meta": {"dataset": config["dataset"], "n_entities": len(i2e), "n_relations": len(i2r)}}
             tag = f"{config['dataset']}_{model_type}"
             if va[0] < best_val:
                 best_val = va[0]
                 torch.save(ckpt, os.path.join(run_dir, f"{tag}_best_model.pt"), _use_new_zipfile_serialization=False)
-            if (epoch + 1) % int(config.get("save_every", 50)) == 0:
+            if (epoch + 1) % int(config.get("save_every", 10)) == 0:
                 torch.save(ckpt, os.path.join(run_dir, f"{tag}_checkpoint_epoch_{epoch + 1}.pt"),
                            _use_new_zipfile_serialization=False)
+    if rank == 0:     # final evaluation (reference final_validation, ablation_study.py:190-346, minus the intelligraphs parts)
+        final = {}
+        splits = [("final_val", val_loader)] + ([("final_test", test_loader)] if config.get("use_test_for_final_eval") else [])
+        for tag, loader in splits:
+            fl = validate(model, loader, config, device, 1.0)
+            stats = posterior_compression(model, seq_dataset(loader), config, device)
+            final.update({f"{tag}/loss": fl[0], f"{tag}/reconstruction_loss": fl[1], f"{tag}/kl_loss": fl[2],
+                          f"{tag}/compression_bits": stats["avg_total_bits"], f"{tag}/compression_kl_bits": stats["avg_kl_bits"],
+                          f"{tag}/compression_ar_bits": stats["avg_ar_bits"]})
+        log.log(final)
     log.finish()
     if world > 1:
         torch.distributed.destroy_process_group()

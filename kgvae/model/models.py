@@ -83,10 +83,13 @@ class AutoRegEncoderMLP(nn.Module):
                 g = _linear_f32(g, m, ops.EPI_GELU)
         return _linear_f32(g, self.mu), _linear_f32(g, self.logv).clamp_(-10, 10)
 
+    eps_hook = None     # tests: callable(mu) -> eps replacing the randn_like draw (CPU-generator fixtures)
+
     @torch.no_grad()
     def forward(self, triples):
         mu, logv = self.encode_stats(triples)
-        z = mu + torch.randn_like(mu) * torch.exp(0.5 * logv)   # same RNG call as the reference (models.py:63)
+        eps = torch.randn_like(mu) if self.eps_hook is None else self.eps_hook(mu)   # the reference's RNG call (models.py:63)
+        z = mu + eps * torch.exp(0.5 * logv)
         return z, mu, logv
 
 
@@ -195,6 +198,67 @@ class AutoRegDecoder(nn.Module):
         if self.training and self._owner().engine().p_drop > 0:
             raise RuntimeError("dec() is the fp32 inference path; train with SAIL.elbo_step (dropout lives there)")
         return self._owner().engine().decode_logits(z, tgt)
+
+
+
+class _ForwardFn(torch.autograd.Function):
+    """Differentiable ``SAIL.forward`` / ``ARK.forward`` (reference models.py:317-320,395-405) on the fused engine.
+
+    The reference trains by ``logits, mu, logv = model(triples, seq_in); loss = CE + b*KL; loss.backward()``
+    (ablation_study.py:63-75).  This node makes that loop work unmodified on the CUDA kernels: forward runs the
+    engine's bf16 tensor-core path over ALL B x L positions (PAD positions included: the reference returns logits
+    for them too) and returns fp32 ``[B, L, V]`` logits; backward receives d(loss)/d(logits, mu, logv), writes the
+    logit gradient into the engine's packed buffer and resumes the engine's hand-written backward pass; the
+    parameter gradients come back through autograd (``p.grad`` accumulation semantics of torch are kept).
+    The materialised fp32 logits make this the COMPATIBILITY path (the fused ``elbo_step`` never builds them)."""
+
+    @staticmethod
+    def forward(ctx, model, triples, seq_in, eps, *params):
+        from ark_b200.layout import _uniform_layout
+        eng = model.engine()
+        eng.refresh_shadow()                # a torch optimiser may have stepped the fp32 masters since the last call
+        dev = eng.device
+        B, L = seq_in.shape
+        V, ldv = eng.V, eng.ldv
+        seq = torch.cat([seq_in.to(dev), seq_in.new_zeros(B, 1).to(dev)], dim=1).contiguous()   # engine: inputs = seq[:, :-1]
+        lay = _uniform_layout(B, L).to(dev)
+        tri = None if triples is None else triples.to(dev).contiguous()
+        gen = eng._fb_gen(tri, seq, lay, eps, 0.0, train=True, dropout=model.training, autograd=True)
+        st = next(gen)
+        ctx.gen, ctx.st, ctx.shape, ctx.eng = gen, st, (B, L, V, ldv), eng
+        ctx.names = [n for n, _ in model.named_parameters()]
+        logits = st["logits"].view(L, B, ldv)[:, :, :V].transpose(0, 1).float().contiguous()
+        if st["heads"] is None:
+            return (logits,)
+        dz = eng.dz
+        heads = st["heads"]
+        return logits, heads[:, :dz].clone(), heads[:, dz:2 * dz].clamp(-10.0, 10.0)
+
+    @staticmethod
+    def backward(ctx, dlogits, dmu=None, dlogv=None):
+        eng, st = ctx.eng, ctx.st
+        B, L, V, ldv = ctx.shape
+        buf = st["logits"].view(L, B, ldv)
+        if dlogits is None:
+            buf.zero_()
+        else:
+            buf[:, :, :V].copy_(dlogits.transpose(0, 1))
+            if ldv > V:
+                buf[:, :, V:].zero_()
+        f = eng.flat
+        keep, f.grad = f.grad, torch.empty_like(f.grad)      # a private buffer: p.grad (a view of flat.grad) keeps torch's
+        try:                                                 # accumulate-into-.grad semantics
+            try:
+                ctx.gen.send({"dmu": None if dmu is None else dmu.contiguous().float(),
+                              "dlogv": None if dlogv is None else dlogv.contiguous().float()})
+            except StopIteration:
+                pass
+            eng._sync_grads()
+            grads = tuple(f.g(n) for n in ctx.names)
+        finally:
+            f.grad = keep
+            ctx.gen = ctx.st = None
+        return (None, None, None, None) + grads
 
 
 class _EngineMixin:
@@ -306,7 +370,20 @@ class SAIL(_EngineMixin, nn.Module):
     def kl_mean(self, mu, logv):
         return -0.5 * torch.mean(1 + logv - mu.pow(2) - logv.exp())
 
+    eps_hook = None     # tests: callable(B, dz, device) -> eps, replacing the randn draw of the differentiable forward
+
     def forward(self, triples, seq_in):
+        """(logits [B, L, V], mu, logv) — reference models.py:317-320.  With autograd enabled this is a differentiable
+        node on the fused engine (`_ForwardFn`: the reference's own loop `model(...)`, `loss.backward()`,
+        `optimizer.step()` trains through it); under `torch.no_grad()` it is the fp32 inference path whose integer
+        outputs (beam search, generation) match the reference bit for bit."""
+        if torch.is_grad_enabled() and self.config["model_type"] == "SAIL" and any(p.requires_grad for p in self.parameters()):
+            _need_cuda(triples, "forward")
+            B, dz = triples.shape[0], self.config["d_latent"]
+            dev = self.engine().device
+            # the reference's draw: torch.randn_like(mu), first RNG call of the step (models.py:63)
+            eps = self.eps_hook(B, dz, dev) if self.eps_hook is not None else torch.randn(B, dz, device=dev)
+            return _ForwardFn.apply(self, triples, seq_in, eps.contiguous(), *self.parameters())
         z, mu, logv = self.enc(triples)
         return self.dec(z, seq_in), mu, logv
 
@@ -463,8 +540,13 @@ class ARK(_EngineMixin, nn.Module):
         self._init_engine_slot()
 
     def forward(self, triples_or_seq, seq_in=None):
-        """forward(seq) or forward(triples, seq) — triples are ignored (reference models.py:395-405)."""
-        return self.dec(triples_or_seq if seq_in is None else seq_in)
+        """forward(seq) or forward(triples, seq) — triples are ignored (reference models.py:395-405).  Differentiable
+        on the fused engine when autograd is enabled (GRU model), fp32 inference path under torch.no_grad()."""
+        seq = triples_or_seq if seq_in is None else seq_in
+        if torch.is_grad_enabled() and self.config["model_type"] == "ARK" and any(p.requires_grad for p in self.parameters()):
+            _need_cuda(seq, "forward")
+            return _ForwardFn.apply(self, None, seq, None, *self.parameters())[0]
+        return self.dec(seq)
 
     def ce_backward(self, seq, layout: PackedLayout = None, n_tok_global=None):
         """Fused CE forward + backward over packed rows (reference train step: train.py:42-58)."""

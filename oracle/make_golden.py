@@ -315,7 +315,90 @@ def ark_golden():
     ark_case("wd", n_ent=23, n_rel=4, lo=1, hi=6, use_padding=True, d=16, nl=2, B=6, seed=12)
 
 
+def eval_golden():
+    """Evaluation-time paths of the reference: `posterior_bits` / `bits_per_sequence`
+    (models.py:202-260, 473-520) and SAMPLED `ARK.generate` (temperature / top-k / top-p, models.py:408-471).
+    The reference samples with torch.multinomial on the CPU generator, which no CUDA run can replay; the fixture
+    therefore records the FILTERED distributions the reference hands to torch.multinomial (what the filtering code
+    computes) with multinomial replaced by argmax for the duration of the call, so the token path is deterministic."""
+    arrays, meta = {}, {}
+    # ---- SAIL posterior bits (padded, ragged)
+    rng = np.random.default_rng(31)
+    lay = layout_from_reference_rules(23, 4, 6, True)
+    graphs = random_graphs(rng, 7, 23, 4, 1, 6)
+    cfg = dict(lay, model_type="SAIL", d_model=32, d_latent=8, n_heads=2, n_layers=2, dec_dropout=0.0, tie_weights=True)
+    ds = ref_utils.GraphSeqDataset(graphs=graphs, i2e=None, i2r=None, triple_order="keep", permute=False, use_padding=True,
+                                   pad_eid=lay["pad_eid"], pad_rid=lay["pad_rid"], max_triples=lay["max_edges"],
+                                   special_tokens=lay["special_tokens"], ent_base=lay["ENT_BASE"], rel_base=lay["REL_BASE"],
+                                   seq_len=lay["seq_len"])
+    torch.manual_seed(31)
+    model = ref_models.SAIL(cfg).eval()
+    torch.manual_seed(77)
+    draws, real_randn_like = [], torch.randn_like
+
+    def recording_randn_like(t, *a, **k):       # record the reference's own eps draws (models.py:63), one per graph
+        e = real_randn_like(t, *a, **k)
+        draws.append(e.detach().clone())
+        return e
+    torch.randn_like = recording_randn_like
+    try:
+        stats = model.posterior_bits(ds, torch.device("cpu"), pad_id=0, sample_frac=1.0)
+    finally:
+        torch.randn_like = real_randn_like
+    assert len(draws) == len(ds)
+    arrays["sail_eps"] = torch.cat(draws, 0).numpy()
+    for k, v in model.state_dict().items():
+        arrays["sail_param::" + k] = v.detach().numpy().copy()
+    arrays["sail_ar_bits"] = np.asarray([r["ar_bits"] for r in stats["records"]])
+    arrays["sail_kl_bits"] = np.asarray([r["kl_bits"] for r in stats["records"]])
+    z1 = torch.from_numpy(arrays["sail_eps"][:1])
+    arrays["sail_bits_seq0_z"] = np.float64(model.bits_per_sequence(ds[0][1], z1, 0))
+    meta["sail"] = {"cfg": cfg, "graphs": graphs, "stats": {k: v for k, v in stats.items() if k != "records"}}
+    # ---- ARK posterior bits + sampled generation
+    lay2 = layout_from_reference_rules(23, 4, 5, True)
+    graphs2 = random_graphs(rng, 5, 23, 4, 1, 5)
+    cfg2 = dict(lay2, model_type="ARK", d_model=32, d_latent=4, n_heads=2, n_layers=2, dec_dropout=0.0, tie_weights=True)
+    ds2 = ref_utils.GraphSeqDataset(graphs=graphs2, i2e=None, i2r=None, triple_order="keep", permute=False, use_padding=True,
+                                    pad_eid=lay2["pad_eid"], pad_rid=lay2["pad_rid"], max_triples=lay2["max_edges"],
+                                    special_tokens=lay2["special_tokens"], ent_base=lay2["ENT_BASE"], rel_base=lay2["REL_BASE"],
+                                    seq_len=lay2["seq_len"])
+    torch.manual_seed(32)
+    ark = ref_models.ARK(cfg2).eval()
+    st2 = ark.posterior_bits(ds2, torch.device("cpu"), pad_id=0, sample_frac=1.0)
+    for k, v in ark.state_dict().items():
+        arrays["ark_param::" + k] = v.detach().numpy().copy()
+    arrays["ark_ar_bits"] = np.asarray([r["ar_bits"] for r in st2["records"]])
+    meta["ark"] = {"cfg": cfg2, "graphs": graphs2, "stats": {k: v for k, v in st2.items() if k != "records"}}
+    real_multinomial = torch.multinomial
+    gens = []
+    for gi, kw in enumerate([dict(temperature=1.0, top_p=0.9, top_k=0), dict(temperature=0.7, top_p=0.0, top_k=5),
+                             dict(temperature=1.3, top_p=0.8, top_k=7), dict(temperature=1.0, top_p=0.0, top_k=0)]):
+        seen = []
+
+        def fake(probs, n, *a, **k):
+            seen.append(probs.detach().clone().reshape(-1, probs.shape[-1]))
+            return probs.argmax(dim=-1, keepdim=True)
+        torch.multinomial = fake
+        try:
+            out = ark.generate(lay2["seq_len"], lay2["special_tokens"], batch_size=3, sample=True, **kw)
+        finally:
+            torch.multinomial = real_multinomial
+        arrays[f"gen{gi}_seq"] = out.numpy()
+        # top-p: one call per batch row (sorted probabilities); otherwise one call per step ([B, V])
+        arrays[f"gen{gi}_probs"] = torch.cat(seen, 0).numpy()
+        gens.append(dict(kw, n_calls=len(seen)))
+    meta["gen"] = gens
+    np.savez_compressed(os.path.join(OUT, "eval_bits.npz"), **arrays)
+    with open(os.path.join(OUT, "eval_bits.json"), "w") as f:
+        json.dump(meta, f)
+    print(f"[golden] eval_bits: sail avg_total={stats['avg_total_bits']:.4f} ark avg_total={st2['avg_total_bits']:.4f} "
+          f"gen calls {[g['n_calls'] for g in gens]}")
+
+
 if __name__ == "__main__":
+    if "--eval-only" in sys.argv:
+        eval_golden()
+        sys.exit(0)
     if "--ark-only" in sys.argv:
         ark_golden()
         sys.exit(0)
@@ -337,3 +420,4 @@ if __name__ == "__main__":
     ark_golden()
     tsail_golden()
     tark_golden()
+    eval_golden()

@@ -102,3 +102,53 @@ def time_cpu_baseline(cfg, batches, n_triples, beta=0.5, lr=1e-3, budget_s=20.0,
     return {"value": done_triples / dt, "unit": "triples/s", "cores": threads, "kind": "port",
             "sample": f"{steps} full train steps (fwd+bwd+Adam, fp32, train mode) of the same workload batches after 1 "
                       f"warm-up, {dt:.1f} s wall", "s_per_step": dt / steps, "steps": steps}
+
+
+def time_cuda_library_baseline(cfg, batches, n_triples, beta=0.5, lr=1e-3, steps=20, warmup=5, tf32=False, device="cuda"):
+    """The SAME restated reference modules on device='cuda' (what the reference does when a GPU is present,
+    kgvae/experiments/ablation_study.py:392): torch eager -> cuDNN RNN, cuBLASLt, ATen embedding / softmax kernels,
+    torch.optim.Adam.  This is the library-path bar of SURVEY.md §2.3 / §8(d), CUDA-event timed over whole train steps
+    (zero_grad, forward, CE + beta*KL, backward, Adam, three .item() read-backs per step exactly like
+    ablation_study.py:59-80), inputs already resident on the device."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    try:
+        torch.manual_seed(0)
+        model = CpuSail(cfg).to(device)
+        opt = torch.optim.Adam(model.parameters(), lr=lr)
+        dev_batches = [(t.to(device), s.to(device)) for t, s in batches]
+        for i in range(warmup):
+            train_steps(model, opt, dev_batches[i % len(dev_batches):i % len(dev_batches) + 1], beta)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        done = 0
+        e0.record()
+        for i in range(steps):
+            j = i % len(dev_batches)
+            train_steps(model, opt, dev_batches[j:j + 1], beta)
+            done += n_triples[j]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return {"value": done / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms / steps, "steps": steps,
+            "precision": "tf32" if tf32 else "fp32", "kind": "port on cuda (torch eager: cuDNN GRU, cuBLASLt, ATen)"}
+
+
+@torch.no_grad()
+def posterior_bits_port(model: CpuSail, triples, seq, eps):
+    """(ar_bits, kl_bits) of ONE graph: the reference's posterior_bits record (kgvae/model/models.py:218-260) with
+    bits_per_sequence (:202-213) restated as a single teacher-forced pass — the GRU decoder is causal, so the logits
+    of position t under the full prefix equal the last-position logits of the reference's prefix [:t] loop."""
+    import math
+    model.eval()
+    z, mu, logv = model.encode(triples[None], eps[None])
+    n = int((seq[1:] != 0).long().cumprod(0).sum())
+    ar = 0.0
+    if n:
+        logp = F.log_softmax(model.decode(z, seq[None, :n]), dim=-1)[0]
+        ar = float(-logp[torch.arange(n), seq[1:n + 1]].sum() / math.log(2))
+    kl = float(-0.5 * (1 + logv - mu.square() - logv.exp()).sum() / math.log(2))
+    return ar, kl
