@@ -38,6 +38,7 @@
 #include "philox.cuh"
 #include <string.h>
 #include <stdlib.h>
+extern "C" char** environ;
 
 namespace ark {
 
@@ -1129,7 +1130,6 @@ static int launch_cluster(Kern kern, const Params& prm, dim3 grid, int cs, int s
     // Nsight Compute's injection does not survive a cooperative cluster launch (the profiler exits with rc 9 and
     // takes the process with it, so there is no error to retry on): recognise a profiled process by the variables
     // its launcher exports
-    extern char** environ;
     for (char** e = environ; !ev && e && *e; ++e)
       if (!strncmp(*e, "NV_NSIGHT", 9) || !strncmp(*e, "NV_COMPUTE_PROFILER", 19) || !strncmp(*e, "CUDA_INJECTION64_PATH", 21) ||
           !strncmp(*e, "NVTX_INJECTION64_PATH", 21))

@@ -29,6 +29,12 @@ namespace ark {
 constexpr int GP_BM = 128;
 constexpr int GP_BK = 64;
 constexpr int GP_A_BYTES = GP_BM * GP_BK * 2;  // 16 KB per ring stage
+// 8 epilogue warps: warps 2..5 drain the 4 TMEM lane quadrants into shared memory, then ALL 256 threads share the
+// (row, 4-unit group) work items of the gate math (measured at d = 1024: the math + stores of 4 items per thread took
+// 3 400 of the 14 400 cycles of a forward step with 128 threads)
+constexpr int GP_EPI = 256;
+constexpr int GP_THREADS = 64 + GP_EPI;
+__device__ __forceinline__ void gp_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct GruPersistFwdParams {
   const int32_t* bt;
@@ -41,6 +47,7 @@ struct GruPersistFwdParams {
   uint16_t* hp_b;      // [N, d] bf16 packed h_prev rows (block 0 pre-filled with bf16(h0)); written for t+1
   uint16_t* y_b;       // [N, d] bf16 outputs
   uint16_t *r, *z, *n, *ghn;  // [N, d] bf16 saved gates (may all be null)
+  long long* dbg;      // ARK_GRU_PERSIST_DBG: clock64 timeline of CTA (0,0), steps 2..5 ([4][8] words), else NULL
 };
 
 struct GruPersistBwdParams {
@@ -53,7 +60,13 @@ struct GruPersistBwdParams {
   uint16_t *dgi_b, *dgh_b;                  // [N, 3d] bf16 (dgh_b is also the A operand of the next step)
   float* dh0;                               // [bt[0], d]
   int dh0_accumulate;
+  long long* dbg;                           // as in the forward parameters ([4][8] words behind the forward's)
 };
+
+// debug timeline: event e of step t (CTA (0,0) only, 4 steps starting at step 2 of the kernel's own iteration order)
+__device__ __forceinline__ void gp_dbg(long long* dbg, int it, int e) {
+  if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && it >= 2 && it < 6) dbg[(it - 2) * 8 + e] = clock64();
+}
 
 template <int DJ, int STAGES>
 struct GpSmem {
@@ -65,7 +78,7 @@ struct GpSmem {
 // forward
 // =====================================================================================================
 template <int DJ, int STAGES, int CS>
-__global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmW,
                                                                  const GruPersistFwdParams p) {
   constexpr int NROWS = 3 * DJ;  // UMMA N
@@ -124,6 +137,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
       for (int t = 0; t < L; ++t) {
         if (m0 >= p.bt[t]) break;
         if (t > 0) wait_counter(p.sync + bi, t * ns);   // every slice of h_{t-1} is in global memory
+        gp_dbg(p.dbg, t, 0);
         asm volatile("fence.proxy.async;" ::: "memory");
         const int row0 = p.off[t] + m0;
         for (int kc = 0; kc < nkc; ++kc, ++it) {
@@ -134,6 +148,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
           else ptx::tma_load_2d_mc(a_sm + s * GP_A_BYTES + crank * (MC_ROWS * 128), &tmA, &full_bar[s], kc * GP_BK,
                                    row0 + (int)crank * MC_ROWS, MC_MASK);
         }
+        gp_dbg(p.dbg, t, 1);
       }
     }
   } else if (warp == 1) {
@@ -147,6 +162,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
         for (int kc = 0; kc < nkc; ++kc, ++it) {
           const int s = it % STAGES;
           ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if (kc == 0) gp_dbg(p.dbg, t, 2);
           ptx::tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < GP_BK / 16; ++kk) {
@@ -158,6 +174,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
           else ptx::umma_commit_mc(&empty_bar[s], MC_MASK);
         }
         ptx::umma_commit(tmem_full_bar);
+        gp_dbg(p.dbg, t, 3);
       }
     }
   } else {
@@ -168,26 +185,28 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
     // recurrent state of its 4 units stays in registers.  gi for step t is fetched BEFORE waiting for the
     // MMA of step t (it does not depend on h).
     constexpr int G = DJ / 4;                    // groups per row
+    constexpr int IT = G * GP_BM / GP_EPI;       // work items per thread
     const int q = warp & 3;
-    const int tid = threadIdx.x - 64;            // 0..127
+    const bool drainer = warp < 6;               // warps 2..5 own the TMEM lane quadrants 2,3,0,1
+    const int tid = threadIdx.x - 64;            // 0..255
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int64_t d3 = 3 * (int64_t)d;
-    float hreg[G][4];
+    float hreg[IT][4];
     const int bt0 = p.bt[0];
 #pragma unroll
-    for (int i = 0; i < G; ++i) {
-      const int e = tid + 128 * i, bl = e / G, j = j0 + (e % G) * 4;
+    for (int i = 0; i < IT; ++i) {
+      const int e = tid + GP_EPI * i, bl = e / G, j = j0 + (e % G) * 4;
       const int b = m0 + bl;
       const float4 hv = (b < bt0) ? *reinterpret_cast<const float4*>(p.h0 + (int64_t)b * d + j) : make_float4(0, 0, 0, 0);
       hreg[i][0] = hv.x; hreg[i][1] = hv.y; hreg[i][2] = hv.z; hreg[i][3] = hv.w;
     }
-    float4 gpre[G][3];
+    float4 gpre[IT][3];
     auto prefetch_gi = [&](int t) {
       const int Bt = p.bt[t];
       const int64_t base = (int64_t)p.off[t] + m0;
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const int e = tid + 128 * i, bl = e / G, j = j0 + (e % G) * 4;
+      for (int i = 0; i < IT; ++i) {
+        const int e = tid + GP_EPI * i, bl = e / G, j = j0 + (e % G) * 4;
         if (m0 + bl < Bt) {
           const float* gp = p.gi + (base + bl) * d3 + j;
           gpre[i][0] = *reinterpret_cast<const float4*>(gp);
@@ -204,8 +223,9 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
       const int64_t base = (int64_t)p.off[t] + m0;
       const int64_t base_n = (t + 1 < L) ? (int64_t)p.off[t + 1] + m0 : 0;
       ptx::mbar_wait(tmem_full_bar, t & 1);
+      if (tid == 0) gp_dbg(p.dbg, t, 4);
       ptx::tc_fence_after();
-      if (m0 + q * 32 < Bt) {                     // warp-uniform: skip lane quadrants without live rows
+      if (drainer && m0 + q * 32 < Bt) {          // warp-uniform: skip lane quadrants without live rows
         float* dst = acc_sm + (q * 32 + lane) * ACC_LD;
 #pragma unroll
         for (int c = 0; c < NROWS; c += 16) {
@@ -217,10 +237,11 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
         }
       }
       ptx::tc_fence_before();
-      epi_bar_sync();
+      gp_bar_sync();
+      if (tid == 0) gp_dbg(p.dbg, t, 5);
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const int e = tid + 128 * i, bl = e / G, jl = (e % G) * 4;
+      for (int i = 0; i < IT; ++i) {
+        const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
         const int b = m0 + bl;
         if (b < Bt) {
           const float* ap = acc_sm + bl * ACC_LD + jl;
@@ -251,8 +272,10 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
           }
         }
       }
-      epi_bar_sync();                             // all stores of the tile issued (and acc_sm free again)
+      gp_bar_sync();                             // all stores of the tile issued (and acc_sm free again)
+      if (tid == 0) gp_dbg(p.dbg, t, 6);
       if (tid == 0) red_release_add(p.sync + bi, 1);   // release: cumulative over the barrier above
+      if (tid == 0) gp_dbg(p.dbg, t, 7);
       if (t + 1 < L && m0 < Bn) prefetch_gi(t + 1);
     }
   }
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_fwd_kernel(const __grid_co
 // backward through time
 // =====================================================================================================
 template <int DJ, int STAGES, int CS>
-__global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmW,
                                                                  const GruPersistBwdParams p) {
   constexpr int NROWS = DJ;  // UMMA N
@@ -329,6 +352,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
         if (!tile_active(t)) continue;
         if (has_mma(t)) {
           wait_counter(p.sync + bi, done * ns);   // every slice of dgh_{t+1} is in global memory
+          gp_dbg(p.dbg, done, 0);
           asm volatile("fence.proxy.async;" ::: "memory");
           const int row0 = p.off[t + 1] + m0;
           for (int kc = 0; kc < nkc; ++kc, ++it) {
@@ -339,6 +363,7 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
             else ptx::tma_load_2d_mc(a_sm + s * GP_A_BYTES + crank * (MC_ROWS * 128), &tmA, &full_bar[s], kc * GP_BK,
                                      row0 + (int)crank * MC_ROWS, MC_MASK);
           }
+          gp_dbg(p.dbg, done, 1);
         }
         ++done;
       }
@@ -348,12 +373,14 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
       constexpr uint32_t idesc = ptx::make_idesc_bf16(GP_BM, NROWS, 0, 0);
       ptx::mbar_wait(w_bar, 0);
       const uint32_t w_addr = ptx::smem_u32(w_sm), a_addr0 = ptx::smem_u32(a_sm);
-      int it = 0;
+      int it = 0, nm = 0;
       for (int t = L - 1; t >= -1; --t) {
         if (!tile_active(t) || !has_mma(t)) continue;
+        ++nm;
         for (int kc = 0; kc < nkc; ++kc, ++it) {
           const int s = it % STAGES;
           ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if (kc == 0) gp_dbg(p.dbg, nm, 2);
           ptx::tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < GP_BK / 16; ++kk) {
@@ -365,29 +392,32 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
           else ptx::umma_commit_mc(&empty_bar[s], MC_MASK);
         }
         ptx::umma_commit(tmem_full_bar);
+        gp_dbg(p.dbg, nm, 3);
       }
     }
   } else {
     // same two-phase epilogue as the forward kernel: TMEM -> smem, then (row, 4-unit group) work items
     // spread over the 128 threads; dy and the saved gates of step t are fetched BEFORE the MMA wait.
     constexpr int G = DJ / 4;
+    constexpr int IT = G * GP_BM / GP_EPI;       // work items per thread
     const int q = warp & 3;
+    const bool drainer = warp < 6;               // warps 2..5 own the TMEM lane quadrants 2,3,0,1
     const int tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int64_t d3 = 3 * (int64_t)d;
-    float carry[G][4];   // dh_{t+1} * z_{t+1}: the direct path into h_t (valid for rows of step t+1)
+    float carry[IT][4];   // dh_{t+1} * z_{t+1}: the direct path into h_t (valid for rows of step t+1)
 #pragma unroll
-    for (int i = 0; i < G; ++i)
+    for (int i = 0; i < IT; ++i)
 #pragma unroll
       for (int k = 0; k < 4; ++k) carry[i][k] = 0.f;
-    float4 dyp[G];
-    uint2 sp[G][5];
+    float4 dyp[IT];
+    uint2 sp[IT][5];
     auto prefetch = [&](int t) {
       const int Bt = p.bt[t];
       const int64_t base = (int64_t)p.off[t] + m0;
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const int e = tid + 128 * i, bl = e / G, jl = (e % G) * 4;
+      for (int i = 0; i < IT; ++i) {
+        const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
         if (m0 + bl < Bt) {
           const int64_t o = (base + bl) * d + j0 + jl;
           dyp[i] = *reinterpret_cast<const float4*>(p.dy + o);
@@ -411,7 +441,8 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
         ptx::mbar_wait(tmem_full_bar, n_mma & 1);
         ptx::tc_fence_after();
         ++n_mma;
-        if (m0 + q * 32 < B_next) {
+        if (tid == 0) gp_dbg(p.dbg, n_mma, 4);
+        if (drainer && m0 + q * 32 < B_next) {
           float* dst = acc_sm + (q * 32 + lane) * ACC_LD;
 #pragma unroll
           for (int c = 0; c < NROWS; c += 16) {
@@ -424,11 +455,12 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
         }
         ptx::tc_fence_before();
       }
-      epi_bar_sync();
+      gp_bar_sync();
+      if (tid == 0) gp_dbg(p.dbg, n_mma, 5);
       const int64_t base = (t >= 0) ? (int64_t)p.off[t] + m0 : 0;
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const int e = tid + 128 * i, bl = e / G, jl = (e % G) * 4;
+      for (int i = 0; i < IT; ++i) {
+        const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
         const int b = m0 + bl;
         if (b >= Bt) continue;
         const bool from_next = b < B_next;
@@ -471,14 +503,287 @@ __global__ void __launch_bounds__(192, 1) gru_persist_bwd_kernel(const __grid_co
         st4_bf16(p.dgh_b + o3 + d, daz);
         st4_bf16(p.dgh_b + o3 + 2 * d, danr);
       }
-      epi_bar_sync();
+      gp_bar_sync();
+      if (tid == 0) gp_dbg(p.dbg, n_mma, 6);
       if (tid == 0) red_release_add(p.sync + bi, 1);
+      if (tid == 0) gp_dbg(p.dbg, n_mma, 7);
       if (t - 1 >= 0) prefetch(t - 1);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (CS > 1) ptx::cluster_sync_all();       // no CTA leaves while a peer may still multicast into it
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// =====================================================================================================
+// backward through time, K-SPLIT variant (d = 1024-class layers: syn-types / syn-tipr)
+// =====================================================================================================
+// Measured on the kernel above at d = 1024, B = 256 (tools/gru_persist_bench.py, clock64 timeline): of the 25 300
+// cycles of a step, 18 700 are the A-operand fetch — every CTA pulls the WHOLE dgh_{t+1} tile ([128 x 3d] bf16 =
+// 768 KB) through TMA at ~43 B/clk per SM, whatever the ring depth or multicast width.  The bytes have to go: here a
+// CLUSTER of KS = 4 CTAs owns 64 output units together; CTA r multiplies only ITS QUARTER of the contraction
+// (gate columns [r*3d/4, (r+1)*3d/4): 192 KB of dgh per step instead of 768 KB, N = 64 MMAs instead of N = 16) and
+// the four [128 x 64] fp32 partial sums are reduce-scattered through distributed shared memory: the [128 x 16] block
+// that belongs to peer q goes there with ONE 8 KB bulk copy that completes on the peer's mbarrier (24 KB out, 24 KB
+// in per CTA per step).  Each CTA then runs the unchanged gate math on its own 16 units.
+//   resident weights: rows [64 units of the cluster] x K quarter of W_hh^T  = 64 * (3d/4) * 2 B  (96 KB at d = 1024)
+constexpr int KS = 4;            // K splits = cluster width
+constexpr int KS_NC = 64;        // output units per cluster = UMMA N
+constexpr int KS_DJ = 16;        // output units per CTA
+constexpr int KS_BLK = GP_BM * KS_DJ * 4;   // one [128 x 16] fp32 partial block: 8 KB
+
+// 16-byte chunk c (0..3) of row `row` inside a partial block: XOR-swizzled so that a warp's float4 row writes and the
+// (row, 4-unit) item reads are both bank-conflict free
+__device__ __forceinline__ int ks_chunk_off(int row, int c) { return row * KS_DJ + ((c ^ ((row >> 1) & 3)) << 2); }
+
+template <int STAGES>
+__global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmW,
+                                                                    const GruPersistBwdParams p) {
+  constexpr int DJ = KS_DJ;
+  constexpr uint32_t TMEM_COLS = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.d, L = p.L;
+  const int kq = 3 * d / KS;                 // contraction elements of this CTA
+  const int nkc = kq / GP_BK;
+  uint8_t* w_sm = smem;                                            // [nkc][64 rows x 128 B]
+  uint8_t* a_sm = w_sm + nkc * (KS_NC * 128);                      // ring
+  float* send_sm = reinterpret_cast<float*>(a_sm + STAGES * GP_A_BYTES);   // [KS dst][128 x 16] (own block stays here)
+  float* part_sm = send_sm + KS * (KS_BLK / 4);                    // [KS src][128 x 16] (slot of the own rank unused)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(part_sm + KS * (KS_BLK / 4));
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* w_bar = empty_bar + STAGES;
+  uint64_t* tmem_full_bar = w_bar + 1;
+  uint64_t* part_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(part_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bi = blockIdx.y, ns = gridDim.x;
+  const uint32_t crank = ptx::cluster_ctarank();               // == blockIdx.x % KS (cluster = KS consecutive x)
+  const int jc0 = ((int)blockIdx.x / KS) * KS_NC;              // first output unit of the cluster
+  const int j0 = jc0 + (int)crank * DJ;                        // first output unit of this CTA
+  const int k0 = (int)crank * kq;                              // first contraction element of this CTA
+  const int m0 = bi * GP_BM;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::mbar_init(part_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();                   // the peers' part_bar exists before anybody copies into them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_active = [&](int t) { return m0 < p.bt[t < 0 ? 0 : t]; };
+  auto has_mma = [&](int t) { return (t + 1 <= L - 1) && (m0 < p.bt[t + 1]); };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(nkc * KS_NC * 128));
+      for (int kc = 0; kc < nkc; ++kc)
+        ptx::tma_load_2d(w_sm + kc * (KS_NC * 128), &tmW, w_bar, k0 + kc * GP_BK, jc0);
+      int it = 0, done = 0;
+      for (int t = L - 1; t >= -1; --t) {
+        if (!tile_active(t)) continue;
+        if (has_mma(t)) {
+          wait_counter(p.sync + bi, done * ns);   // every slice of dgh_{t+1} is in global memory
+          gp_dbg(p.dbg, done, 0);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const int row0 = p.off[t + 1] + m0;
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % STAGES;
+            ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[s], GP_A_BYTES);
+            ptx::tma_load_2d(a_sm + s * GP_A_BYTES, &tmA, &full_bar[s], k0 + kc * GP_BK, row0);
+          }
+          gp_dbg(p.dbg, done, 1);
+        }
+        ++done;
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(GP_BM, KS_NC, 0, 0);
+      ptx::mbar_wait(w_bar, 0);
+      const uint32_t w_addr = ptx::smem_u32(w_sm), a_addr0 = ptx::smem_u32(a_sm);
+      int it = 0, nm = 0;
+      for (int t = L - 1; t >= -1; --t) {
+        if (!tile_active(t) || !has_mma(t)) continue;
+        ++nm;
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if (kc == 0) gp_dbg(p.dbg, nm, 2);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < GP_BK / 16; ++kk) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES + kk * 32, 16, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (KS_NC * 128) + kk * 32, 16, 1024);
+            ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+        }
+        ptx::umma_commit(tmem_full_bar);
+        gp_dbg(p.dbg, nm, 3);
+      }
+    }
+  } else {
+    constexpr int G = DJ / 4;                    // 4-unit groups per row
+    constexpr int IT = G * GP_BM / GP_EPI;       // work items per thread
+    const int q = warp & 3;
+    const bool drainer = warp < 6;               // warps 2..5 own the TMEM lane quadrants 2,3,0,1
+    const int tid = threadIdx.x - 64;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t d3 = 3 * (int64_t)d;
+    float carry[IT][4];
+#pragma unroll
+    for (int i = 0; i < IT; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) carry[i][k] = 0.f;
+    float4 dyp[IT];
+    uint2 sp[IT][5];
+    auto prefetch = [&](int t) {
+      const int Bt = p.bt[t];
+      const int64_t base = (int64_t)p.off[t] + m0;
+#pragma unroll
+      for (int i = 0; i < IT; ++i) {
+        const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
+        if (m0 + bl < Bt) {
+          const int64_t o = (base + bl) * d + j0 + jl;
+          dyp[i] = *reinterpret_cast<const float4*>(p.dy + o);
+          sp[i][0] = *reinterpret_cast<const uint2*>(p.r + o);
+          sp[i][1] = *reinterpret_cast<const uint2*>(p.z + o);
+          sp[i][2] = *reinterpret_cast<const uint2*>(p.n + o);
+          sp[i][3] = *reinterpret_cast<const uint2*>(p.ghn + o);
+          sp[i][4] = *reinterpret_cast<const uint2*>(p.hp_b + o);
+        }
+      }
+    };
+    int t_first = L - 1;
+    while (t_first >= 0 && !tile_active(t_first)) --t_first;
+    if (t_first >= 0) prefetch(t_first);
+    int n_mma = 0;
+    const uint32_t part_bar_a = ptx::smem_u32(part_bar);
+    for (int t = t_first; t >= -1; --t) {
+      const bool mma = has_mma(t);
+      const int B_next = (t + 1 <= L - 1) ? p.bt[t + 1] : 0;
+      const int Bt = p.bt[t < 0 ? 0 : t];
+      if (mma) {
+        ptx::mbar_wait(tmem_full_bar, n_mma & 1);
+        ptx::tc_fence_after();
+        ++n_mma;
+        if (tid == 0) gp_dbg(p.dbg, n_mma, 4);
+        if (drainer && m0 + q * 32 < B_next) {   // warp-uniform: quadrants without live rows have nothing to send
+          const int row = q * 32 + lane;
+#pragma unroll
+          for (int dst = 0; dst < KS; ++dst) {   // columns [16 dst, 16 dst + 16) of the cluster belong to peer `dst`
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(dst * DJ), v);
+            ptx::tmem_ld_wait();
+            float* blk = send_sm + dst * (KS_BLK / 4);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(blk + ks_chunk_off(row, c)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+        }
+        ptx::tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the bulk copies below read what we just wrote
+        gp_bar_sync();
+        if (tid == 0) {
+          // incoming: the three peers' blocks for MY units (8 KB each) complete on part_bar
+          ptx::mbar_arrive_expect_tx(part_bar, (uint32_t)((KS - 1) * KS_BLK));
+#pragma unroll
+          for (int o = 1; o < KS; ++o) {
+            const uint32_t dst = (crank + (uint32_t)o) % KS;
+            ptx::bulk_copy_s2c(ptx::mapa_u32(ptx::smem_u32(part_sm + crank * (KS_BLK / 4)), dst),
+                               ptx::smem_u32(send_sm + dst * (KS_BLK / 4)), (uint32_t)KS_BLK, ptx::mapa_u32(part_bar_a, dst));
+          }
+        }
+        ptx::mbar_wait_cluster(part_bar, (n_mma - 1) & 1);
+        if (tid == 0) gp_dbg(p.dbg, n_mma, 5);
+      } else {
+        gp_bar_sync();
+      }
+      const int64_t base = (t >= 0) ? (int64_t)p.off[t] + m0 : 0;
+#pragma unroll
+      for (int i = 0; i < IT; ++i) {
+        const int e = tid + GP_EPI * i, bl = e / G, g4 = e % G, jl = g4 * 4;
+        const int b = m0 + bl;
+        if (b >= Bt) continue;
+        const bool from_next = b < B_next;
+        float dh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dh[k] = from_next ? carry[i][k] : 0.f;
+        if (from_next && mma) {
+          const int o4 = ks_chunk_off(bl, g4);
+#pragma unroll
+          for (int src = 0; src < KS; ++src) {
+            const float* blk = (src == (int)crank) ? send_sm + crank * (KS_BLK / 4) : part_sm + src * (KS_BLK / 4);
+            const float4 v = *reinterpret_cast<const float4*>(blk + o4);
+            dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
+          }
+        }
+        if (t < 0) {
+          float* o = p.dh0 + (int64_t)b * d + j0 + jl;
+          float4 v = make_float4(dh[0], dh[1], dh[2], dh[3]);
+          if (p.dh0_accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(o);
+            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+          }
+          *reinterpret_cast<float4*>(o) = v;
+          continue;
+        }
+        const float dyv[4] = {dyp[i].x, dyp[i].y, dyp[i].z, dyp[i].w};
+        float r[4], z[4], n[4], g[4], hp[4];
+        {
+          float2 a, c2;
+          a = unpack_bf16x2(sp[i][0].x); c2 = unpack_bf16x2(sp[i][0].y); r[0] = a.x; r[1] = a.y; r[2] = c2.x; r[3] = c2.y;
+          a = unpack_bf16x2(sp[i][1].x); c2 = unpack_bf16x2(sp[i][1].y); z[0] = a.x; z[1] = a.y; z[2] = c2.x; z[3] = c2.y;
+          a = unpack_bf16x2(sp[i][2].x); c2 = unpack_bf16x2(sp[i][2].y); n[0] = a.x; n[1] = a.y; n[2] = c2.x; n[3] = c2.y;
+          a = unpack_bf16x2(sp[i][3].x); c2 = unpack_bf16x2(sp[i][3].y); g[0] = a.x; g[1] = a.y; g[2] = c2.x; g[3] = c2.y;
+          a = unpack_bf16x2(sp[i][4].x); c2 = unpack_bf16x2(sp[i][4].y); hp[0] = a.x; hp[1] = a.y; hp[2] = c2.x; hp[3] = c2.y;
+        }
+        float dar[4], daz[4], dan[4], danr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const GruBwd w = gru_bwd_math(dh[k] + dyv[k], r[k], z[k], n[k], g[k], hp[k]);
+          dar[k] = w.dar; daz[k] = w.daz; dan[k] = w.dan; danr[k] = w.dan_r;
+          carry[i][k] = w.dh_prev;
+        }
+        const int64_t o3 = (base + bl) * d3 + j0 + jl;
+        st4_bf16(p.dgi_b + o3, dar);
+        st4_bf16(p.dgi_b + o3 + d, daz);
+        st4_bf16(p.dgi_b + o3 + 2 * d, dan);
+        st4_bf16(p.dgh_b + o3, dar);
+        st4_bf16(p.dgh_b + o3 + d, daz);
+        st4_bf16(p.dgh_b + o3 + 2 * d, danr);
+      }
+      gp_bar_sync();
+      if (tid == 0) gp_dbg(p.dbg, n_mma, 6);
+      if (tid == 0) red_release_add(p.sync + bi, 1);
+      if (tid == 0) gp_dbg(p.dbg, n_mma, 7);
+      if (t - 1 >= 0) prefetch(t - 1);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();                   // no CTA leaves while a peer may still copy into it
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -519,6 +824,22 @@ __global__ void __launch_bounds__(256) transpose_bf16_x2_kernel(const uint16_t* 
 }
 
 // ---------------------------------------------------------------------------------------------- host
+static int max_stages() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ARK_GRU_STAGES"); v = e ? atoi(e) : 4; if (v < 2) v = 2; if (v > 6) v = 6; }
+  return v;
+}
+static long long* g_pdbg = nullptr;      // ARK_GRU_PERSIST_DBG=1: [fwd 4x8 | bwd 4x8] clock64 words
+static long long* pdbg_buffer() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ARK_GRU_PERSIST_DBG"); on = e ? atoi(e) : 0; }
+  if (!on) return nullptr;
+  if (!g_pdbg) {
+    if (cudaMalloc(&g_pdbg, sizeof(long long) * 64) != cudaSuccess) { (void)cudaGetLastError(); g_pdbg = nullptr; return nullptr; }
+    cudaMemset(g_pdbg, 0, sizeof(long long) * 64);
+  }
+  return g_pdbg;
+}
 static int pick_dj(int64_t d, int64_t bt0, int* stages_out) {
   if (d % 64 != 0 || d < 64 || bt0 <= 0) return 0;
   const int64_t nbt = (bt0 + GP_BM - 1) / GP_BM;
@@ -527,7 +848,7 @@ static int pick_dj(int64_t d, int64_t bt0, int* stages_out) {
     const int dj = cand[i];
     if (d % dj) continue;
     if (nbt * (d / dj) > kNumSMs) continue;
-    for (int st = 4; st >= 2; --st) {
+    for (int st = (dj == 16 ? max_stages() : (max_stages() < 4 ? max_stages() : 4)); st >= 2; --st) {
       const int64_t smem = 3LL * dj * d * 2 + (int64_t)st * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048;
       if (smem <= 227 * 1024) {
         *stages_out = st;
@@ -545,7 +866,7 @@ static int launch_coop(Kern kern, const CUtensorMap& tmA, const CUtensorMap& tmW
   if (e != cudaSuccess) return fail((int)e, "%s: smem attribute (%d B): %s", who, smem, cudaGetErrorString(e));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(GP_THREADS);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = s;
   cudaLaunchAttribute attrs[2];
@@ -569,7 +890,7 @@ static int launch_coop(Kern kern, const CUtensorMap& tmA, const CUtensorMap& tmW
 // Largest cluster width (4, 2, 1) along the hidden-slice dimension for which ALL clusters of the grid are co-resident
 // (the kernel spins on flags written by other CTAs, so co-residency is a correctness requirement).
 template <typename Kern>
-static int pick_cluster(Kern k4, Kern k2, dim3 grid, int smem) {
+static int pick_cluster(Kern k8, Kern k4, Kern k2, dim3 grid, int smem) {
   static int forced = -1;
   if (forced < 0) {
     // Default 1 (no clusters): measured on B200 (syn-types, d=1024) the 4-CTA multicast cuts the L2 reads of the A
@@ -581,21 +902,21 @@ static int pick_cluster(Kern k4, Kern k2, dim3 grid, int smem) {
   static thread_local struct { const void* k; unsigned gx, gy; int smem, cs; } memo[16];
   static thread_local int n_memo = 0;
   for (int i = 0; i < n_memo; ++i)
-    if (memo[i].k == (const void*)k4 && memo[i].gx == grid.x && memo[i].gy == grid.y && memo[i].smem == smem) return memo[i].cs;
+    if (memo[i].k == (const void*)k8 && memo[i].gx == grid.x && memo[i].gy == grid.y && memo[i].smem == smem) return memo[i].cs;
   auto remember = [&](int cs) {
-    if (n_memo < 16) { memo[n_memo].k = (const void*)k4; memo[n_memo].gx = grid.x; memo[n_memo].gy = grid.y; memo[n_memo].smem = smem; memo[n_memo].cs = cs; ++n_memo; }
+    if (n_memo < 16) { memo[n_memo].k = (const void*)k8; memo[n_memo].gx = grid.x; memo[n_memo].gy = grid.y; memo[n_memo].smem = smem; memo[n_memo].cs = cs; ++n_memo; }
     return cs;
   };
-  const int cand[2] = {4, 2};
-  for (int i = 0; i < 2; ++i) {
+  const int cand[3] = {8, 4, 2};
+  for (int i = 0; i < 3; ++i) {
     const int cs = cand[i];
     if (cs > forced) continue;
     if (grid.x % cs) continue;
-    Kern k = cs == 4 ? k4 : k2;
+    Kern k = cs == 8 ? k8 : (cs == 4 ? k4 : k2);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) continue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(GP_THREADS);
     cfg.dynamicSmemBytes = (size_t)smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -605,6 +926,7 @@ static int pick_cluster(Kern k4, Kern k2, dim3 grid, int smem) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
+    if (cs > 8) continue;
     const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, k, &cfg);
     if (qe != cudaSuccess) {
       if (getenv("ARK_GRU_DEBUG")) fprintf(stderr, "[arkb200] cudaOccupancyMaxActiveClusters(cluster=%d): %s\n", cs, cudaGetErrorString(qe));
@@ -619,9 +941,64 @@ static int pick_cluster(Kern k4, Kern k2, dim3 grid, int smem) {
   return remember(1);
 }
 
+
+// K-split backward (gru_persist_bwd_ks_kernel): shared-memory bytes and ring depth, or 0 when it does not apply.
+// It pays where the dgh tile is large (d >= 512) and needs 3d/4 % 64 == 0, 16-unit slices filling <= 148 SMs and all
+// d/64 * nbt clusters of 4 co-resident (ARK_GRU_KSPLIT=0 switches it off).
+static int ks_plan(int64_t d, int64_t bt0, int* stages_out) {
+  static int want = -1;
+  if (want < 0) { const char* e = getenv("ARK_GRU_KSPLIT"); want = e ? atoi(e) : 1; }
+  if (!want || d < 512 || d % 256 != 0 || bt0 <= 0) return 0;
+  const int64_t nbt = (bt0 + GP_BM - 1) / GP_BM;
+  if (nbt * (d / KS_DJ) > kNumSMs) return 0;
+  for (int st = 4; st >= 2; --st) {
+    const int64_t smem = (3 * d / KS) * KS_NC * 2 + (int64_t)st * GP_A_BYTES + 2LL * KS * KS_BLK + (2 * st + 4) * 8 + 16 + 1024;
+    if (smem > 227 * 1024) continue;
+    // co-residency of every cluster (the kernel spins on counters written by the other clusters)
+    static thread_local struct { int64_t d, nbt; int st, ok; } memo[8];
+    static thread_local int n_memo = 0;
+    int ok = -1;
+    for (int i = 0; i < n_memo; ++i)
+      if (memo[i].d == d && memo[i].nbt == nbt && memo[i].st == st) ok = memo[i].ok;
+    if (ok < 0) {
+      auto kern = st == 4 ? gru_persist_bwd_ks_kernel<4> : (st == 3 ? gru_persist_bwd_ks_kernel<3> : gru_persist_bwd_ks_kernel<2>);
+      ok = 0;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(d / KS_DJ), (unsigned)nbt);
+        cfg.blockDim = dim3(GP_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = KS;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess) ok = ((int64_t)n * KS >= nbt * (d / KS_DJ)) ? 1 : 0;
+        else (void)cudaGetLastError();
+        if (getenv("ARK_GRU_DEBUG")) fprintf(stderr, "[arkb200] gru_persist_bwd_ks d=%lld nbt=%lld stages=%d smem=%lld: max active clusters %d\n", (long long)d, (long long)nbt, st, (long long)smem, n);
+      } else {
+        (void)cudaGetLastError();
+      }
+      if (n_memo < 8) { memo[n_memo].d = d; memo[n_memo].nbt = nbt; memo[n_memo].st = st; memo[n_memo].ok = ok; ++n_memo; }
+    }
+    if (ok) { *stages_out = st; return (int)smem; }
+  }
+  return 0;
+}
+
 }  // namespace ark
 
 using namespace ark;
+
+extern "C" int ark_gru_persist_debug_dump(int64_t* out_host, int64_t n_words) {
+  if (!g_pdbg) return fail(ARK_E_BADARG, "gru_persist_debug_dump: ARK_GRU_PERSIST_DBG was not set");
+  if (n_words > 64) n_words = 64;
+  cudaError_t e = cudaMemcpy(out_host, g_pdbg, sizeof(long long) * n_words, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? 0 : fail((int)e, "gru_persist_debug_dump: %s", cudaGetErrorString(e));
+}
 
 extern "C" int ark_gru_persist_supported(int64_t d, int64_t bt0) {
   int st;
@@ -665,17 +1042,19 @@ extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16
   GruPersistFwdParams prm;
   prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.gi = gi; prm.b_hh = b_hh;
   prm.h0 = h0; prm.hp_b = hp_b; prm.y_b = y_b; prm.r = r; prm.z = z; prm.n = n; prm.ghn = ghn;
+  prm.dbg = pdbg_buffer();
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
   const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
 #define ARK_GP_FWD(DJ, ST)                                                                                              \
   if (dj == DJ && stages == ST) {                                                                                       \
-    const int cs = (bt0 >= GP_BM) ? pick_cluster(gru_persist_fwd_kernel<DJ, ST, 4>, gru_persist_fwd_kernel<DJ, ST, 2>, grid, smem) : 1; \
+    const int cs = (bt0 >= GP_BM) ? pick_cluster(gru_persist_fwd_kernel<DJ, ST, 8>, gru_persist_fwd_kernel<DJ, ST, 4>, gru_persist_fwd_kernel<DJ, ST, 2>, grid, smem) : 1; \
     if ((rc = make_tmap_2d_bf16(&tmA, hp_b, (uint64_t)d, (uint64_t)N, (uint64_t)d, GP_BK, GP_BM / cs))) return rc;       \
+    if (cs == 8) return launch_coop(gru_persist_fwd_kernel<DJ, ST, 8>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd", 8); \
     if (cs == 4) return launch_coop(gru_persist_fwd_kernel<DJ, ST, 4>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd", 4); \
     if (cs == 2) return launch_coop(gru_persist_fwd_kernel<DJ, ST, 2>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd", 2); \
     return launch_coop(gru_persist_fwd_kernel<DJ, ST, 1>, tmA, tmW, prm, grid, smem, s, "gru_persist_fwd", 1);          \
   }
-  ARK_GP_FWD(16, 4); ARK_GP_FWD(16, 3); ARK_GP_FWD(16, 2);
+  ARK_GP_FWD(16, 6); ARK_GP_FWD(16, 5); ARK_GP_FWD(16, 4); ARK_GP_FWD(16, 3); ARK_GP_FWD(16, 2);
   ARK_GP_FWD(32, 4); ARK_GP_FWD(32, 3); ARK_GP_FWD(32, 2);
   ARK_GP_FWD(64, 4); ARK_GP_FWD(64, 3); ARK_GP_FWD(64, 2);
 #undef ARK_GP_FWD
@@ -706,17 +1085,32 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
   prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.dy = dy; prm.r = r;
   prm.z = z; prm.n = n; prm.ghn = ghn; prm.hp_b = hp_b; prm.dgi_b = dgi_b; prm.dgh_b = dgh_b; prm.dh0 = dh0;
   prm.dh0_accumulate = dh0_accumulate;
+  prm.dbg = pdbg_buffer() ? pdbg_buffer() + 32 : nullptr;
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
+  {
+    int ks_st = 0;
+    const int ks_smem = ks_plan(d, bt0, &ks_st);
+    if (ks_smem > 0) {
+      CUtensorMap tmAk, tmWk;
+      if ((rc = make_tmap_2d_bf16(&tmWk, WhhT_b, (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), GP_BK, KS_NC))) return rc;
+      if ((rc = make_tmap_2d_bf16(&tmAk, dgh_b, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d), GP_BK, GP_BM))) return rc;
+      dim3 gk((unsigned)(d / KS_DJ), (unsigned)nbt);
+      if (ks_st == 4) return launch_coop(gru_persist_bwd_ks_kernel<4>, tmAk, tmWk, prm, gk, ks_smem, s, "gru_persist_bwd_ks", KS);
+      if (ks_st == 3) return launch_coop(gru_persist_bwd_ks_kernel<3>, tmAk, tmWk, prm, gk, ks_smem, s, "gru_persist_bwd_ks", KS);
+      return launch_coop(gru_persist_bwd_ks_kernel<2>, tmAk, tmWk, prm, gk, ks_smem, s, "gru_persist_bwd_ks", KS);
+    }
+  }
   const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
 #define ARK_GP_BWD(DJ, ST)                                                                                              \
   if (dj == DJ && stages == ST) {                                                                                       \
-    const int cs = (bt0 >= GP_BM) ? pick_cluster(gru_persist_bwd_kernel<DJ, ST, 4>, gru_persist_bwd_kernel<DJ, ST, 2>, grid, smem) : 1; \
+    const int cs = (bt0 >= GP_BM) ? pick_cluster(gru_persist_bwd_kernel<DJ, ST, 8>, gru_persist_bwd_kernel<DJ, ST, 4>, gru_persist_bwd_kernel<DJ, ST, 2>, grid, smem) : 1; \
     if ((rc = make_tmap_2d_bf16(&tmA, dgh_b, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d), GP_BK, GP_BM / cs))) return rc; \
+    if (cs == 8) return launch_coop(gru_persist_bwd_kernel<DJ, ST, 8>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd", 8); \
     if (cs == 4) return launch_coop(gru_persist_bwd_kernel<DJ, ST, 4>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd", 4); \
     if (cs == 2) return launch_coop(gru_persist_bwd_kernel<DJ, ST, 2>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd", 2); \
     return launch_coop(gru_persist_bwd_kernel<DJ, ST, 1>, tmA, tmW, prm, grid, smem, s, "gru_persist_bwd", 1);          \
   }
-  ARK_GP_BWD(16, 4); ARK_GP_BWD(16, 3); ARK_GP_BWD(16, 2);
+  ARK_GP_BWD(16, 6); ARK_GP_BWD(16, 5); ARK_GP_BWD(16, 4); ARK_GP_BWD(16, 3); ARK_GP_BWD(16, 2);
   ARK_GP_BWD(32, 4); ARK_GP_BWD(32, 3); ARK_GP_BWD(32, 2);
   ARK_GP_BWD(64, 4); ARK_GP_BWD(64, 3); ARK_GP_BWD(64, 2);
 #undef ARK_GP_BWD

@@ -217,6 +217,8 @@ int ark_gru_cluster_supported(int64_t d, int64_t bt0, int64_t nl, int64_t L);
 /* debugging aid: with ARK_GRU_CLUSTER_DBG=<first iteration> in the environment the cluster kernels record a clock64
  * timeline [2 dir][8 blockIdx.z][3 thread roles][4 iterations][16 points] of CTA (0,0) of every stage */
 int ark_gru_cluster_debug_dump(int64_t* out_host, int64_t n_words);
+/* same for the per-layer persistent kernels (ARK_GRU_PERSIST_DBG=1): [fwd 4 steps x 8 events | bwd 4 x 8] */
+int ark_gru_persist_debug_dump(int64_t* out_host, int64_t n_words);
 int64_t ark_gru_cluster_workspace_bytes(int64_t L, int64_t bt0, int64_t d, int64_t nl);
 int ark_gru_cluster_fwd(const uint16_t* x_b, uint16_t* hp_b, uint16_t* out_b, const float* h0,
                         const uint16_t* const* Wih_b, const uint16_t* const* Whh_b, const float* const* b_ih,

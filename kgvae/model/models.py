@@ -373,11 +373,12 @@ class SAIL(_EngineMixin, nn.Module):
     eps_hook = None     # tests: callable(B, dz, device) -> eps, replacing the randn draw of the differentiable forward
 
     def forward(self, triples, seq_in):
-        """(logits [B, L, V], mu, logv) — reference models.py:317-320.  With autograd enabled this is a differentiable
+        """(logits [B, L, V], mu, logv) — reference models.py:317-320.  In train() mode with autograd enabled this is a differentiable
         node on the fused engine (`_ForwardFn`: the reference's own loop `model(...)`, `loss.backward()`,
-        `optimizer.step()` trains through it); under `torch.no_grad()` it is the fp32 inference path whose integer
+        `optimizer.step()` trains through it); in eval() mode or under `torch.no_grad()` it is the fp32 inference path whose integer
         outputs (beam search, generation) match the reference bit for bit."""
-        if torch.is_grad_enabled() and self.config["model_type"] == "SAIL" and any(p.requires_grad for p in self.parameters()):
+        if (self.training and torch.is_grad_enabled() and self.config["model_type"] == "SAIL"
+                and any(p.requires_grad for p in self.parameters())):
             _need_cuda(triples, "forward")
             B, dz = triples.shape[0], self.config["d_latent"]
             dev = self.engine().device
@@ -541,9 +542,11 @@ class ARK(_EngineMixin, nn.Module):
 
     def forward(self, triples_or_seq, seq_in=None):
         """forward(seq) or forward(triples, seq) — triples are ignored (reference models.py:395-405).  Differentiable
-        on the fused engine when autograd is enabled (GRU model), fp32 inference path under torch.no_grad()."""
+        on the fused engine in train() mode with autograd enabled (GRU model); fp32 inference path in eval() mode or
+        under torch.no_grad()."""
         seq = triples_or_seq if seq_in is None else seq_in
-        if torch.is_grad_enabled() and self.config["model_type"] == "ARK" and any(p.requires_grad for p in self.parameters()):
+        if (self.training and torch.is_grad_enabled() and self.config["model_type"] == "ARK"
+                and any(p.requires_grad for p in self.parameters())):
             _need_cuda(seq, "forward")
             return _ForwardFn.apply(self, None, seq, None, *self.parameters())[0]
         return self.dec(seq)
