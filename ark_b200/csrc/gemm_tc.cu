@@ -460,6 +460,13 @@ int tc_enqueue(const CUtensorMap& tmA, const CUtensorMap& tmB, int a_major, int 
     if (tiles >= 2 * kNumSMs) return dispatch_major<128, 4, true>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
     return dispatch_major<128, 3, false>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
   }
+  // BN = 64 means the grid is small (< 148 tiles of 128x128).  With at most one CTA per SM and a long K the main loop
+  // is bound by bytes in flight x HBM latency (measured: the encoder MLP, M = 256, K = 3072, 96 CTAs, ran 26 us with a
+  // 4 x 24 KB ring = 25 B/clk per SM): such shapes get an 8-stage ring (192 KB in flight per SM)
+  const int64_t tiles64 = (int64_t)((M + TC_BM - 1) / TC_BM) * ((N + 63) / 64);
+  const bool splitk_ok = !ep.c_bf16 && ep.epilogue == ARK_EPI_NONE && !ep.aux;   // those keep 2 CTAs/SM + split-K
+  if (tiles64 <= kNumSMs && K >= 16 * TC_BK && !splitk_ok)
+    return dispatch_major<64, 8, false>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
   return dispatch_major<64, 4, false>(a_major, b_major, tmA, tmB, ep, M, N, K, a_row0, b_row0, s);
 }
 

@@ -21,6 +21,7 @@
 #include "tmap.cuh"
 #include "gru_math.cuh"
 #include "gru_dev.cuh"
+#include "philox.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -46,7 +47,13 @@ struct GruPersistFwdParams {
   const float* h0;     // [bt[0], d] fp32 initial state
   uint16_t* hp_b;      // [N, d] bf16 packed h_prev rows (block 0 pre-filled with bf16(h0)); written for t+1
   uint16_t* y_b;       // [N, d] bf16 outputs
-  uint16_t *r, *z, *n, *ghn;  // [N, d] bf16 saved gates (may all be null)
+ uint16_t *r, *z, *n, *ghn;  // [N, d] bf16 saved gates (may all be null)
+  // fused inter-layer dropout of the OUTPUT rows y_b (hp_b keeps the undropped state): same Philox draw as
+  // ark_dropout_bf16 over the [N, d] tensor (counter = offset + element/4); mask u8 [N, d] or null
+  uint8_t* mask;
+  const uint64_t* offset_dev;
+  uint64_t seed, offset;
+  float p_drop;
   long long* dbg;      // ARK_GRU_PERSIST_DBG: clock64 timeline of CTA (0,0), steps 2..5 ([4][8] words), else NULL
 };
 
@@ -58,8 +65,10 @@ struct GruPersistBwdParams {
   const float* dy;                          // [N, d] gradient w.r.t. the layer outputs
   const uint16_t *r, *z, *n, *ghn, *hp_b;   // saved by the forward kernel
   uint16_t *dgi_b, *dgh_b;                  // [N, 3d] bf16 (dgh_b is also the A operand of the next step)
-  float* dh0;                               // [bt[0], d]
+ float* dh0;                               // [bt[0], d]
   int dh0_accumulate;
+  const uint8_t* dy_mask;                   // keep mask of the dropout applied to this layer's OUTPUT in the forward pass
+  float dy_scale;                           // (dy is multiplied by keep / (1 - p) on the fly), or null
   long long* dbg;                           // as in the forward parameters ([4][8] words behind the forward's)
 };
 
@@ -200,6 +209,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       const float4 hv = (b < bt0) ? *reinterpret_cast<const float4*>(p.h0 + (int64_t)b * d + j) : make_float4(0, 0, 0, 0);
       hreg[i][0] = hv.x; hreg[i][1] = hv.y; hreg[i][2] = hv.z; hreg[i][3] = hv.w;
     }
+    const bool drop = p.p_drop > 0.f;
+    const float drop_scale = drop ? 1.f / (1.f - p.p_drop) : 1.f;
+    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    const uint64_t ctr0 = p.offset + (p.offset_dev ? *p.offset_dev : 0ull);
     float4 gpre[IT][3];
     auto prefetch_gi = [&](int t) {
       const int Bt = p.bt[t];
@@ -239,6 +252,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
       ptx::tc_fence_before();
       gp_bar_sync();
       if (tid == 0) gp_dbg(p.dbg, t, 5);
+      float o_r[IT][4], o_z[IT][4], o_n[IT][4], o_g[IT][4];
 #pragma unroll
       for (int i = 0; i < IT; ++i) {
         const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
@@ -253,29 +267,52 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           const float4 b_n = __ldg(reinterpret_cast<const float4*>(p.b_hh + 2 * d + j0 + jl));
           const float br[4] = {b_r.x, b_r.y, b_r.z, b_r.w}, bz[4] = {b_z.x, b_z.y, b_z.z, b_z.w};
           const float bn[4] = {b_n.x, b_n.y, b_n.z, b_n.w};
-          float o_r[4], o_z[4], o_n[4], o_g[4], o_h[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const GruFwd o = gru_fwd_math_fast(gr[k], gz[k], gn[k], ap[k] + br[k], ap[DJ + k] + bz[k],
                                                ap[2 * DJ + k] + bn[k], hreg[i][k]);
             hreg[i][k] = o.h;
-            o_r[k] = o.r; o_z[k] = o.z; o_n[k] = o.n; o_g[k] = o.ghn; o_h[k] = o.h;
+            o_r[i][k] = o.r; o_z[i][k] = o.z; o_n[i][k] = o.n; o_g[i][k] = o.ghn;
           }
-          const int64_t o = (base + bl) * d + j0 + jl;
-          st4_bf16(p.y_b + o, o_h);
-          if (b < Bn) st4_bf16(p.hp_b + (base_n + bl) * d + j0 + jl, o_h);
-          if (p.r) {
-            st4_bf16(p.r + o, o_r);
-            st4_bf16(p.z + o, o_z);
-            st4_bf16(p.n + o, o_n);
-            st4_bf16(p.ghn + o, o_g);
-          }
+          // ONLY the h_prev rows of step t+1 sit on the recurrent chain: they go out before the release; the layer
+          // output and the saved gates (read by later kernels) are stored after it, off the chain
+          if (b < Bn) st4_bf16(p.hp_b + (base_n + bl) * d + j0 + jl, hreg[i]);
         }
       }
-      gp_bar_sync();                             // all stores of the tile issued (and acc_sm free again)
+      gp_bar_sync();                             // the chain's stores are issued (and acc_sm is free again)
       if (tid == 0) gp_dbg(p.dbg, t, 6);
       if (tid == 0) red_release_add(p.sync + bi, 1);   // release: cumulative over the barrier above
       if (tid == 0) gp_dbg(p.dbg, t, 7);
+#pragma unroll
+      for (int i = 0; i < IT; ++i) {
+        const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
+        if (m0 + bl < Bt) {
+          const int64_t o = (base + bl) * d + j0 + jl;
+          if (drop) {   // same draw as dropout_bf16_kernel over the [N, d] output of this layer
+            const uint64_t c = ctr0 + (uint64_t)(o >> 2);
+            const uint4 rn = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+            const uint32_t rr[4] = {rn.x, rn.y, rn.z, rn.w};
+            float yo[4];
+            uint32_t mk = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const bool keep = (float)(rr[k] >> 8) * (1.f / 16777216.f) >= p.p_drop;
+              mk |= (keep ? 1u : 0u) << (8 * k);
+              yo[k] = keep ? bf16_bits_to_f32(f32_to_bf16_bits(hreg[i][k])) * drop_scale : 0.f;
+            }
+            if (p.mask) *reinterpret_cast<uint32_t*>(p.mask + o) = mk;
+            st4_bf16(p.y_b + o, yo);
+          } else {
+            st4_bf16(p.y_b + o, hreg[i]);
+          }
+          if (p.r) {
+            st4_bf16(p.r + o, o_r[i]);
+            st4_bf16(p.z + o, o_z[i]);
+            st4_bf16(p.n + o, o_n[i]);
+            st4_bf16(p.ghn + o, o_g[i]);
+          }
+        }
+      }
       if (t + 1 < L && m0 < Bn) prefetch_gi(t + 1);
     }
   }
@@ -421,6 +458,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
         if (m0 + bl < Bt) {
           const int64_t o = (base + bl) * d + j0 + jl;
           dyp[i] = *reinterpret_cast<const float4*>(p.dy + o);
+          if (p.dy_mask) {     // backward of the inter-layer dropout applied to this layer's output
+            const uint32_t mk = *reinterpret_cast<const uint32_t*>(p.dy_mask + o);
+            dyp[i].x = (mk & 0xFFu) ? dyp[i].x * p.dy_scale : 0.f;
+            dyp[i].y = (mk & 0xFF00u) ? dyp[i].y * p.dy_scale : 0.f;
+            dyp[i].z = (mk & 0xFF0000u) ? dyp[i].z * p.dy_scale : 0.f;
+            dyp[i].w = (mk & 0xFF000000u) ? dyp[i].w * p.dy_scale : 0.f;
+          }
           sp[i][0] = *reinterpret_cast<const uint2*>(p.r + o);
           sp[i][1] = *reinterpret_cast<const uint2*>(p.z + o);
           sp[i][2] = *reinterpret_cast<const uint2*>(p.n + o);
@@ -458,6 +502,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
       gp_bar_sync();
       if (tid == 0) gp_dbg(p.dbg, n_mma, 5);
       const int64_t base = (t >= 0) ? (int64_t)p.off[t] + m0 : 0;
+      float dar[IT][4], daz[IT][4], dan[IT][4];
 #pragma unroll
       for (int i = 0; i < IT; ++i) {
         const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
@@ -488,25 +533,36 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
           a = unpack_bf16x2(sp[i][3].x); c2 = unpack_bf16x2(sp[i][3].y); g[0] = a.x; g[1] = a.y; g[2] = c2.x; g[3] = c2.y;
           a = unpack_bf16x2(sp[i][4].x); c2 = unpack_bf16x2(sp[i][4].y); hp[0] = a.x; hp[1] = a.y; hp[2] = c2.x; hp[3] = c2.y;
         }
-        float dar[4], daz[4], dan[4], danr[4];
+        float danr[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const GruBwd w = gru_bwd_math(dh[k] + dyv[k], r[k], z[k], n[k], g[k], hp[k]);
-          dar[k] = w.dar; daz[k] = w.daz; dan[k] = w.dan; danr[k] = w.dan_r;
+          dar[i][k] = w.dar; daz[i][k] = w.daz; dan[i][k] = w.dan; danr[k] = w.dan_r;
           carry[i][k] = w.dh_prev;
         }
+        // dgh_t is the next iteration's A operand: on the chain, stored before the release; dgi_t (read by the
+        // weight-gradient GEMMs after the kernel) is stored after it
         const int64_t o3 = (base + bl) * d3 + j0 + jl;
-        st4_bf16(p.dgi_b + o3, dar);
-        st4_bf16(p.dgi_b + o3 + d, daz);
-        st4_bf16(p.dgi_b + o3 + 2 * d, dan);
-        st4_bf16(p.dgh_b + o3, dar);
-        st4_bf16(p.dgh_b + o3 + d, daz);
+        st4_bf16(p.dgh_b + o3, dar[i]);
+        st4_bf16(p.dgh_b + o3 + d, daz[i]);
         st4_bf16(p.dgh_b + o3 + 2 * d, danr);
       }
       gp_bar_sync();
       if (tid == 0) gp_dbg(p.dbg, n_mma, 6);
       if (tid == 0) red_release_add(p.sync + bi, 1);
       if (tid == 0) gp_dbg(p.dbg, n_mma, 7);
+      if (t >= 0) {
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+          const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
+          if (m0 + bl < Bt) {
+            const int64_t o3 = (base + bl) * d3 + j0 + jl;
+            st4_bf16(p.dgi_b + o3, dar[i]);
+            st4_bf16(p.dgi_b + o3 + d, daz[i]);
+            st4_bf16(p.dgi_b + o3 + 2 * d, dan[i]);
+          }
+        }
+      }
       if (t - 1 >= 0) prefetch(t - 1);
     }
   }
@@ -596,8 +652,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
   if (warp == 0) {
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(nkc * KS_NC * 128));
+      // W_hh itself ([3d gate rows, d units], units contiguous) is the B operand in MN-major form: chunk kc = 64 gate
+      // rows x 64 units (128 B rows, 128B swizzle) — no transposed copy of the weights is ever made
       for (int kc = 0; kc < nkc; ++kc)
-        ptx::tma_load_2d(w_sm + kc * (KS_NC * 128), &tmW, w_bar, k0 + kc * GP_BK, jc0);
+        ptx::tma_load_2d(w_sm + kc * (KS_NC * 128), &tmW, w_bar, jc0, k0 + kc * GP_BK);
       int it = 0, done = 0;
       for (int t = L - 1; t >= -1; --t) {
         if (!tile_active(t)) continue;
@@ -619,7 +677,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(GP_BM, KS_NC, 0, 0);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(GP_BM, KS_NC, 0, 1);     // A K-major, B MN-major
       ptx::mbar_wait(w_bar, 0);
       const uint32_t w_addr = ptx::smem_u32(w_sm), a_addr0 = ptx::smem_u32(a_sm);
       int it = 0, nm = 0;
@@ -634,7 +692,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
 #pragma unroll
           for (int kk = 0; kk < GP_BK / 16; ++kk) {
             const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES + kk * 32, 16, 1024);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (KS_NC * 128) + kk * 32, 16, 1024);
+            // MN-major: 16 k-rows of 128 B = 2048 B further per UMMA k-step (same form as gemm_tc's B_MN operand)
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (KS_NC * 128) + kk * 2048, GP_BK * 128, 1024);
             ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[s]);
@@ -667,6 +726,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
         if (m0 + bl < Bt) {
           const int64_t o = (base + bl) * d + j0 + jl;
           dyp[i] = *reinterpret_cast<const float4*>(p.dy + o);
+          if (p.dy_mask) {     // backward of the inter-layer dropout applied to this layer's output
+            const uint32_t mk = *reinterpret_cast<const uint32_t*>(p.dy_mask + o);
+            dyp[i].x = (mk & 0xFFu) ? dyp[i].x * p.dy_scale : 0.f;
+            dyp[i].y = (mk & 0xFF00u) ? dyp[i].y * p.dy_scale : 0.f;
+            dyp[i].z = (mk & 0xFF0000u) ? dyp[i].z * p.dy_scale : 0.f;
+            dyp[i].w = (mk & 0xFF000000u) ? dyp[i].w * p.dy_scale : 0.f;
+          }
           sp[i][0] = *reinterpret_cast<const uint2*>(p.r + o);
           sp[i][1] = *reinterpret_cast<const uint2*>(p.z + o);
           sp[i][2] = *reinterpret_cast<const uint2*>(p.n + o);
@@ -721,6 +787,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
         gp_bar_sync();
       }
       const int64_t base = (t >= 0) ? (int64_t)p.off[t] + m0 : 0;
+      float dar[IT][4], daz[IT][4], dan[IT][4];
 #pragma unroll
       for (int i = 0; i < IT; ++i) {
         const int e = tid + GP_EPI * i, bl = e / G, g4 = e % G, jl = g4 * 4;
@@ -759,25 +826,36 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
           a = unpack_bf16x2(sp[i][3].x); c2 = unpack_bf16x2(sp[i][3].y); g[0] = a.x; g[1] = a.y; g[2] = c2.x; g[3] = c2.y;
           a = unpack_bf16x2(sp[i][4].x); c2 = unpack_bf16x2(sp[i][4].y); hp[0] = a.x; hp[1] = a.y; hp[2] = c2.x; hp[3] = c2.y;
         }
-        float dar[4], daz[4], dan[4], danr[4];
+        float danr[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const GruBwd w = gru_bwd_math(dh[k] + dyv[k], r[k], z[k], n[k], g[k], hp[k]);
-          dar[k] = w.dar; daz[k] = w.daz; dan[k] = w.dan; danr[k] = w.dan_r;
+          dar[i][k] = w.dar; daz[i][k] = w.daz; dan[i][k] = w.dan; danr[k] = w.dan_r;
           carry[i][k] = w.dh_prev;
         }
+        // dgh_t is the next iteration's A operand: on the chain, stored before the release; dgi_t (read by the
+        // weight-gradient GEMMs after the kernel) is stored after it
         const int64_t o3 = (base + bl) * d3 + j0 + jl;
-        st4_bf16(p.dgi_b + o3, dar);
-        st4_bf16(p.dgi_b + o3 + d, daz);
-        st4_bf16(p.dgi_b + o3 + 2 * d, dan);
-        st4_bf16(p.dgh_b + o3, dar);
-        st4_bf16(p.dgh_b + o3 + d, daz);
+        st4_bf16(p.dgh_b + o3, dar[i]);
+        st4_bf16(p.dgh_b + o3 + d, daz[i]);
         st4_bf16(p.dgh_b + o3 + 2 * d, danr);
       }
       gp_bar_sync();
       if (tid == 0) gp_dbg(p.dbg, n_mma, 6);
       if (tid == 0) red_release_add(p.sync + bi, 1);
       if (tid == 0) gp_dbg(p.dbg, n_mma, 7);
+      if (t >= 0) {
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+          const int e = tid + GP_EPI * i, bl = e / G, jl = (e % G) * 4;
+          if (m0 + bl < Bt) {
+            const int64_t o3 = (base + bl) * d3 + j0 + jl;
+            st4_bf16(p.dgi_b + o3, dar[i]);
+            st4_bf16(p.dgi_b + o3 + d, daz[i]);
+            st4_bf16(p.dgi_b + o3 + 2 * d, dan[i]);
+          }
+        }
+      }
       if (t - 1 >= 0) prefetch(t - 1);
     }
   }
@@ -1000,6 +1078,11 @@ extern "C" int ark_gru_persist_debug_dump(int64_t* out_host, int64_t n_words) {
   return e == cudaSuccess ? 0 : fail((int)e, "gru_persist_debug_dump: %s", cudaGetErrorString(e));
 }
 
+extern "C" int ark_gru_persist_bwd_ksplit(int64_t d, int64_t bt0) {
+  int st;
+  return ks_plan(d, bt0, &st) > 0 ? 1 : 0;
+}
+
 extern "C" int ark_gru_persist_supported(int64_t d, int64_t bt0) {
   int st;
   return pick_dj(d, bt0, &st);
@@ -1020,7 +1103,9 @@ extern "C" int ark_transpose_bf16(const uint16_t* in, int64_t R, int64_t C, uint
 extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16_t* Whh_b, const float* gi,
                                    const float* b_hh, const int32_t* bt_dev, const int32_t* off_dev, int64_t L,
                                    int64_t bt0, int64_t N, int64_t d, uint16_t* y_b, uint16_t* r, uint16_t* z,
-                                   uint16_t* n, uint16_t* ghn, int32_t* sync_ws, void* stream) {
+                                   uint16_t* n, uint16_t* ghn, uint8_t* mask, float p_drop, uint64_t seed,
+                                   uint64_t offset, const uint64_t* offset_dev, int32_t* sync_ws, void* stream) {
+  ARK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, ARK_E_BADARG, "gru_persist_fwd: dropout probability must be in [0,1)");
   ARK_REQUIRE(hp_b && h0 && Whh_b && gi && b_hh && bt_dev && off_dev && y_b && sync_ws, ARK_E_BADARG,
               "gru_persist_fwd: null pointer");
   ARK_REQUIRE((r && z && n && ghn) || (!r && !z && !n && !ghn), ARK_E_BADARG,
@@ -1042,6 +1127,8 @@ extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16
   GruPersistFwdParams prm;
   prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.gi = gi; prm.b_hh = b_hh;
   prm.h0 = h0; prm.hp_b = hp_b; prm.y_b = y_b; prm.r = r; prm.z = z; prm.n = n; prm.ghn = ghn;
+  prm.mask = p_drop > 0.f ? mask : nullptr; prm.p_drop = p_drop; prm.seed = seed; prm.offset = offset;
+  prm.offset_dev = p_drop > 0.f ? offset_dev : nullptr;
   prm.dbg = pdbg_buffer();
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
   const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
@@ -1065,34 +1152,38 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
                                    const uint16_t* ghn, const uint16_t* hp_b, const uint16_t* WhhT_b,
                                    const int32_t* bt_dev, const int32_t* off_dev, int64_t L, int64_t bt0, int64_t N,
                                    int64_t d, uint16_t* dgi_b, uint16_t* dgh_b, float* dh0, int dh0_accumulate,
-                                   int32_t* sync_ws, void* stream) {
-  ARK_REQUIRE(dy && r && z && n && ghn && hp_b && WhhT_b && bt_dev && off_dev && dgi_b && dgh_b && dh0 && sync_ws,
+                                   const uint16_t* Whh_b, const uint8_t* dy_mask, float p_drop, int32_t* sync_ws,
+                                   void* stream) {
+  ARK_REQUIRE(dy && r && z && n && ghn && hp_b && (WhhT_b || Whh_b) && bt_dev && off_dev && dgi_b && dgh_b && dh0 && sync_ws,
               ARK_E_BADARG, "gru_persist_bwd: null pointer");
+  ARK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, ARK_E_BADARG, "gru_persist_bwd: dropout probability must be in [0,1)");
   ARK_REQUIRE(L > 0 && N > 0 && bt0 > 0, ARK_E_BADARG, "gru_persist_bwd: bad sizes");
   int stages = 0;
   const int dj = pick_dj(d, bt0, &stages);
   ARK_REQUIRE(dj > 0, ARK_E_SHAPE, "gru_persist_bwd: unsupported shape d=%lld bt0=%lld", (long long)d, (long long)bt0);
-  ARK_REQUIRE(aligned16(dy) && aligned16(WhhT_b) && aligned16(dgi_b) && aligned16(dgh_b) && aligned16(dh0), ARK_E_ALIGN,
-              "gru_persist_bwd: 16-byte alignment");
+  ARK_REQUIRE(aligned16(dy) && aligned16(WhhT_b) && aligned16(Whh_b) && aligned16(dgi_b) && aligned16(dgh_b) && aligned16(dh0),
+              ARK_E_ALIGN, "gru_persist_bwd: 16-byte alignment");
   cudaStream_t s = (cudaStream_t)stream;
   const int nbt = (int)((bt0 + GP_BM - 1) / GP_BM);
   cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * nbt, s);
   if (e != cudaSuccess) return fail((int)e, "gru_persist_bwd: memset: %s", cudaGetErrorString(e));
   CUtensorMap tmA, tmW;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&tmW, WhhT_b, (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), GP_BK, dj))) return rc;
   GruPersistBwdParams prm;
   prm.bt = bt_dev; prm.off = off_dev; prm.L = (int)L; prm.d = (int)d; prm.sync = sync_ws; prm.dy = dy; prm.r = r;
   prm.z = z; prm.n = n; prm.ghn = ghn; prm.hp_b = hp_b; prm.dgi_b = dgi_b; prm.dgh_b = dgh_b; prm.dh0 = dh0;
   prm.dh0_accumulate = dh0_accumulate;
+  prm.dy_mask = (p_drop > 0.f) ? dy_mask : nullptr;
+  prm.dy_scale = 1.f / (1.f - p_drop);
   prm.dbg = pdbg_buffer() ? pdbg_buffer() + 32 : nullptr;
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
   {
     int ks_st = 0;
-    const int ks_smem = ks_plan(d, bt0, &ks_st);
+    const int ks_smem = Whh_b ? ks_plan(d, bt0, &ks_st) : 0;
     if (ks_smem > 0) {
       CUtensorMap tmAk, tmWk;
-      if ((rc = make_tmap_2d_bf16(&tmWk, WhhT_b, (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), GP_BK, KS_NC))) return rc;
+      // W_hh [3d, d] untransposed: inner = units, box = 64 units x 64 gate rows
+      if ((rc = make_tmap_2d_bf16(&tmWk, Whh_b, (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, 64, GP_BK))) return rc;
       if ((rc = make_tmap_2d_bf16(&tmAk, dgh_b, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d), GP_BK, GP_BM))) return rc;
       dim3 gk((unsigned)(d / KS_DJ), (unsigned)nbt);
       if (ks_st == 4) return launch_coop(gru_persist_bwd_ks_kernel<4>, tmAk, tmWk, prm, gk, ks_smem, s, "gru_persist_bwd_ks", KS);
@@ -1100,6 +1191,8 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
       return launch_coop(gru_persist_bwd_ks_kernel<2>, tmAk, tmWk, prm, gk, ks_smem, s, "gru_persist_bwd_ks", KS);
     }
   }
+  ARK_REQUIRE(WhhT_b, ARK_E_BADARG, "gru_persist_bwd: this shape runs the N-sliced kernel, which needs W_hh^T (WhhT_b)");
+  if ((rc = make_tmap_2d_bf16(&tmW, WhhT_b, (uint64_t)(3 * d), (uint64_t)d, (uint64_t)(3 * d), GP_BK, dj))) return rc;
   const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
 #define ARK_GP_BWD(DJ, ST)                                                                                              \
   if (dj == DJ && stages == ST) {                                                                                       \

@@ -319,13 +319,26 @@ class SailEngine:
             self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, tag="gru_gi",
                        bias=f.p(f"dec.gru.bias_ih_l{k}"))
             hp_b, y_b = new(N, d, dtype=bf), new(N, d, dtype=bf)
+            mask = None
             if persist:
-                # one cooperative launch for all L steps: W_hh slice resident in smem, state in registers
+                # one cooperative launch for all L steps: W_hh slice resident in smem, state in registers; the
+                # inter-layer dropout of the output rows (same Philox draw as the stand-alone kernel) is fused in
                 ops.cast_bf16(h0[:b0], hp_b[:b0])
                 gates = tuple(new(N, d, dtype=bf) for _ in range(4))
+                drop_k = dropout and self.p_drop > 0 and k < nl - 1
+                stride = (N * d + 3) // 4
+                if drop_k:
+                    mask = new(N, d, dtype=torch.uint8)
                 with self._timed("gru_persist_fwd", flops=2.0 * N * d * d3):
                     ops.gru_persist_fwd(hp_b, h0, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
-                                        lay.bt_dev, lay.off_dev, L, b0, d, y_b, gates, sync_ws)
+                                        lay.bt_dev, lay.off_dev, L, b0, d, y_b, gates, sync_ws, mask=mask,
+                                        p_drop=self.p_drop if drop_k else 0.0, seed=self.seed,
+                                        offset=self._drop_calls * stride if self._capturing else self.philox_offset,
+                                        offset_dev=self.dyn_i if (self._capturing and drop_k) else None)
+                if drop_k:
+                    if not self._capturing:
+                        self.philox_offset += stride
+                    self._drop_calls += 1
                 hp_f = None
             else:
                 hp_f = new(N, d)
@@ -336,8 +349,7 @@ class SailEngine:
                 with self._timed("gru_layer_fwd", flops=2.0 * N * d * d3):
                     ops.gru_layer_fwd(hp_b, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), gi, f.p(f"dec.gru.bias_hh_l{k}"),
                                       lay.bt, lay.off, L, d, y, y_b, gates, gh_ws, use_tc)
-            mask = None
-            if dropout and self.p_drop > 0 and k < nl - 1:
+            if dropout and self.p_drop > 0 and k < nl - 1 and not persist:
                 mask = new(N, d, dtype=torch.uint8)
                 if self._capturing:   # replayed graphs read the running Philox offset from device memory
                     ops.dropout_bf16(y_b, self.p_drop, self.seed, self._drop_calls * ((N * d + 3) // 4), y_b, mask,
@@ -417,19 +429,23 @@ class SailEngine:
             deferred.append(gru_weight_grads)
         else:
             dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
+            ks_bwd = persist and ops.gru_persist_bwd_ksplit(d, b0)    # K-split cluster kernel: W_hh untransposed
             if persist:
-                whh_t = new(d, d3, dtype=bf)
+                whh_t = None if ks_bwd else new(d, d3, dtype=bf)
             else:
                 dh_a, dh_b = new(b0, d), new(b0, d)
         for k in range(nl - 1, -1 if not wave else nl - 1, -1):
             u_in, hp_f, hp_b, gates, mask = saved[k]
-            if mask is not None:
+            if mask is not None and not persist:
                 ops.dropout_bwd(dy, mask, self.p_drop, dy)
             if persist:
-                ops.transpose_bf16(self._w(f"dec.gru.weight_hh_l{k}"), whh_t)
+                if not ks_bwd:
+                    ops.transpose_bf16(self._w(f"dec.gru.weight_hh_l{k}"), whh_t)
                 with self._timed("gru_persist_bwd", flops=2.0 * N * d * d3):
+                    # (the backward of the inter-layer dropout is applied to dy on the fly)
                     ops.gru_persist_bwd(dy, gates, hp_b, whh_t, lay.bt_dev, lay.off_dev, L, b0, d, dgi, dgh, dh0,
-                                        k != nl - 1, sync_ws)
+                                        k != nl - 1, sync_ws, Whh_b=self._w(f"dec.gru.weight_hh_l{k}") if ks_bwd else None,
+                                        dy_mask=mask, p_drop=self.p_drop if mask is not None else 0.0)
             else:
                 with self._timed("gru_layer_bwd", flops=2.0 * N * d * d3):
                     dh_k = ops.gru_layer_bwd(dy, gates, hp_f, self._w(f"dec.gru.weight_hh_l{k}"), lay.bt, lay.off, L, d,

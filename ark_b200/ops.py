@@ -232,23 +232,32 @@ def transpose_bf16(x, out):
     _C.lib().call("ark_transpose_bf16", _ptr(x, torch.bfloat16), R, C, _ptr(out, torch.bfloat16), _stream())
 
 
-def gru_persist_fwd(hp_b, h0, Whh_b, gi, b_hh, bt_dev, off_dev, L, bt0, d, y_b, gates, sync_ws):
+def gru_persist_fwd(hp_b, h0, Whh_b, gi, b_hh, bt_dev, off_dev, L, bt0, d, y_b, gates, sync_ws, mask=None, p_drop=0.0,
+                    seed=0, offset=0, offset_dev=None):
     r, z, n, ghn = gates if gates is not None else (None, None, None, None)
-    _contig(hp_b, h0, Whh_b, gi, y_b)
+    _contig(hp_b, h0, Whh_b, gi, y_b, mask)
     _C.lib().call("ark_gru_persist_fwd", _ptr(hp_b, torch.bfloat16), _ptr(h0, torch.float32), _ptr(Whh_b, torch.bfloat16),
                   _ptr(gi, torch.float32), _ptr(b_hh, torch.float32), _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32),
                   L, bt0, hp_b.shape[0], d, _ptr(y_b, torch.bfloat16), _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16),
-                  _ptr(n, torch.bfloat16), _ptr(ghn, torch.bfloat16), _ptr(sync_ws, torch.int32), _stream())
+                  _ptr(n, torch.bfloat16), _ptr(ghn, torch.bfloat16), _ptr(mask, torch.uint8), float(p_drop), int(seed),
+                  int(offset), _ptr(offset_dev, torch.int64), _ptr(sync_ws, torch.int32), _stream())
 
 
-def gru_persist_bwd(dy, gates, hp_b, WhhT_b, bt_dev, off_dev, L, bt0, d, dgi_b, dgh_b, dh0, accumulate, sync_ws):
+def gru_persist_bwd_ksplit(d, bt0) -> bool:
+    """True when the backward runs the K-split cluster kernel, which reads W_hh untransposed."""
+    return bool(_C.lib().raw("ark_gru_persist_bwd_ksplit")(int(d), int(bt0)))
+
+
+def gru_persist_bwd(dy, gates, hp_b, WhhT_b, bt_dev, off_dev, L, bt0, d, dgi_b, dgh_b, dh0, accumulate, sync_ws, Whh_b=None,
+                    dy_mask=None, p_drop=0.0):
     r, z, n, ghn = gates
-    _contig(dy, hp_b, WhhT_b, dgi_b, dgh_b, dh0)
+    _contig(dy, hp_b, WhhT_b, Whh_b, dgi_b, dgh_b, dh0, dy_mask)
     _C.lib().call("ark_gru_persist_bwd", _ptr(dy, torch.float32), _ptr(r, torch.bfloat16), _ptr(z, torch.bfloat16),
                   _ptr(n, torch.bfloat16), _ptr(ghn, torch.bfloat16), _ptr(hp_b, torch.bfloat16),
                   _ptr(WhhT_b, torch.bfloat16), _ptr(bt_dev, torch.int32), _ptr(off_dev, torch.int32), L, bt0,
                   hp_b.shape[0], d, _ptr(dgi_b, torch.bfloat16), _ptr(dgh_b, torch.bfloat16), _ptr(dh0, torch.float32),
-                  int(accumulate), _ptr(sync_ws, torch.int32), _stream())
+                  int(accumulate), _ptr(Whh_b, torch.bfloat16), _ptr(dy_mask, torch.uint8), float(p_drop),
+                  _ptr(sync_ws, torch.int32), _stream())
 
 
 def dropout_bf16(x, p, seed, offset, y, mask=None, offset_dev=None):

@@ -168,17 +168,26 @@ int ark_gru_layer_bwd(const float* dy, const float* r, const float* z, const flo
  * (d/slice) x ceil(bt0/128) grid does not fit the 148 SMs): callers then use ark_gru_layer_fwd/bwd. */
 int ark_gru_persist_supported(int64_t d, int64_t bt0);
 /* hp_b [N,d]: block 0 pre-filled with bf16(h0); blocks 1.. are written here.  h0 f32 [bt0,d].
- * gi f32 [N,3d]; outputs y_b and (optional, all or none) r,z,n,ghn bf16 [N,d]; sync_ws int32 [ceil(bt0/128)]. */
+ * gi f32 [N,3d]; outputs y_b and (optional, all or none) r,z,n,ghn bf16 [N,d]; sync_ws int32 [ceil(bt0/128)].
+ * p_drop > 0: y_b receives the layer output AFTER the inter-layer dropout (nn.GRU(dropout=p), models.py:121-127), drawn
+ * from the Philox stream of ark_dropout_bf16 (seed, offset [+ *offset_dev]) over the [N,d] tensor, keep mask -> mask
+ * u8 [N,d] (may be NULL); hp_b always holds the undropped state. */
 int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16_t* Whh_b, const float* gi, const float* b_hh,
                         const int32_t* bt_dev, const int32_t* off_dev, int64_t L, int64_t bt0, int64_t N, int64_t d,
                         uint16_t* y_b, uint16_t* r, uint16_t* z, uint16_t* n, uint16_t* ghn,
+                        uint8_t* mask, float p_drop, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
                         int32_t* sync_ws, void* stream);
-/* WhhT_b = W_hh^T bf16 [d,3d] (ark_transpose_bf16).  dy f32 [N,d].  Writes dgi_b/dgh_b bf16 [N,3d] and
- * dh0 f32 [bt0,d] (+= when dh0_accumulate != 0). */
+/* dy f32 [N,d].  Writes dgi_b/dgh_b bf16 [N,3d] and dh0 f32 [bt0,d] (+= when dh0_accumulate != 0).
+ * Weights: WhhT_b = W_hh^T bf16 [d,3d] (ark_transpose_bf16) for the N-sliced kernel; Whh_b = W_hh bf16 [3d,d] itself for
+ * the K-split cluster kernel (ark_gru_persist_bwd_ksplit(d, bt0) != 0: d >= 512, d % 256 == 0 — it consumes the weights
+ * untransposed, so callers may pass WhhT_b = NULL there).  dy_mask (u8 [N,d] keep mask of the forward dropout of this
+ * layer's output, NULL = none) with p_drop: dy is multiplied by keep/(1-p) on the fly (replaces ark_dropout_bwd). */
+int ark_gru_persist_bwd_ksplit(int64_t d, int64_t bt0);
 int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uint16_t* z, const uint16_t* n, const uint16_t* ghn,
                         const uint16_t* hp_b, const uint16_t* WhhT_b, const int32_t* bt_dev, const int32_t* off_dev,
                         int64_t L, int64_t bt0, int64_t N, int64_t d, uint16_t* dgi_b, uint16_t* dgh_b,
-                        float* dh0, int dh0_accumulate, int32_t* sync_ws, void* stream);
+                        float* dh0, int dh0_accumulate, const uint16_t* Whh_b, const uint8_t* dy_mask, float p_drop,
+                        int32_t* sync_ws, void* stream);
 /* Wavefront GRU STACK (ark_b200/csrc/gru_wave.cu): all nl layers x L steps of nn.GRU (models.py:121-127,141;
  * decoder-only :329-343) in ONE cooperative launch per direction; layer k step t runs as soon as layer k-1 step t
  * and layer k step t-1 are done (L+nl-1 dependent steps instead of nl*L).  The input projections W_ih u_t run

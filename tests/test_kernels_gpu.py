@@ -442,7 +442,7 @@ def test_gru_persist_fwd_bwd_matches_torch(d, lens):
     dgi = torch.empty(N, 3 * d, device=DEV, dtype=bf)
     dgh = torch.empty(N, 3 * d, device=DEV, dtype=bf)
     dh0 = torch.full((B, d), 7.0, device=DEV)
-    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0, False, sync)
+    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0, False, sync, Whh_b=Wb)
     torch.cuda.synchronize()
     assert _rel(dh0, h0.grad) < 3e-2
     assert _rel(dgi.float() @ Wih, x.grad[bi, ti]) < 3e-2
@@ -450,5 +450,26 @@ def test_gru_persist_fwd_bwd_matches_torch(d, lens):
     assert _rel(dgh.float().t() @ hp_b.float(), gru.weight_hh_l0.grad) < 3e-2
     # accumulate mode adds to what is there
     dh0b = dh0.clone()
-    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0b, True, sync)
+    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0b, True, sync, Whh_b=Wb)
     torch.testing.assert_close(dh0b, 2 * dh0, rtol=1e-5, atol=1e-6)
+    if d >= 512:     # both backward kernels (K-split clusters with untransposed W_hh / N-sliced with W_hh^T) agree
+        assert ops.gru_persist_bwd_ksplit(d, B)
+        dgi2, dgh2, dh02 = torch.empty_like(dgi), torch.empty_like(dgh), torch.empty_like(dh0)
+        ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi2, dgh2, dh02, False, sync)   # no Whh_b -> N-sliced
+        assert _rel(dgh2, dgh) < 5e-3 and _rel(dgi2, dgi) < 5e-3 and _rel(dh02, dh0) < 5e-3
+    # fused inter-layer dropout == the stand-alone kernels with the same Philox stream
+    y_d, mask = torch.empty_like(y_b), torch.empty(N, d, device=DEV, dtype=torch.uint8)
+    hp2 = hp_b.clone()
+    ops.gru_persist_fwd(hp2, h0.detach().contiguous(), Wb, gi, gru.bias_hh_l0.detach(), bt_d, off_d, L, B, d, y_d,
+                        gates, sync, mask=mask, p_drop=0.25, seed=77, offset=1000)
+    y_ref2, mask_ref = torch.empty_like(y_b), torch.empty_like(mask)
+    ops.dropout_bf16(y_b, 0.25, 77, 1000, y_ref2, mask_ref)
+    assert torch.equal(mask, mask_ref) and torch.equal(y_d, y_ref2) and torch.equal(hp2, hp_b)
+    dy_m = torch.empty_like(dy)
+    ops.dropout_bwd(dy, mask, 0.25, dy_m)
+    dgi_a, dgh_a, dh0_a = torch.empty_like(dgi), torch.empty_like(dgh), torch.empty_like(dh0)
+    dgi_b_, dgh_b_, dh0_b_ = torch.empty_like(dgi), torch.empty_like(dgh), torch.empty_like(dh0)
+    ops.gru_persist_bwd(dy_m, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi_a, dgh_a, dh0_a, False, sync, Whh_b=Wb)
+    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi_b_, dgh_b_, dh0_b_, False, sync, Whh_b=Wb,
+                        dy_mask=mask, p_drop=0.25)
+    assert torch.equal(dgi_a, dgi_b_) and torch.equal(dgh_a, dgh_b_) and torch.equal(dh0_a, dh0_b_)

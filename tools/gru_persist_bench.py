@@ -39,7 +39,7 @@ def fwd():
 
 
 def bwd():
-    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0, False, sync)
+    ops.gru_persist_bwd(dy, gates, hp_b, WT, bt_d, off_d, L, B, d, dgi, dgh, dh0, False, sync, Whh_b=Wb)
 
 
 def timeit(fn, n=50):
