@@ -111,13 +111,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
         int m0, n0;
         tile_origin(tile, m0, n0);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+          ptx::mbar_wait(&empty_bar[s], ph);
           uint8_t* a_s = smem + s * L::STAGE_BYTES;
           uint8_t* b_s = a_s + L::A_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
@@ -142,7 +142,18 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int it = 0, lt = 0;
+      // The issue loop of this ONE thread is the tensor pipe's feeder: measured (tools/probe_mma_rate.cu) a
+      // 128 x 128 x 16 MMA retires every 64 cycles, but with the descriptors rebuilt from the address for every
+      // instruction the loop issued one only every ~100.  So: descriptors of stage 0 are built once; a stage / k-step
+      // is an ADD on the 14-bit (address >> 4) field (shared-memory addresses < 256 KB never carry out of it).
+      // K-major: a k-step is 32 B along the swizzled 128 B row; MN-major: 16 k-rows of 128 B = 2048 B.
+      const uint32_t a_addr0 = ptx::smem_u32(smem);
+      const uint64_t adesc0 = A_MN ? ptx::make_smem_desc_sw128(a_addr0, TC_BK * 128, 1024) : ptx::make_smem_desc_sw128(a_addr0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc_sw128(a_addr0 + L::A_BYTES, TC_BK * 128, 1024)
+                                   : ptx::make_smem_desc_sw128(a_addr0 + L::A_BYTES, 16, 1024);
+      constexpr uint64_t A_STEP = (A_MN ? 2048 : 32) >> 4, B_STEP = (B_MN ? 2048 : 32) >> 4, S_STEP = L::STAGE_BYTES >> 4;
+      int lt = 0, s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step, ++lt) {
         const int acc = PERSIST ? (lt & 1) : 0;
         if (PERSIST) {   // the epilogue must have drained this accumulator (2 tiles ago)
@@ -150,23 +161,15 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
           ptx::tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
+          const uint64_t ad = adesc0 + (uint64_t)s * S_STEP, bd = bdesc0 + (uint64_t)s * S_STEP;
+          ptx::umma_f16(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < TC_BK / 16; ++kk) {
-            // K-major: 16 bf16 = 32 B further along the swizzled 128 B row; rows of 8 are 1024 B apart.
-            // MN-major: 16 k-rows of 128 B = 2048 B further; 64-element MN groups are TC_BK*128 B apart.
-            const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(a_addr + kk * 2048, TC_BK * 128, 1024)
-                                        : ptx::make_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(b_addr + kk * 2048, TC_BK * 128, 1024)
-                                        : ptx::make_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
-          }
+          for (int kk = 1; kk < TC_BK / 16; ++kk) ptx::umma_f16_acc(d_tmem, ad + kk * A_STEP, bd + kk * B_STEP, idesc);
           ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(&tmem_full_bar[acc]);
       }

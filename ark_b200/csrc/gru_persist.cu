@@ -24,6 +24,7 @@
 #include "philox.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <vector>
 
 namespace ark {
 
@@ -173,11 +174,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_kernel(const __
           ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
           if (kc == 0) gp_dbg(p.dbg, t, 2);
           ptx::tc_fence_after();
+{   // descriptors built once per chunk, a k-step is an ADD on the (address >> 4) field (see gemm_tc.cu)
+            const uint64_t ad = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES, 16, 1024);
+            const uint64_t bd = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128), 16, 1024);
+            ptx::umma_f16(tmem_base, ad, bd, idesc, kc != 0 ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < GP_BK / 16; ++kk) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES + kk * 32, 16, 1024);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128) + kk * 32, 16, 1024);
-            ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+            for (int kk = 1; kk < GP_BK / 16; ++kk) ptx::umma_f16_acc(tmem_base, ad + kk * 2, bd + kk * 2, idesc);
           }
           if (CS == 1) ptx::umma_commit(&empty_bar[s]);
           else ptx::umma_commit_mc(&empty_bar[s], MC_MASK);
@@ -419,11 +421,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_kernel(const __
           ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
           if (kc == 0) gp_dbg(p.dbg, nm, 2);
           ptx::tc_fence_after();
+{   // descriptors built once per chunk, a k-step is an ADD on the (address >> 4) field (see gemm_tc.cu)
+            const uint64_t ad = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES, 16, 1024);
+            const uint64_t bd = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128), 16, 1024);
+            ptx::umma_f16(tmem_base, ad, bd, idesc, kc != 0 ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < GP_BK / 16; ++kk) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES + kk * 32, 16, 1024);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128) + kk * 32, 16, 1024);
-            ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+            for (int kk = 1; kk < GP_BK / 16; ++kk) ptx::umma_f16_acc(tmem_base, ad + kk * 2, bd + kk * 2, idesc);
           }
           if (CS == 1) ptx::umma_commit(&empty_bar[s]);
           else ptx::umma_commit_mc(&empty_bar[s], MC_MASK);
@@ -689,12 +692,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
           ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
           if (kc == 0) gp_dbg(p.dbg, nm, 2);
           ptx::tc_fence_after();
+{   // descriptors built once per chunk, a k-step is an ADD on the (address >> 4) field (see gemm_tc.cu)
+            const uint64_t ad = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES, 16, 1024);
+            const uint64_t bd = ptx::make_smem_desc_sw128(w_addr + kc * (KS_NC * 128), GP_BK * 128, 1024);
+            ptx::umma_f16(tmem_base, ad, bd, idesc, kc != 0 ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < GP_BK / 16; ++kk) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr0 + s * GP_A_BYTES + kk * 32, 16, 1024);
-            // MN-major: 16 k-rows of 128 B = 2048 B further per UMMA k-step (same form as gemm_tc's B_MN operand)
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(w_addr + kc * (KS_NC * 128) + kk * 2048, GP_BK * 128, 1024);
-            ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
+            for (int kk = 1; kk < GP_BK / 16; ++kk) ptx::umma_f16_acc(tmem_base, ad + kk * 2, bd + kk * 128, idesc);
           }
           ptx::umma_commit(&empty_bar[s]);
         }
@@ -865,6 +868,524 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_kernel(const
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// =====================================================================================================
+// HALF-TILE variants (d = 1024-class layers): two independent recurrence chains per CTA
+// =====================================================================================================
+// Timeline of the kernels above at d = 1024, B = 256 (tools/gru_persist_bench.py): a forward step is 13 300 cycles of
+// which only ~4 400 stream the A operand; the rest is a chain of latencies — counter observed -> first TMA byte
+// (2 000), MMA tail (1 300), TMEM drain + gate math (2 100), release fence (1 350), counter propagation to the
+// slowest CTA (1 600+) — during which the TMA and tensor pipes of the SM idle.  The 128 rows of a batch tile are
+// independent graphs, so each CTA now runs TWO chains, the 64-row halves of its tile, with their own counters and
+// TMEM accumulators: while half 0 sits in its release/propagation/latency window the CTA loads, multiplies and
+// finishes half 1, and vice versa.  Bytes per CTA are unchanged; a step of both halves costs about one chain latency
+// (~9 000 cycles) instead of latency + stream.
+// The MMAs are M = 64 instructions (half the shared-memory operand traffic of an M = 128 one: measured, the MMA phase
+// of a step is bound by the ~64 B/clk at which the tensor core reads its smem operands, 92 cycles per 128 x 48 x 16
+// MMA).  Their accumulator layout (tools/probe_m64.cu): row i of the 64 lives in TMEM lane (i % 16) + 32 * (i / 16),
+// i.e. each of the four lane quadrants holds 16 rows in its lanes 0..15.
+constexpr int H2_ROWS = 64;
+constexpr int H2_A_BYTES = H2_ROWS * GP_BK * 2;     // 8 KB per ring stage
+
+template <int STAGES>
+__global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_fwd_h2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                           const __grid_constant__ CUtensorMap tmW,
+                                                                           const GruPersistFwdParams p) {
+  constexpr int DJ = 16, NROWS = 3 * DJ, ACC_LD = NROWS + 1;
+  constexpr uint32_t TMEM_COLS = 128;          // two [128 x 48] accumulators at columns 0 and 64
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.d, L = p.L;
+  const int nkc = d / GP_BK;
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + 3 * DJ * d * 2;
+  float* acc_sm = reinterpret_cast<float*>(a_sm + (STAGES + 1) * H2_A_BYTES);   // [64][ACC_LD]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc_sm + H2_ROWS * ACC_LD + 1);
+  full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~(uintptr_t)7);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* w_bar = empty_bar + STAGES;
+  uint64_t* tmem_full_bar = w_bar + 1;         // [2]: one per half
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ji = blockIdx.x, bi = blockIdx.y, ns = gridDim.x;
+  const int j0 = ji * DJ, m0 = bi * GP_BM;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::mbar_init(&tmem_full_bar[0], 1);
+    ptx::mbar_init(&tmem_full_bar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(3 * DJ * d * 2));
+      for (int kc = 0; kc < nkc; ++kc)
+        for (int g = 0; g < 3; ++g)
+          ptx::tma_load_2d(w_sm + kc * (NROWS * 128) + g * (DJ * 128), &tmW, w_bar, kc * GP_BK, g * d + j0);
+      int it = 0;
+      for (int t = 0; t < L; ++t) {
+        if (m0 >= p.bt[t]) break;
+        for (int h = 0; h < 2; ++h) {
+          const int mh = m0 + h * H2_ROWS;
+          if (mh >= p.bt[t]) continue;
+          if (t > 0) wait_counter(p.sync + 2 * bi + h, t * ns);   // every slice of this half's h_{t-1} is in global memory
+          if (h == 0) gp_dbg(p.dbg, t, 0);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const int row0 = p.off[t] + mh;
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % STAGES;
+            ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[s], H2_A_BYTES);
+            ptx::tma_load_2d(a_sm + s * H2_A_BYTES, &tmA, &full_bar[s], kc * GP_BK, row0);
+          }
+          if (h == 0) gp_dbg(p.dbg, t, 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(H2_ROWS, NROWS, 0, 0);
+      ptx::mbar_wait(w_bar, 0);
+      const uint32_t w_addr = ptx::smem_u32(w_sm), a_addr0 = ptx::smem_u32(a_sm);
+      int it = 0;
+      for (int t = 0; t < L; ++t) {
+        if (m0 >= p.bt[t]) break;
+        for (int h = 0; h < 2; ++h) {
+          if (m0 + h * H2_ROWS >= p.bt[t]) continue;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(h * 64);
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % STAGES;
+            ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+            if (kc == 0 && h == 0) gp_dbg(p.dbg, t, 2);
+            ptx::tc_fence_after();
+{   // descriptors built once per chunk, a k-step is an ADD on the (address >> 4) field (see gemm_tc.cu)
+              const uint64_t ad = ptx::make_smem_desc_sw128(a_addr0 + s * H2_A_BYTES, 16, 1024);
+              const uint64_t bd = ptx::make_smem_desc_sw128(w_addr + kc * (NROWS * 128), 16, 1024);
+              ptx::umma_f16(d_tmem, ad, bd, idesc, kc != 0 ? 1u : 0u);
+#pragma unroll
+              for (int kk = 1; kk < GP_BK / 16; ++kk) ptx::umma_f16_acc(d_tmem, ad + kk * 2, bd + kk * 2, idesc);
+            }
+            ptx::umma_commit(&empty_bar[s]);
+          }
+          ptx::umma_commit(&tmem_full_bar[h]);
+          if (h == 0) gp_dbg(p.dbg, t, 3);
+        }
+      }
+    }
+  } else {
+    // epilogue: warps 2..5 drain the 16 rows held by lanes 0..15 of their TMEM lane quadrant (M = 64 layout); then the
+    // 256 threads take one (row, 4-unit group) item each
+    constexpr int G = DJ / 4;
+    const int q = warp & 3;
+    const int tid = threadIdx.x - 64;            // 0..255
+    const bool drainer = warp < 6;
+    const int bl = tid / G, jl = (tid % G) * 4;  // this thread's row (of a half) and unit group
+    const int64_t d3 = 3 * (int64_t)d;
+    const int bt0 = p.bt[0];
+    float hreg[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = m0 + h * H2_ROWS + bl;
+      const float4 hv = (b < bt0) ? *reinterpret_cast<const float4*>(p.h0 + (int64_t)b * d + j0 + jl) : make_float4(0, 0, 0, 0);
+      hreg[h][0] = hv.x; hreg[h][1] = hv.y; hreg[h][2] = hv.z; hreg[h][3] = hv.w;
+    }
+    const bool drop = p.p_drop > 0.f;
+    const float drop_scale = drop ? 1.f / (1.f - p.p_drop) : 1.f;
+    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    const uint64_t ctr0 = p.offset + (p.offset_dev ? *p.offset_dev : 0ull);
+    const float4 b_r = __ldg(reinterpret_cast<const float4*>(p.b_hh + j0 + jl));
+    const float4 b_z = __ldg(reinterpret_cast<const float4*>(p.b_hh + d + j0 + jl));
+    const float4 b_n = __ldg(reinterpret_cast<const float4*>(p.b_hh + 2 * d + j0 + jl));
+    const float br[4] = {b_r.x, b_r.y, b_r.z, b_r.w}, bz[4] = {b_z.x, b_z.y, b_z.z, b_z.w};
+    const float bn[4] = {b_n.x, b_n.y, b_n.z, b_n.w};
+    float4 gpre[2][3];
+    auto prefetch_gi = [&](int t, int h) {
+      const int mh = m0 + h * H2_ROWS;
+      if (mh + bl < p.bt[t]) {
+        const float* gp = p.gi + ((int64_t)p.off[t] + mh + bl) * d3 + j0 + jl;
+        gpre[h][0] = *reinterpret_cast<const float4*>(gp);
+        gpre[h][1] = *reinterpret_cast<const float4*>(gp + d);
+        gpre[h][2] = *reinterpret_cast<const float4*>(gp + 2 * d);
+      }
+    };
+    if (m0 < bt0) prefetch_gi(0, 0);
+    if (m0 + H2_ROWS < bt0) prefetch_gi(0, 1);
+    for (int t = 0; t < L; ++t) {
+      const int Bt = p.bt[t];
+      if (m0 >= Bt) break;
+      const int Bn = (t + 1 < L) ? p.bt[t + 1] : 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int mh = m0 + h * H2_ROWS;
+        if (mh >= Bt) continue;
+        const int64_t base = (int64_t)p.off[t] + mh;
+        const int64_t base_n = (t + 1 < L) ? (int64_t)p.off[t + 1] + mh : 0;
+        ptx::mbar_wait(&tmem_full_bar[h], t & 1);
+        if (tid == 0 && h == 0) gp_dbg(p.dbg, t, 4);
+        ptx::tc_fence_after();
+        if (drainer && mh + q * 16 < Bt) {
+          const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 64);
+          float* dst = acc_sm + (q * 16 + (lane & 15)) * ACC_LD;
+#pragma unroll
+          for (int c = 0; c < NROWS; c += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
+            ptx::tmem_ld_wait();
+            if (lane < 16) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) dst[c + k] = __uint_as_float(v[k]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        gp_bar_sync();
+        if (tid == 0 && h == 0) gp_dbg(p.dbg, t, 5);
+        const int b = mh + bl;
+        float o_r[4], o_z[4], o_n[4], o_g[4];
+        if (b < Bt) {
+          const float* ap = acc_sm + bl * ACC_LD + jl;
+          const float gr[4] = {gpre[h][0].x, gpre[h][0].y, gpre[h][0].z, gpre[h][0].w};
+          const float gz[4] = {gpre[h][1].x, gpre[h][1].y, gpre[h][1].z, gpre[h][1].w};
+          const float gn[4] = {gpre[h][2].x, gpre[h][2].y, gpre[h][2].z, gpre[h][2].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const GruFwd o = gru_fwd_math_fast(gr[k], gz[k], gn[k], ap[k] + br[k], ap[DJ + k] + bz[k],
+                                               ap[2 * DJ + k] + bn[k], hreg[h][k]);
+            hreg[h][k] = o.h;
+            o_r[k] = o.r; o_z[k] = o.z; o_n[k] = o.n; o_g[k] = o.ghn;
+          }
+          if (b < Bn) st4_bf16(p.hp_b + (base_n + bl) * d + j0 + jl, hreg[h]);   // the only store on the chain
+        }
+        gp_bar_sync();                             // the chain's stores are issued (and acc_sm is free again)
+        if (tid == 0 && h == 0) gp_dbg(p.dbg, t, 6);
+        if (tid == 0) red_release_add(p.sync + 2 * bi + h, 1);
+        if (tid == 0 && h == 0) gp_dbg(p.dbg, t, 7);
+        if (b < Bt) {
+          const int64_t o = (base + bl) * d + j0 + jl;
+          if (drop) {   // same draw as dropout_bf16_kernel over the [N, d] output of this layer
+            const uint64_t c = ctr0 + (uint64_t)(o >> 2);
+            const uint4 rn = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+            const uint32_t rr[4] = {rn.x, rn.y, rn.z, rn.w};
+            float yo[4];
+            uint32_t mk = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const bool keep = (float)(rr[k] >> 8) * (1.f / 16777216.f) >= p.p_drop;
+              mk |= (keep ? 1u : 0u) << (8 * k);
+              yo[k] = keep ? bf16_bits_to_f32(f32_to_bf16_bits(hreg[h][k])) * drop_scale : 0.f;
+            }
+            if (p.mask) *reinterpret_cast<uint32_t*>(p.mask + o) = mk;
+            st4_bf16(p.y_b + o, yo);
+          } else {
+            st4_bf16(p.y_b + o, hreg[h]);
+          }
+          if (p.r) {
+            st4_bf16(p.r + o, o_r);
+            st4_bf16(p.z + o, o_z);
+            st4_bf16(p.n + o, o_n);
+            st4_bf16(p.ghn + o, o_g);
+          }
+        }
+        if (t + 1 < L && mh < Bn) prefetch_gi(t + 1, h);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// K-split backward with half tiles: as gru_persist_bwd_ks_kernel, two chains per CTA.  The [128 x 16] partial blocks
+// are exchanged per half (rows 64h..64h+63 of a block are contiguous: one 4 KB bulk copy per peer), each half has its
+// own part_bar.
+template <int STAGES>
+__global__ void __launch_bounds__(GP_THREADS, 1) gru_persist_bwd_ks_h2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                              const __grid_constant__ CUtensorMap tmW,
+                                                                              const GruPersistBwdParams p) {
+  constexpr int DJ = KS_DJ;
+  constexpr uint32_t TMEM_COLS = 128;          // two [128 x 64] accumulators
+  constexpr int HBLK = KS_BLK / 2;             // bytes of half a partial block (64 rows x 16 fp32)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int d = p.d, L = p.L;
+  const int kq = 3 * d / KS;
+  const int nkc = kq / GP_BK;
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = w_sm + nkc * (KS_NC * 128);
+  float* send_sm = reinterpret_cast<float*>(a_sm + (STAGES + 1) * H2_A_BYTES);
+  float* part_sm = send_sm + KS * (KS_BLK / 4);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(part_sm + KS * (KS_BLK / 4));
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* w_bar = empty_bar + STAGES;
+  uint64_t* tmem_full_bar = w_bar + 1;         // [2]
+  uint64_t* part_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(part_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bi = blockIdx.y, ns = gridDim.x;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const int jc0 = ((int)blockIdx.x / KS) * KS_NC;
+  const int j0 = jc0 + (int)crank * DJ;
+  const int k0 = (int)crank * kq;
+  const int m0 = bi * GP_BM;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(w_bar, 1);
+    for (int h = 0; h < 2; ++h) {
+      ptx::mbar_init(&tmem_full_bar[h], 1);
+      ptx::mbar_init(&part_bar[h], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // iterations t = L-1 .. -1 of half h (rows m0 + 64h ..): active while the half has rows at step max(t, 0)
+  auto half_active = [&](int t, int h) { return m0 + h * H2_ROWS < p.bt[t < 0 ? 0 : t]; };
+  auto has_mma = [&](int t, int h) { return (t + 1 <= L - 1) && (m0 + h * H2_ROWS < p.bt[t + 1]); };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(nkc * KS_NC * 128));
+      for (int kc = 0; kc < nkc; ++kc)
+        ptx::tma_load_2d(w_sm + kc * (KS_NC * 128), &tmW, w_bar, jc0, k0 + kc * GP_BK);
+      int it = 0, done[2] = {0, 0};
+      for (int t = L - 1; t >= -1; --t) {
+        for (int h = 0; h < 2; ++h) {
+          if (!half_active(t, h)) continue;
+          if (has_mma(t, h)) {
+            wait_counter(p.sync + 2 * bi + h, done[h] * ns);
+            if (h == 0) gp_dbg(p.dbg, done[0], 0);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            const int row0 = p.off[t + 1] + m0 + h * H2_ROWS;
+            for (int kc = 0; kc < nkc; ++kc, ++it) {
+              const int s = it % STAGES;
+              ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+              ptx::mbar_arrive_expect_tx(&full_bar[s], H2_A_BYTES);
+              ptx::tma_load_2d(a_sm + s * H2_A_BYTES, &tmA, &full_bar[s], k0 + kc * GP_BK, row0);
+            }
+            if (h == 0) gp_dbg(p.dbg, done[0], 1);
+          }
+          ++done[h];
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(H2_ROWS, KS_NC, 0, 1);
+      ptx::mbar_wait(w_bar, 0);
+      const uint32_t w_addr = ptx::smem_u32(w_sm), a_addr0 = ptx::smem_u32(a_sm);
+      int it = 0, nm0 = 0;
+      for (int t = L - 1; t >= -1; --t) {
+        for (int h = 0; h < 2; ++h) {
+          if (!half_active(t, h) || !has_mma(t, h)) continue;
+          if (h == 0) ++nm0;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(h * 64);
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % STAGES;
+            ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+            if (kc == 0 && h == 0) gp_dbg(p.dbg, nm0, 2);
+            ptx::tc_fence_after();
+{   // descriptors built once per chunk, a k-step is an ADD on the (address >> 4) field (see gemm_tc.cu)
+              const uint64_t ad = ptx::make_smem_desc_sw128(a_addr0 + s * H2_A_BYTES, 16, 1024);
+              const uint64_t bd = ptx::make_smem_desc_sw128(w_addr + kc * (KS_NC * 128), GP_BK * 128, 1024);
+              ptx::umma_f16(d_tmem, ad, bd, idesc, kc != 0 ? 1u : 0u);
+#pragma unroll
+              for (int kk = 1; kk < GP_BK / 16; ++kk) ptx::umma_f16_acc(d_tmem, ad + kk * 2, bd + kk * 128, idesc);
+            }
+            ptx::umma_commit(&empty_bar[s]);
+          }
+          ptx::umma_commit(&tmem_full_bar[h]);
+          if (h == 0) gp_dbg(p.dbg, nm0, 3);
+        }
+      }
+    }
+  } else {
+    constexpr int G = DJ / 4;
+    const int q = warp & 3;
+    const int tid = threadIdx.x - 64;            // 0..255: one (row, 4-unit group) item per half
+    const bool drainer = warp < 6;               // M = 64 accumulator: 16 rows in lanes 0..15 of every lane quadrant
+    const int bl = tid / G, g4 = tid % G, jl = g4 * 4;
+    const int64_t d3 = 3 * (int64_t)d;
+    float carry[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) carry[h][k] = 0.f;
+    float4 dyp[2];
+    uint2 sp[2][5];
+    auto prefetch = [&](int t, int h) {
+      const int mh = m0 + h * H2_ROWS;
+      if (mh + bl < p.bt[t]) {
+        const int64_t o = ((int64_t)p.off[t] + mh + bl) * d + j0 + jl;
+        dyp[h] = *reinterpret_cast<const float4*>(p.dy + o);
+        if (p.dy_mask) {
+          const uint32_t mk = *reinterpret_cast<const uint32_t*>(p.dy_mask + o);
+          dyp[h].x = (mk & 0xFFu) ? dyp[h].x * p.dy_scale : 0.f;
+          dyp[h].y = (mk & 0xFF00u) ? dyp[h].y * p.dy_scale : 0.f;
+          dyp[h].z = (mk & 0xFF0000u) ? dyp[h].z * p.dy_scale : 0.f;
+          dyp[h].w = (mk & 0xFF000000u) ? dyp[h].w * p.dy_scale : 0.f;
+        }
+        sp[h][0] = *reinterpret_cast<const uint2*>(p.r + o);
+        sp[h][1] = *reinterpret_cast<const uint2*>(p.z + o);
+        sp[h][2] = *reinterpret_cast<const uint2*>(p.n + o);
+        sp[h][3] = *reinterpret_cast<const uint2*>(p.ghn + o);
+        sp[h][4] = *reinterpret_cast<const uint2*>(p.hp_b + o);
+      }
+    };
+    int t_first[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      t_first[h] = L - 1;
+      while (t_first[h] >= 0 && !half_active(t_first[h], h)) --t_first[h];
+      if (t_first[h] >= 0) prefetch(t_first[h], h);
+    }
+    int n_mma[2] = {0, 0};
+    const uint32_t part_bar_a[2] = {ptx::smem_u32(&part_bar[0]), ptx::smem_u32(&part_bar[1])};
+    for (int t = L - 1; t >= -1; --t) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (t > t_first[h] || !half_active(t, h)) continue;
+        const int mh = m0 + h * H2_ROWS;
+        const bool mma = has_mma(t, h);
+        const int B_next = (t + 1 <= L - 1) ? p.bt[t + 1] : 0;
+        const int Bt = p.bt[t < 0 ? 0 : t];
+        if (mma) {
+          ptx::mbar_wait(&tmem_full_bar[h], n_mma[h] & 1);
+          ptx::tc_fence_after();
+          ++n_mma[h];
+          if (tid == 0 && h == 0) gp_dbg(p.dbg, n_mma[0], 4);
+          if (drainer) {
+            const int row = h * H2_ROWS + q * 16 + (lane & 15);    // row of the full [128 x 16] block
+            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 64);
+#pragma unroll
+            for (int dst = 0; dst < KS; ++dst) {
+              uint32_t v[16];
+              ptx::tmem_ld_32x32b_x16(t_lane + (uint32_t)(dst * DJ), v);
+              ptx::tmem_ld_wait();
+              float* blk = send_sm + dst * (KS_BLK / 4);
+              if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  *reinterpret_cast<uint4*>(blk + ks_chunk_off(row, c)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          gp_bar_sync();
+          if (tid == 0) {
+            ptx::mbar_arrive_expect_tx(&part_bar[h], (uint32_t)((KS - 1) * HBLK));
+#pragma unroll
+            for (int o = 1; o < KS; ++o) {
+              const uint32_t dst = (crank + (uint32_t)o) % KS;
+              ptx::bulk_copy_s2c(ptx::mapa_u32(ptx::smem_u32(part_sm + crank * (KS_BLK / 4) + h * (HBLK / 4)), dst),
+                                 ptx::smem_u32(send_sm + dst * (KS_BLK / 4) + h * (HBLK / 4)), (uint32_t)HBLK,
+                                 ptx::mapa_u32(part_bar_a[h], dst));
+            }
+          }
+          ptx::mbar_wait_cluster(&part_bar[h], (n_mma[h] - 1) & 1);
+          if (tid == 0 && h == 0) gp_dbg(p.dbg, n_mma[0], 5);
+        }
+        const int64_t base = (t >= 0) ? (int64_t)p.off[t] + mh : 0;
+        const int b = mh + bl;
+        const bool live = b < Bt;
+        float dar[4], daz[4], dan[4];
+        if (live) {
+          const bool from_next = b < B_next;
+          float dh[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dh[k] = from_next ? carry[h][k] : 0.f;
+          if (from_next && mma) {
+            const int o4 = ks_chunk_off(h * H2_ROWS + bl, g4);
+#pragma unroll
+            for (int src = 0; src < KS; ++src) {
+              const float* blk = (src == (int)crank) ? send_sm + crank * (KS_BLK / 4) : part_sm + src * (KS_BLK / 4);
+              const float4 v = *reinterpret_cast<const float4*>(blk + o4);
+              dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
+            }
+          }
+          if (t < 0) {
+            float* o = p.dh0 + (int64_t)b * d + j0 + jl;
+            float4 v = make_float4(dh[0], dh[1], dh[2], dh[3]);
+            if (p.dh0_accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(o);
+              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+            }
+            *reinterpret_cast<float4*>(o) = v;
+          } else {
+            const float dyv[4] = {dyp[h].x, dyp[h].y, dyp[h].z, dyp[h].w};
+            float r[4], z[4], n[4], g[4], hp[4];
+            {
+              float2 a, c2;
+              a = unpack_bf16x2(sp[h][0].x); c2 = unpack_bf16x2(sp[h][0].y); r[0] = a.x; r[1] = a.y; r[2] = c2.x; r[3] = c2.y;
+              a = unpack_bf16x2(sp[h][1].x); c2 = unpack_bf16x2(sp[h][1].y); z[0] = a.x; z[1] = a.y; z[2] = c2.x; z[3] = c2.y;
+              a = unpack_bf16x2(sp[h][2].x); c2 = unpack_bf16x2(sp[h][2].y); n[0] = a.x; n[1] = a.y; n[2] = c2.x; n[3] = c2.y;
+              a = unpack_bf16x2(sp[h][3].x); c2 = unpack_bf16x2(sp[h][3].y); g[0] = a.x; g[1] = a.y; g[2] = c2.x; g[3] = c2.y;
+              a = unpack_bf16x2(sp[h][4].x); c2 = unpack_bf16x2(sp[h][4].y); hp[0] = a.x; hp[1] = a.y; hp[2] = c2.x; hp[3] = c2.y;
+            }
+            float danr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const GruBwd w = gru_bwd_math(dh[k] + dyv[k], r[k], z[k], n[k], g[k], hp[k]);
+              dar[k] = w.dar; daz[k] = w.daz; dan[k] = w.dan; danr[k] = w.dan_r;
+              carry[h][k] = w.dh_prev;
+            }
+            const int64_t o3 = (base + bl) * d3 + j0 + jl;
+            st4_bf16(p.dgh_b + o3, dar);                    // dgh_t: the next iteration's A operand, on the chain
+            st4_bf16(p.dgh_b + o3 + d, daz);
+            st4_bf16(p.dgh_b + o3 + 2 * d, danr);
+          }
+        }
+        gp_bar_sync();
+        if (tid == 0 && h == 0) gp_dbg(p.dbg, n_mma[0], 6);
+        if (tid == 0) red_release_add(p.sync + 2 * bi + h, 1);
+        if (tid == 0 && h == 0) gp_dbg(p.dbg, n_mma[0], 7);
+        if (live && t >= 0) {
+          const int64_t o3 = (base + bl) * d3 + j0 + jl;
+          st4_bf16(p.dgi_b + o3, dar);
+          st4_bf16(p.dgi_b + o3 + d, daz);
+          st4_bf16(p.dgi_b + o3 + 2 * d, dan);
+        }
+        if (t - 1 >= 0) prefetch(t - 1, h);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // [R, C] bf16 -> [C, R] bf16 (W_hh^T for the backward kernel; 32x32 tiles through padded smem)
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const uint16_t* __restrict__ in, int R, int C,
                                                              uint16_t* __restrict__ out) {
@@ -1020,6 +1541,77 @@ static int pick_cluster(Kern k8, Kern k4, Kern k2, dim3 grid, int smem) {
 }
 
 
+// all CTAs (clusters) of a cooperative launch must be co-resident: occupancy query, memoised per (kernel, grid, smem)
+static bool gp_coresident(const void* kern, dim3 grid, int smem, int cluster) {
+  struct Memo { const void* k; unsigned gx, gy; int smem, cluster, ok; };
+  static thread_local std::vector<Memo> memo;
+  for (const Memo& m : memo)
+    if (m.k == kern && m.gx == grid.x && m.gy == grid.y && m.smem == smem && m.cluster == cluster) return m.ok != 0;
+  int ok = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(GP_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess) ok = ((long long)n * cluster >= (long long)grid.x * grid.y) ? 1 : 0;
+    else (void)cudaGetLastError();
+    if (getenv("ARK_GRU_DEBUG"))
+      fprintf(stderr, "[arkb200] gru_persist variant grid=(%u,%u) cluster=%d smem=%d: max active clusters %d -> %s\n", grid.x,
+              grid.y, cluster, smem, n, ok ? "ok" : "does not fit");
+  } else {
+    (void)cudaGetLastError();
+  }
+  memo.push_back(Memo{kern, grid.x, grid.y, smem, cluster, ok});
+  return ok != 0;
+}
+static bool h2_wanted() {
+  static int want = -1;
+  if (want < 0) { const char* e = getenv("ARK_GRU_H2"); want = e ? atoi(e) : 1; }
+  return want != 0;
+}
+// half-tile forward kernel: ring stages (12 / 8 / 4) and shared-memory bytes, or 0 when it does not apply (it pays for
+// d >= 512 with more than one half tile of rows; 16-unit slices must fill <= 148 SMs)
+static int h2_fwd_plan(int64_t d, int64_t bt0, int* stages_out) {
+  if (!h2_wanted() || d < 512 || d % 64 != 0 || bt0 <= H2_ROWS) return 0;
+  const int64_t nbt = (bt0 + GP_BM - 1) / GP_BM;
+  if (nbt * (d / 16) > kNumSMs) return 0;
+  const int cand[3] = {12, 8, 4};
+  for (int i = 0; i < 3; ++i) {
+    const int st = cand[i];
+    const int64_t smem = 3LL * 16 * d * 2 + (int64_t)(st + 1) * H2_A_BYTES + (int64_t)H2_ROWS * 49 * 4 + (2 * st + 4) * 8 + 64 + 1024;
+    if (smem > 227 * 1024) continue;
+    const void* k = st == 12 ? (const void*)gru_persist_fwd_h2_kernel<12> : (st == 8 ? (const void*)gru_persist_fwd_h2_kernel<8> : (const void*)gru_persist_fwd_h2_kernel<4>);
+    if (!gp_coresident(k, dim3((unsigned)(d / 16), (unsigned)nbt), (int)smem, 1)) continue;
+    *stages_out = st;
+    return (int)smem;
+  }
+  return 0;
+}
+static int h2_bwd_plan(int64_t d, int64_t bt0, int* stages_out) {
+  if (!h2_wanted() || d < 512 || d % 256 != 0 || bt0 <= H2_ROWS) return 0;
+  const int64_t nbt = (bt0 + GP_BM - 1) / GP_BM;
+  if (nbt * (d / KS_DJ) > kNumSMs) return 0;
+  const int cand[2] = {7, 4};
+  for (int i = 0; i < 2; ++i) {
+    const int st = cand[i];
+    const int64_t smem = (3 * d / KS) * KS_NC * 2 + (int64_t)(st + 1) * H2_A_BYTES + 2LL * KS * KS_BLK + (2 * st + 6) * 8 + 64 + 1024;
+    if (smem > 227 * 1024) continue;
+    const void* k = st == 7 ? (const void*)gru_persist_bwd_ks_h2_kernel<7> : (const void*)gru_persist_bwd_ks_h2_kernel<4>;
+    if (!gp_coresident(k, dim3((unsigned)(d / KS_DJ), (unsigned)nbt), (int)smem, KS)) continue;
+    *stages_out = st;
+    return (int)smem;
+  }
+  return 0;
+}
+
 // K-split backward (gru_persist_bwd_ks_kernel): shared-memory bytes and ring depth, or 0 when it does not apply.
 // It pays where the dgh tile is large (d >= 512) and needs 3d/4 % 64 == 0, 16-unit slices filling <= 148 SMs and all
 // d/64 * nbt clusters of 4 co-resident (ARK_GRU_KSPLIT=0 switches it off).
@@ -1119,7 +1711,7 @@ extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16
               "gru_persist_fwd: 16-byte alignment");
   cudaStream_t s = (cudaStream_t)stream;
   const int nbt = (int)((bt0 + GP_BM - 1) / GP_BM);
-  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * nbt, s);
+  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * 2 * nbt, s);     // (two counters per tile: half-tile kernels)
   if (e != cudaSuccess) return fail((int)e, "gru_persist_fwd: memset: %s", cudaGetErrorString(e));
   CUtensorMap tmA, tmW;
   int rc;
@@ -1131,6 +1723,19 @@ extern "C" int ark_gru_persist_fwd(uint16_t* hp_b, const float* h0, const uint16
   prm.offset_dev = p_drop > 0.f ? offset_dev : nullptr;
   prm.dbg = pdbg_buffer();
   dim3 grid((unsigned)(d / dj), (unsigned)nbt);
+  {
+    int h2_st = 0;
+    const int h2_smem = h2_fwd_plan(d, bt0, &h2_st);
+    if (h2_smem > 0) {       // two 64-row chains per CTA (16-unit slices)
+      CUtensorMap tmAh, tmWh;
+      if ((rc = make_tmap_2d_bf16(&tmWh, Whh_b, (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, GP_BK, 16))) return rc;
+      if ((rc = make_tmap_2d_bf16(&tmAh, hp_b, (uint64_t)d, (uint64_t)N, (uint64_t)d, GP_BK, H2_ROWS))) return rc;
+      dim3 gh((unsigned)(d / 16), (unsigned)nbt);
+      if (h2_st == 12) return launch_coop(gru_persist_fwd_h2_kernel<12>, tmAh, tmWh, prm, gh, h2_smem, s, "gru_persist_fwd_h2", 1);
+      if (h2_st == 8) return launch_coop(gru_persist_fwd_h2_kernel<8>, tmAh, tmWh, prm, gh, h2_smem, s, "gru_persist_fwd_h2", 1);
+      return launch_coop(gru_persist_fwd_h2_kernel<4>, tmAh, tmWh, prm, gh, h2_smem, s, "gru_persist_fwd_h2", 1);
+    }
+  }
   const int smem = (int)(3LL * dj * d * 2 + (int64_t)stages * GP_A_BYTES + 128LL * (3 * dj + 1) * 4 + 2048);
 #define ARK_GP_FWD(DJ, ST)                                                                                              \
   if (dj == DJ && stages == ST) {                                                                                       \
@@ -1165,7 +1770,7 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
               ARK_E_ALIGN, "gru_persist_bwd: 16-byte alignment");
   cudaStream_t s = (cudaStream_t)stream;
   const int nbt = (int)((bt0 + GP_BM - 1) / GP_BM);
-  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * nbt, s);
+  cudaError_t e = cudaMemsetAsync(sync_ws, 0, sizeof(int32_t) * 2 * nbt, s);
   if (e != cudaSuccess) return fail((int)e, "gru_persist_bwd: memset: %s", cudaGetErrorString(e));
   CUtensorMap tmA, tmW;
   int rc;
@@ -1180,6 +1785,16 @@ extern "C" int ark_gru_persist_bwd(const float* dy, const uint16_t* r, const uin
   {
     int ks_st = 0;
     const int ks_smem = Whh_b ? ks_plan(d, bt0, &ks_st) : 0;
+    int h2_st = 0;
+    const int h2_smem = ks_smem > 0 ? h2_bwd_plan(d, bt0, &h2_st) : 0;
+    if (h2_smem > 0) {       // K-split clusters AND two 64-row chains per CTA
+      CUtensorMap tmAk, tmWk;
+      if ((rc = make_tmap_2d_bf16(&tmWk, Whh_b, (uint64_t)d, (uint64_t)(3 * d), (uint64_t)d, 64, GP_BK))) return rc;
+      if ((rc = make_tmap_2d_bf16(&tmAk, dgh_b, (uint64_t)(3 * d), (uint64_t)N, (uint64_t)(3 * d), GP_BK, H2_ROWS))) return rc;
+      dim3 gk((unsigned)(d / KS_DJ), (unsigned)nbt);
+      if (h2_st == 7) return launch_coop(gru_persist_bwd_ks_h2_kernel<7>, tmAk, tmWk, prm, gk, h2_smem, s, "gru_persist_bwd_ks_h2", KS);
+      return launch_coop(gru_persist_bwd_ks_h2_kernel<4>, tmAk, tmWk, prm, gk, h2_smem, s, "gru_persist_bwd_ks_h2", KS);
+    }
     if (ks_smem > 0) {
       CUtensorMap tmAk, tmWk;
       // W_hh [3d, d] untransposed: inner = units, box = 64 units x 64 gate rows

@@ -159,6 +159,11 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// accumulate-always form (no predicate set-up in the issuing thread's instruction stream)
+__device__ __forceinline__ void umma_f16_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+               : "memory");
+}
 // D[tmem] (+)= A[tmem] . B[smem desc]: the A operand lives in tensor memory (lane = row m, 32-bit column c holds the
 // K elements 2c, 2c+1 of that row), so an MMA only streams the B tile out of shared memory.
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,

@@ -44,6 +44,7 @@ class SailEngine:
     _hold_comm, _held = False, ()
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
+    _leaf_used, use_leaf_stream, leaf_stream = False, False, None     # (the Transformer engines do not fork leaf work)
     max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
     keep = None                      # tests: a dict that receives references to the GRU stack's internal tensors
 
@@ -78,6 +79,12 @@ class SailEngine:
         # gradient all-reduce + per-bucket Adam, overlapping backward.  High priority: its (few) NCCL CTAs must not queue
         # behind the full grids of the main stream's GEMMs
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1 if os.environ.get("ARK_COMM_PRIORITY", "1") != "0" else 0)
+        # weight-gradient GEMMs / bias column sums that nothing in the backward pass consumes ("leaves") run on their own
+        # stream, concurrently with the dependent chain (dY -> GRU backward -> dX -> scatter -> encoder backward): they fill
+        # the SMs the latency-bound chain kernels leave idle (and each other's partial last waves)
+        self.leaf_stream = torch.cuda.Stream(device=dev)
+        self.use_leaf_stream = os.environ.get("ARK_LEAF_STREAM", "1") != "0"
+        self._leaf_used = False
         self._upd = None                 # (mode, lr) while a train step is in flight: buckets are updated as they finish
         self._pending = []
         self._hold_comm, self._held = False, []   # see _comm_action: no NCCL next to the 128-CTA cooperative GRU kernels
@@ -381,7 +388,7 @@ class SailEngine:
         # Order of the backward pass: the CHAIN first (dY -> GRU backward -> dX -> embedding scatter -> encoder), the
         # LEAVES (weight-gradient GEMMs nothing in this pass consumes) after it, so that the two large late buckets
         # (token / entity embedding tables: all-reduce + dense Adam on the side stream) overlap the leaf GEMMs.
-        deferred = []
+        deferred, keep_alive = [], []
         dy = new(N, d)
         self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")                         # dY = dLogits . W
 
@@ -393,7 +400,6 @@ class SailEngine:
             self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
             if self.tied:
                 self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
-        deferred.append(vocab_weight_grads)
         del logits
         dh0 = new(b0, d)
         if wave:
@@ -426,9 +432,10 @@ class SailEngine:
                     ops.colsum(dgi_all[k], N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
                     ops.colsum(dgh_all[k], N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
                     self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
-            deferred.append(gru_weight_grads)
+            self._leaf(gru_weight_grads)
         else:
-            dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
+            if not persist:
+                dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
             ks_bwd = persist and ops.gru_persist_bwd_ksplit(d, b0)    # K-split cluster kernel: W_hh untransposed
             if persist:
                 whh_t = None if ks_bwd else new(d, d3, dtype=bf)
@@ -439,6 +446,7 @@ class SailEngine:
             if mask is not None and not persist:
                 ops.dropout_bwd(dy, mask, self.p_drop, dy)
             if persist:
+                dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)   # per layer: read later by the leaf stream
                 if not ks_bwd:
                     ops.transpose_bf16(self._w(f"dec.gru.weight_hh_l{k}"), whh_t)
                 with self._timed("gru_persist_bwd", flops=2.0 * N * d * d3):
@@ -454,18 +462,25 @@ class SailEngine:
                     dh0.copy_(dh_k)
                 else:
                     ops.add_(dh0, dh_k, dh0, None)
-            self._gemm(dgi, MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
-            self._gemm(dgh, MN, hp_b, MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
-            ops.colsum(dgi, N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
-            ops.colsum(dgh, N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
-            self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3, tag="gru_dX")   # grad w.r.t. layer input
-            self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+            def layer_weight_grads(k=k, dgi=dgi, dgh=dgh, u_in=u_in, hp_b=hp_b):
+                self._gemm(dgi, MN, u_in, MN, f.g(f"dec.gru.weight_ih_l{k}"), d3, d, N, tag="gru_dWih")
+                self._gemm(dgh, MN, hp_b, MN, f.g(f"dec.gru.weight_hh_l{k}"), d3, d, N, tag="gru_dWhh")
+                ops.colsum(dgi, N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
+                ops.colsum(dgh, N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
+                self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
+            self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3, tag="gru_dX")   # the chain: grad w.r.t. layer input
+            if persist:
+                keep_alive.append((dgi, dgh))
+                self._leaf(layer_weight_grads)
+            else:
+                layer_weight_grads()
         self._release_comm()          # (no-op unless collectives were held back for the persistent GRU kernels)
         f.g("dec.tok_emb.weight").zero_()
         with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
             ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
-        if not self.tied:             # (tied: final once the deferred vocabulary dW has been added)
+        if not self.tied:             # (tied: final once the vocabulary dW has been added on top of the scatter)
             self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+        self._leaf(vocab_weight_grads)
 
         if not self.has_enc:
             g_pos = f.g("dec.pos_emb.weight")
@@ -474,13 +489,16 @@ class SailEngine:
             self._grad_ready("dec.pos_emb.weight", "dec.pos_emb.weight")
             for fn in deferred:
                 fn()
+            self._leaf_join()
             return out
 
         # ---------------- h0 = tanh(W_z z + b_z), reparameterisation, KL
         dpre, dpre_b = new(B, d), new(B, d, dtype=bf)
         ops.tanh_bwd(dh0, h0, dpre, dpre_b)
-        self._gemm(dpre_b, MN, z_b, MN, f.g("dec.z_proj.weight"), d, dz, B, tag="z_proj_bwd")
-        ops.colsum(dpre, B, d, f.g("dec.z_proj.bias"))
+        def z_proj_weight_grads():
+            self._gemm(dpre_b, MN, z_b, MN, f.g("dec.z_proj.weight"), d, dz, B, tag="z_proj_bwd")
+            ops.colsum(dpre, B, d, f.g("dec.z_proj.bias"))
+        self._leaf(z_proj_weight_grads)
         dz_in = new(B, dz)
         self._gemm(dpre_b, K, self._w("dec.z_proj.weight"), MN, dz_in, B, dz, d, tag="z_proj_bwd")
         ld_dh = _up8(2 * dz)
@@ -495,11 +513,13 @@ class SailEngine:
                                dlogv_ext=None if ext is None else ext.get("dlogv"))
         g_wh = f.fused(f.grad, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
         g_bh = f.fused(f.grad, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
-        self._gemm(dheads_b[:, :2 * dz], MN, acts[-1], MN, g_wh, 2 * dz, d3, B, tag="enc_heads_bwd")
-        ops.colsum(dheads, B, 2 * dz, g_bh)
+        def heads_weight_grads():
+            self._gemm(dheads_b[:, :2 * dz], MN, acts[-1], MN, g_wh, 2 * dz, d3, B, tag="enc_heads_bwd")
+            ops.colsum(dheads, B, 2 * dz, g_bh)
+            self._grad_ready("dec.z_proj.weight", "enc.logv.bias")
         da = new(B, d3)
         self._gemm(dheads_b[:, :2 * dz], K, w_heads, MN, da, B, d3, 2 * dz, tag="enc_heads_bwd")
-        self._grad_ready("dec.z_proj.weight", "enc.logv.bias")
+        self._leaf(heads_weight_grads)
 
         # ---------------- encoder MLP + pooled gather backward
         dp_all = [None] * self.n_mlp
@@ -509,13 +529,15 @@ class SailEngine:
             if fg:
                 dp_all[k] = new(self.world * B, d3, dtype=bf)
                 self._comm_action(("gather", dp_all[k], dp_b))       # overlaps the rest of the chain
-            else:
-                self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B, tag="enc_mlp_bwd")
-                ops.colsum(dp_b, B, d3, f.g(f"enc.mlp.{2 * k}.bias"))
             da = new(B, d3)
-            self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3, tag="enc_mlp_bwd")
+            self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3, tag="enc_mlp_dX")
             if not fg:
-                self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
+                def mlp_weight_grads(k=k, dp_b=dp_b):
+                    self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B, tag="enc_mlp_dW")
+                    ops.colsum(dp_b, B, d3, f.g(f"enc.mlp.{2 * k}.bias"))
+                    self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
+                keep_alive.append(dp_b)
+                self._leaf(mlp_weight_grads)
         gE, gR = f.g("enc.e_emb.weight"), f.g("enc.r_emb.weight")
         if fg and fg_emb:
             da_all = new(self.world * B, d3)
@@ -542,7 +564,37 @@ class SailEngine:
                 self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias", reduced=True)
         for fn in deferred:
             fn()
+        self._leaf_join()
+        del keep_alive
         return out
+
+    # ------------------------------------------------------------------ leaf stream
+    def _leaf(self, fn):
+        """Run `fn` (launches of leaf work: nothing later on the current stream reads what it writes before `_leaf_join`)
+        on the leaf stream, ordered after everything queued on the current stream so far.  Inline when the leaf stream is
+        off, or while a data-parallel step is captured (its graph segments end at arbitrary points of the pass and a
+        capture cannot end with un-joined forked work)."""
+        if not self.use_leaf_stream or (self._capturing and self.world > 1) or self.prof is not None and not self._capturing:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.leaf_stream.wait_event(ev)
+        with torch.cuda.stream(self.leaf_stream):
+            fn()
+        self._leaf_used = True
+
+    def _leaf_join(self):
+        if self._leaf_used:
+            torch.cuda.current_stream().wait_stream(self.leaf_stream)
+            self._leaf_used = False
+
+    def _comm_waits_for_leaf(self):
+        """Buckets may contain gradients written on the leaf stream: the side stream waits for it too."""
+        if self._leaf_used:
+            ev = torch.cuda.Event()
+            ev.record(self.leaf_stream)
+            self.comm_stream.wait_event(ev)
 
     # ------------------------------------------------------------------ gradient exchange + bucketed update
     def _grad_ready(self, first, last, reduced=False):
@@ -611,6 +663,7 @@ class SailEngine:
             ev = torch.cuda.Event()
             ev.record()
             self.comm_stream.wait_event(ev)
+            self._comm_waits_for_leaf()
             with torch.cuda.stream(self.comm_stream):
                 with self._timed("nccl_all_gather", nbytes=float(action[1].numel() * action[1].element_size())):
                     torch.distributed.all_gather_into_tensor(action[1], action[2], group=self.group)
@@ -626,6 +679,7 @@ class SailEngine:
         ev = torch.cuda.Event()
         ev.record()
         self.comm_stream.wait_event(ev)
+        self._comm_waits_for_leaf()
         f = self.flat
         with torch.cuda.stream(self.comm_stream):
             for (s, e) in spans:
@@ -642,6 +696,7 @@ class SailEngine:
                                           upd[1], self.betas[0], self.betas[1], self.eps, self.step_count)
 
     def _sync_grads(self):
+        self._leaf_join()
         self._flush_bucket()
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 

@@ -168,7 +168,7 @@ int ark_gru_layer_bwd(const float* dy, const float* r, const float* z, const flo
  * (d/slice) x ceil(bt0/128) grid does not fit the 148 SMs): callers then use ark_gru_layer_fwd/bwd. */
 int ark_gru_persist_supported(int64_t d, int64_t bt0);
 /* hp_b [N,d]: block 0 pre-filled with bf16(h0); blocks 1.. are written here.  h0 f32 [bt0,d].
- * gi f32 [N,3d]; outputs y_b and (optional, all or none) r,z,n,ghn bf16 [N,d]; sync_ws int32 [ceil(bt0/128)].
+ * gi f32 [N,3d]; outputs y_b and (optional, all or none) r,z,n,ghn bf16 [N,d]; sync_ws int32 [2*ceil(bt0/128)].
  * p_drop > 0: y_b receives the layer output AFTER the inter-layer dropout (nn.GRU(dropout=p), models.py:121-127), drawn
  * from the Philox stream of ark_dropout_bf16 (seed, offset [+ *offset_dev]) over the [N,d] tensor, keep mask -> mask
  * u8 [N,d] (may be NULL); hp_b always holds the undropped state. */

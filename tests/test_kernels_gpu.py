@@ -393,6 +393,8 @@ def test_gru_layer_fwd_bwd_matches_torch(use_tc):
     (256, list(range(40, 0, -1)) * 4),                          # 160 graphs, very ragged, tile 1 retires early
     (512, [30, 22, 22, 9, 3, 3, 3, 1]),                         # wd-articles-like small batch
     (1024, [10] * 256),                                         # syn-types shape: 64 slices x 2 tiles = 128 CTAs
+    (512, [1 + (i * 7) % 12 for i in range(200)]),              # half-tile kernels, ragged: halves retire at different steps
+    (512, [6] * 70 + [3] * 30),                                 # half-tile kernels: second half with 6 live rows at first
 ])
 def test_gru_persist_fwd_bwd_matches_torch(d, lens):
     torch.manual_seed(d)
@@ -424,7 +426,7 @@ def test_gru_persist_fwd_bwd_matches_torch(d, lens):
     hp_b[:B] = h0.detach().to(bf)
     y_b = torch.empty(N, d, device=DEV, dtype=bf)
     gates = tuple(torch.empty(N, d, device=DEV, dtype=bf) for _ in range(4))
-    sync = torch.empty((B + 127) // 128, device=DEV, dtype=torch.int32)
+    sync = torch.empty(2 * ((B + 127) // 128), device=DEV, dtype=torch.int32)
     bt_d, off_d = torch.from_numpy(bt).to(DEV), torch.from_numpy(off[:-1].copy()).to(DEV)
     Wb = Whh.to(bf).contiguous()
     ops.gru_persist_fwd(hp_b, h0.detach().contiguous(), Wb, gi, gru.bias_hh_l0.detach(), bt_d, off_d, L, B, d, y_b,
