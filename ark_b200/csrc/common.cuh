@@ -12,6 +12,10 @@ namespace ark {
 // thread-local error text + launch counter (api.cu)
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// true when the process was started by Nsight Compute (its launcher exports NV_NSIGHT_* / NV_COMPUTE_PROFILER_*):
+// the profiler's injection does not survive COOPERATIVE launches with a cluster dimension, so those kernels drop the
+// cooperative attribute there (co-residency is established by the occupancy query before every such launch)
+bool under_profiler();
 
 inline int fail(int code, const char* fmt, ...) {
   char buf[512];

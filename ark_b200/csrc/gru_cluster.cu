@@ -38,7 +38,6 @@
 #include "philox.cuh"
 #include <string.h>
 #include <stdlib.h>
-extern "C" char** environ;
 
 namespace ark {
 
@@ -1127,13 +1126,7 @@ static int launch_cluster(Kern kern, const Params& prm, dim3 grid, int cs, int s
   if (no_coop < 0) {
     const char* ev = getenv("ARK_GRU_CLUSTER_NO_COOP");
     no_coop = ev ? atoi(ev) : 0;
-    // Nsight Compute's injection does not survive a cooperative cluster launch (the profiler exits with rc 9 and
-    // takes the process with it, so there is no error to retry on): recognise a profiled process by the variables
-    // its launcher exports
-    for (char** e = environ; !ev && e && *e; ++e)
-      if (!strncmp(*e, "NV_NSIGHT", 9) || !strncmp(*e, "NV_COMPUTE_PROFILER", 19) || !strncmp(*e, "CUDA_INJECTION64_PATH", 21) ||
-          !strncmp(*e, "NVTX_INJECTION64_PATH", 21))
-        no_coop = 1;
+    if (!ev && under_profiler()) no_coop = 1;     // see common.cuh
   }
   cfg.numAttrs = no_coop ? 1 : 2;
   e = cudaLaunchKernelEx(&cfg, kern, prm);

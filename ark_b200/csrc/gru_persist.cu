@@ -1477,6 +1477,10 @@ static int launch_coop(Kern kern, const CUtensorMap& tmA, const CUtensorMap& tmW
   attrs[1].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = cluster > 1 ? 2 : 1;
+  if (cluster > 1 && under_profiler()) {      // cluster launch without the cooperative attribute (see common.cuh)
+    attrs[0] = attrs[1];
+    cfg.numAttrs = 1;
+  }
   e = cudaLaunchKernelEx(&cfg, kern, tmA, tmW, prm);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();

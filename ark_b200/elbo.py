@@ -44,7 +44,7 @@ class SailEngine:
     _hold_comm, _held = False, ()
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
-    _leaf_used, use_leaf_stream, leaf_stream = False, False, None     # (the Transformer engines do not fork leaf work)
+    _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding = False, False, None, False     # (the Transformer engines do not fork leaf work)
     max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
     keep = None                      # tests: a dict that receives references to the GRU stack's internal tensors
 
@@ -84,6 +84,7 @@ class SailEngine:
         # the SMs the latency-bound chain kernels leave idle (and each other's partial last waves)
         self.leaf_stream = torch.cuda.Stream(device=dev)
         self.use_leaf_stream = os.environ.get("ARK_LEAF_STREAM", "1") != "0"
+        self.leaf_embedding = os.environ.get("ARK_LEAF_EMB", "0") != "0"   # also fork layer-0 dX + the embedding scatter
         self._leaf_used = False
         self._upd = None                 # (mode, lr) while a train step is in flight: buckets are updated as they finish
         self._pending = []
@@ -223,6 +224,38 @@ class SailEngine:
             self._hold_comm = (not stack) and ops.gru_persist_supported(d, b0_) > 0
         new = lambda *s, dtype=f32: torch.empty(*s, device=dev, dtype=dtype)  # noqa: E731
 
+        # ---------------- decoder inputs: token packing + embedding gather + (per-layer GRU path) the layer-0 input
+        # projection do not depend on the encoder, so they run on the leaf stream WHILE the encoder (a chain of
+        # latency-bound small-M GEMMs) runs on this one; joined in front of the GRU
+        b0 = int(lay.bt[0])
+        cl_nb = (self._use_gru_cluster(d, b0, nl, L)
+                 if (use_tc and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru) else 0)
+        wave_ok = use_tc and not self.force_unfused_gru and ops.gru_wave_supported(d, b0, nl) > 0
+        cluster = cl_nb > 0
+        # the two stack kernels share every tensor of their contract, so the direction can be chosen separately: with
+        # 64-row batch tiles the cluster backward (16 work items per epilogue thread) is no faster than the wavefront's
+        cluster_bwd = cluster and (cl_nb <= 32 or self.gru_mode == "cluster" or not wave_ok)
+        wave = cluster or (self.gru_mode in ("auto", "wave") and wave_ok)
+        persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru and not wave
+        tok, tgt = new(N, dtype=torch.int32), new(N, dtype=torch.int32)
+        row_t = None if self.has_enc else new(N, dtype=torch.int32)
+        x_b = new(N, d, dtype=bf)
+        gi0 = None if wave else new(N, d3)
+
+        def decoder_inputs():
+            ops.pack_tokens(seq, lay.perm_dev, lay.bt_dev, lay.off_dev, L, tok, tgt, row_t)
+            if self.has_enc:
+                ops.tok_gather_fwd(self._w("dec.tok_emb.weight"), tok, None, x_b)
+            else:   # token + position embedding (reference models.py:340-342)
+                ops.tok_pos_gather_fwd(self._w("dec.tok_emb.weight"), self._w("dec.pos_emb.weight"), tok, row_t, x_b)
+            if gi0 is not None:
+                self._gemm(x_b, K, self._w("dec.gru.weight_ih_l0"), K, gi0, N, d3, d, tag="gru_gi",
+                           bias=f.p("dec.gru.bias_ih_l0"))
+        if self.has_enc:
+            self._leaf(decoder_inputs)
+        else:
+            decoder_inputs()
+
         # ---------------- encoder forward (models.py:46-64)
         if self.has_enc:
             g_b, inv_cnt = new(B, d3, dtype=bf), new(B)
@@ -268,26 +301,9 @@ class SailEngine:
             h0 = torch.zeros(B, d, device=dev)          # decoder-only ARK: nn.GRU's default initial state
 
         # ---------------- decoder forward (models.py:136-142) over packed rows
-        tok, tgt = new(N, dtype=torch.int32), new(N, dtype=torch.int32)
-        row_t = None if self.has_enc else new(N, dtype=torch.int32)
-        ops.pack_tokens(seq, lay.perm_dev, lay.bt_dev, lay.off_dev, L, tok, tgt, row_t)
-        x_b = new(N, d, dtype=bf)
-        if self.has_enc:
-            ops.tok_gather_fwd(self._w("dec.tok_emb.weight"), tok, None, x_b)
-        else:   # token + position embedding (reference models.py:340-342)
-            ops.tok_pos_gather_fwd(self._w("dec.tok_emb.weight"), self._w("dec.pos_emb.weight"), tok, row_t, x_b)
-        b0 = int(lay.bt[0])
+        self._leaf_join()             # token rows / embeddings / layer-0 input projection are ready
         saved = []
         u_b = x_b
-        cl_nb = (self._use_gru_cluster(d, b0, nl, L)
-                 if (use_tc and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru) else 0)
-        wave_ok = use_tc and not self.force_unfused_gru and ops.gru_wave_supported(d, b0, nl) > 0
-        cluster = cl_nb > 0
-        # the two stack kernels share every tensor of their contract, so the direction can be chosen separately: with
-        # 64-row batch tiles the cluster backward (16 work items per epilogue thread) is no faster than the wavefront's
-        cluster_bwd = cluster and (cl_nb <= 32 or self.gru_mode == "cluster" or not wave_ok)
-        wave = cluster or (self.gru_mode in ("auto", "wave") and wave_ok)
-        persist = use_tc and ops.gru_persist_supported(d, b0) > 0 and not self.force_unfused_gru and not wave
         gh_ws = None if (persist or wave) else new(b0, d3)
         sync_ws = new(32 * nl * ((b0 + 15) // 16), dtype=torch.int32) if (persist or wave) else None   # cluster: 2*nl*tiles*16
         cl_ws = self._cluster_ws(L, b0, d, nl) if cluster else None
@@ -322,9 +338,12 @@ class SailEngine:
                 self._drop_calls += nl - 1
             u_b = out_all[nl - 1]
         for k in range(0 if not wave else nl, nl):
-            gi = new(N, d3)
-            self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, tag="gru_gi",
-                       bias=f.p(f"dec.gru.bias_ih_l{k}"))
+            if k == 0:
+                gi = gi0
+            else:
+                gi = new(N, d3)
+                self._gemm(u_b, K, self._w(f"dec.gru.weight_ih_l{k}"), K, gi, N, d3, d, tag="gru_gi",
+                           bias=f.p(f"dec.gru.bias_ih_l{k}"))
             hp_b, y_b = new(N, d, dtype=bf), new(N, d, dtype=bf)
             mask = None
             if persist:
@@ -389,6 +408,7 @@ class SailEngine:
         # LEAVES (weight-gradient GEMMs nothing in this pass consumes) after it, so that the two large late buckets
         # (token / entity embedding tables: all-reduce + dense Adam on the side stream) overlap the leaf GEMMs.
         deferred, keep_alive = [], []
+        dx0_src, stack_weight_grads = None, None
         dy = new(N, d)
         self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")                         # dY = dLogits . W
 
@@ -420,9 +440,7 @@ class SailEngine:
                     ops.gru_wave_bwd(*bwd_args)
             if self.keep is not None:
                 self.keep.update(gru_out=out_all, gru_dgi=dgi_all, gru_dgh=dgh_all, gru_dh0=dh0)
-            # the chain first: dX feeds the embedding scatter and the encoder backward, whose (large, late) gradient
-            # buckets then reduce / update on the side stream WHILE the GRU weight-gradient GEMMs below run
-            self._gemm(dgi_all[0], K, self._w("dec.gru.weight_ih_l0"), MN, dy, N, d, d3, tag="gru_dX")
+            dx0_src = dgi_all[0]
 
             def gru_weight_grads():
                 for k in range(nl - 1, -1, -1):
@@ -432,7 +450,7 @@ class SailEngine:
                     ops.colsum(dgi_all[k], N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
                     ops.colsum(dgh_all[k], N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
                     self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
-            self._leaf(gru_weight_grads)
+            stack_weight_grads = gru_weight_grads
         else:
             if not persist:
                 dgi, dgh = new(N, d3, dtype=bf), new(N, d3, dtype=bf)
@@ -468,25 +486,49 @@ class SailEngine:
                 ops.colsum(dgi, N, d3, f.g(f"dec.gru.bias_ih_l{k}"))
                 ops.colsum(dgh, N, d3, f.g(f"dec.gru.bias_hh_l{k}"))
                 self._grad_ready(f"dec.gru.weight_ih_l{k}", f"dec.gru.bias_hh_l{k}")
-            self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3, tag="gru_dX")   # the chain: grad w.r.t. layer input
+            if k == 0 and persist:
+                dx0_src = dgi         # layer 0: dX only feeds the embedding scatter -> with it on the leaf stream
+            else:
+                self._gemm(dgi, K, self._w(f"dec.gru.weight_ih_l{k}"), MN, dy, N, d, d3, tag="gru_dX")   # the chain
             if persist:
                 keep_alive.append((dgi, dgh))
                 self._leaf(layer_weight_grads)
             else:
                 layer_weight_grads()
         self._release_comm()          # (no-op unless collectives were held back for the persistent GRU kernels)
-        f.g("dec.tok_emb.weight").zero_()
-        with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
-            ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
-        if not self.tied:             # (tied: final once the vocabulary dW has been added on top of the scatter)
-            self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
-        self._leaf(vocab_weight_grads)
+
+        def embedding_grads():
+            # d(loss)/d(decoder inputs) -> token (+ position) embedding scatter -> vocabulary weight gradients: nothing
+            # in the rest of the pass reads them, so they leave the chain (the encoder backward continues on the main
+            # stream with dh0 only)
+            if dx0_src is not None:
+                self._gemm(dx0_src, K, self._w("dec.gru.weight_ih_l0"), MN, dy, N, d, d3, tag="gru_dX")
+            f.g("dec.tok_emb.weight").zero_()
+            with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
+                ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
+            if not self.tied:             # (tied: final once the vocabulary dW has been added on top of the scatter)
+                self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+            if not self.has_enc:
+                g_pos = f.g("dec.pos_emb.weight")
+                g_pos.zero_()
+                ops.tok_scatter_add(dy, row_t, g_pos)      # d pos_emb[t] = sum of dX over the rows of step t
+                self._grad_ready("dec.pos_emb.weight", "dec.pos_emb.weight")
+            if self.leaf_embedding:
+                vocab_weight_grads()
+                if stack_weight_grads is not None:
+                    stack_weight_grads()
+
+        def tail_weight_grads():
+            vocab_weight_grads()
+            if stack_weight_grads is not None:
+                stack_weight_grads()
+        if self.leaf_embedding:
+            self._leaf(embedding_grads)
+        else:           # dX_0 + scatter stay on the chain's stream; only the weight gradients fork
+            embedding_grads()
+            self._leaf(tail_weight_grads)
 
         if not self.has_enc:
-            g_pos = f.g("dec.pos_emb.weight")
-            g_pos.zero_()
-            ops.tok_scatter_add(dy, row_t, g_pos)      # d pos_emb[t] = sum of dX over the rows of step t
-            self._grad_ready("dec.pos_emb.weight", "dec.pos_emb.weight")
             for fn in deferred:
                 fn()
             self._leaf_join()

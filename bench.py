@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE workloads (`also` array)")
+    ap.add_argument("--no-kernel-profile", action="store_true", help="skip the per-kernel timing pass (ncu runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: YAML batch_size per GPU; strong: YAML batch_size split over the GPUs")
@@ -404,7 +405,7 @@ def main():
 
     e2e = None if args.no_e2e else w.measure_e2e(args.steps, min(args.windows, 3))
 
-    agg, n_prof, mode = w.kernel_profile()
+    agg, n_prof, mode = ({}, 1, "skipped") if args.no_kernel_profile else w.kernel_profile()
     step_ms = total_ms / args.steps
     rows = kernel_table(agg, n_prof, step_ms, pk, args.workload if (args.model == "SAIL" and not args.dense and not args.batch) else "-")
     roof = roofline_from(rows, pk, mode)
