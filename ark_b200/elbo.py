@@ -44,7 +44,7 @@ class SailEngine:
     _hold_comm, _held = False, ()
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
-    _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding = False, False, None, False     # (the Transformer engines do not fork leaf work)
+    _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding, capture_nccl = False, False, None, False, False     # (the Transformer engines do not fork leaf work)
     max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
     keep = None                      # tests: a dict that receives references to the GRU stack's internal tensors
 
@@ -75,6 +75,9 @@ class SailEngine:
         self.ldv = _up8(self.V)
         self.group = dist_group
         self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
+        if self.world > 1 and bucket_mb == 16.0:
+            bucket_mb = 48.0        # with NVSwitch a few large all-reduces beat many launch-latency-bound small ones
+        bucket_mb = float(os.environ.get("ARK_BUCKET_MB", bucket_mb))
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         # gradient all-reduce + per-bucket Adam, overlapping backward.  High priority: its (few) NCCL CTAs must not queue
         # behind the full grids of the main stream's GEMMs
@@ -84,7 +87,11 @@ class SailEngine:
         # the SMs the latency-bound chain kernels leave idle (and each other's partial last waves)
         self.leaf_stream = torch.cuda.Stream(device=dev)
         self.use_leaf_stream = os.environ.get("ARK_LEAF_STREAM", "1") != "0"
-        self.leaf_embedding = os.environ.get("ARK_LEAF_EMB", "0") != "0"   # also fork layer-0 dX + the embedding scatter
+        self.leaf_embedding = os.environ.get("ARK_LEAF_EMB", "0") != "0"
+        # data parallel + CUDA graphs: capture the NCCL collectives INTO the step graph (one replay per step) instead of
+        # cutting the graph into segments with eager collectives in between
+        # (ARK_CAPTURE_NCCL=0: the round-1 scheme — a chain of graph segments with eager collectives between them)
+        self.capture_nccl = os.environ.get("ARK_CAPTURE_NCCL", "1") != "0"   # also fork layer-0 dX + the embedding scatter
         self._leaf_used = False
         self._upd = None                 # (mode, lr) while a train step is in flight: buckets are updated as they finish
         self._pending = []
@@ -281,13 +288,13 @@ class SailEngine:
                       and self.world * B * triples.shape[1] <= nE_rows)
             if fg:
                 x_all = [new(self.world * B, d3, dtype=bf) for _ in range(self.n_mlp)]
-                gathers = [("gather", x_all[k], acts[k]) for k in range(self.n_mlp)]
+                gathers = [(x_all[k], acts[k]) for k in range(self.n_mlp)]
                 if fg_emb:
                     tri_p = triples.index_select(0, lay.perm_dev.long()).contiguous()      # rows in packed order
                     tri_all = torch.empty((self.world * B,) + tuple(triples.shape[1:]), device=dev, dtype=triples.dtype)
                     inv_all = new(self.world * B)
-                    gathers += [("gather", tri_all, tri_p), ("gather", inv_all, inv_cnt)]
-                self._comm_actions(gathers)
+                    gathers += [(tri_all, tri_p), (inv_all, inv_cnt)]
+                self._comm_action(("gathers", gathers))
             w_heads = f.fused(f.shadow, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
             b_heads = f.fused(f.param, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
             heads = new(B, 2 * dz)
@@ -564,15 +571,20 @@ class SailEngine:
         self._leaf(heads_weight_grads)
 
         # ---------------- encoder MLP + pooled gather backward
-        dp_all = [None] * self.n_mlp
+        wb = self.world * B
         for k in range(self.n_mlp - 1, -1, -1):
             dp_b = new(B, d3, dtype=bf)
             ops.gelu_bwd(da, pres[k], None, dp_b)
             if fg:
-                dp_all[k] = new(self.world * B, d3, dtype=bf)
-                self._comm_action(("gather", dp_all[k], dp_b))       # overlaps the rest of the chain
+                # data parallel: this layer's dY factor is gathered, the GLOBAL dW_k = dY_all^T X_all formed and Adam
+                # applied, all on the side stream (in order behind the X-factor gather issued after the encoder
+                # forward) while the chain below continues: nothing on this stream waits for it before the step ends
+                dp_all_k = new(wb, d3, dtype=bf)
+                keep_alive.append((dp_b, dp_all_k))
             da = new(B, d3)
             self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3, tag="enc_mlp_dX")
+            if fg:      # AFTER the dX GEMM is queued: the side stream's Adam rewrites W_k, which that GEMM still reads
+                self._comm_action(("mlp_dw", k, dp_all_k, dp_b, x_all[k]))
             if not fg:
                 def mlp_weight_grads(k=k, dp_b=dp_b):
                     self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B, tag="enc_mlp_dW")
@@ -581,29 +593,22 @@ class SailEngine:
                 keep_alive.append(dp_b)
                 self._leaf(mlp_weight_grads)
         gE, gR = f.g("enc.e_emb.weight"), f.g("enc.r_emb.weight")
-        if fg and fg_emb:
-            da_all = new(self.world * B, d3)
+        if fg and fg_emb:       # (opt-in) the embedding scatter over the GLOBAL batch from gathered factors
+            da_all = new(wb, d3)
             self._comm_action(("gather", da_all, da))
+            self._flush_bucket()
+            self._comm_action(("join",))            # every rank's factors have arrived
+            with self._timed("gather_pool_bwd", nbytes=gE.numel() * 4.0 + wb * d3 * 4 + 3.0 * lay.n_triples * self.world * d * 8):
+                gR.zero_()
+                gE.zero_()
+                ops.gather_pool_bwd(da_all, tri_all, None, inv_all, self.pad_rid, self.pad_eid, gE, gR)
+            self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight", reduced=True)
         else:
             with self._timed("gather_pool_bwd", nbytes=gE.numel() * 4.0 + B * d3 * 4 + 3.0 * lay.n_triples * d * 8):
                 gR.zero_()
                 gE.zero_()
                 ops.gather_pool_bwd(da, triples, lay.perm_dev, inv_cnt, self.pad_rid, self.pad_eid, gE, gR)
             self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight")
-        if fg:
-            self._flush_bucket()                    # the embedding gradients go first: their all-reduce overlaps the GEMMs below
-            self._comm_action(("join",))            # every rank's factors have arrived
-            wb = self.world * B
-            if fg_emb:
-                with self._timed("gather_pool_bwd", nbytes=gE.numel() * 4.0 + wb * d3 * 4 + 3.0 * lay.n_triples * self.world * d * 8):
-                    gR.zero_()
-                    gE.zero_()
-                    ops.gather_pool_bwd(da_all, tri_all, None, inv_all, self.pad_rid, self.pad_eid, gE, gR)
-                self._grad_ready("enc.r_emb.weight", "enc.e_emb.weight", reduced=True)
-            for k in range(self.n_mlp - 1, -1, -1):
-                self._gemm(dp_all[k], MN, x_all[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, wb, tag="enc_mlp_dW_global")
-                ops.colsum(dp_all[k], wb, d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks must agree bitwise
-                self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias", reduced=True)
         for fn in deferred:
             fn()
         self._leaf_join()
@@ -616,7 +621,8 @@ class SailEngine:
         on the leaf stream, ordered after everything queued on the current stream so far.  Inline when the leaf stream is
         off, or while a data-parallel step is captured (its graph segments end at arbitrary points of the pass and a
         capture cannot end with un-joined forked work)."""
-        if not self.use_leaf_stream or (self._capturing and self.world > 1) or self.prof is not None and not self._capturing:
+        if (not self.use_leaf_stream or (self._capturing and self.world > 1 and not self.capture_nccl)
+                or self.prof is not None and not self._capturing):
             fn()
             return
         ev = torch.cuda.Event()
@@ -670,7 +676,7 @@ class SailEngine:
         if self._hold_comm:
             self._held.append(action)
             return
-        if self._capturing and self.world > 1:
+        if self._capturing and self.world > 1 and not self.capture_nccl:
             self._segment_break([action])
             return
         self._run_action(action, self._upd)
@@ -679,7 +685,7 @@ class SailEngine:
         if self._hold_comm:
             self._held.extend(actions)
             return
-        if self._capturing and self.world > 1:
+        if self._capturing and self.world > 1 and not self.capture_nccl:
             self._segment_break(list(actions))      # one segment break for all of them
             return
         for a in actions:
@@ -701,14 +707,34 @@ class SailEngine:
         kind = action[0]
         if kind == "bucket":
             self._bucket_async(action[1], upd, allreduce=action[2])
-        elif kind == "gather":      # all ranks' [B, n] rows -> [world * B, n], on the side stream
+        elif kind in ("gather", "gathers"):      # all ranks' [B, n] rows -> [world * B, n], on the side stream
+            pairs = [(action[1], action[2])] if kind == "gather" else list(action[1])
             ev = torch.cuda.Event()
             ev.record()
             self.comm_stream.wait_event(ev)
             self._comm_waits_for_leaf()
             with torch.cuda.stream(self.comm_stream):
-                with self._timed("nccl_all_gather", nbytes=float(action[1].numel() * action[1].element_size())):
-                    torch.distributed.all_gather_into_tensor(action[1], action[2], group=self.group)
+                with self._timed("nccl_all_gather", nbytes=float(sum(o.numel() * o.element_size() for o, _ in pairs))):
+                    if len(pairs) == 1:
+                        torch.distributed.all_gather_into_tensor(pairs[0][0], pairs[0][1], group=self.group)
+                    else:   # ONE NCCL group launch for all of them (small messages are launch-latency bound)
+                        with torch.distributed._coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                            for o, i in pairs:
+                                torch.distributed.all_gather_into_tensor(o, i, group=self.group)
+        elif kind == "mlp_dw":      # (k, dY_all, dY_local, X_all): gather -> global dW_k GEMM -> bias -> Adam, side stream
+            _, k, dp_all_k, dp_b, x_all_k = action
+            ev = torch.cuda.Event()
+            ev.record()
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                with self._timed("nccl_all_gather", nbytes=float(dp_all_k.numel() * 2)):
+                    torch.distributed.all_gather_into_tensor(dp_all_k, dp_b, group=self.group)
+                d3 = dp_all_k.shape[1]
+                f = self.flat
+                self._gemm(dp_all_k, MN, x_all_k, MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, dp_all_k.shape[0],
+                           tag="enc_mlp_dW_global")
+                ops.colsum(dp_all_k, dp_all_k.shape[0], d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks agree bitwise
+                self._bucket_async([f.span(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")], upd, allreduce=False)
         elif kind == "join":        # the main stream needs what the side stream produced
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         else:
@@ -827,8 +853,8 @@ class SailEngine:
                     out = self.forward_backward(st["triples"], st["seq"], st["lay"], st["eps"], beta, n_tok_global,
                                                 batch_global, train=True)
                     self._flush_bucket()              # the last gradient slices (world > 1: cuts a segment)
-                    if self.world == 1:
-                        torch.cuda.current_stream().wait_stream(self.comm_stream)    # join the Adam branch
+                    if self.world == 1 or self.capture_nccl:
+                        torch.cuda.current_stream().wait_stream(self.comm_stream)    # join the Adam (+ NCCL) branch
                     self.stats[0:2] += out
                     self.stats[2] += 1
                     cur["g"].capture_end()
@@ -861,6 +887,13 @@ class SailEngine:
         self.philox_offset += ent["philox_per_step"]
         self.last_graph = ent
         return ent["out"]
+
+    def release_graphs(self):
+        """Drop every captured step graph (and the private pools they pin).  Under data parallelism the graphs contain
+        NCCL kernels: release them BEFORE torch.distributed.destroy_process_group(), which otherwise waits forever."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        self.last_graph = None
 
     def eval_step(self, triples, seq, lay, eps, beta):
         """Forward only (validation loss, ablation_study.py:92-187 without the generation part)."""

@@ -321,7 +321,7 @@ class Workload:
         return agg, n, mode
 
     def close(self):
-        self.eng._graphs.clear()
+        self.eng.release_graphs()
         del self.eng, self.model, self.dbs, self.eps
         gc.collect()
         torch.cuda.empty_cache()

@@ -374,6 +374,7 @@ def main(argv=None):
         log.log(final)
     log.finish()
     if world > 1:
+        model.engine().release_graphs()     # (captured NCCL kernels must be gone before the group is destroyed)
         torch.distributed.destroy_process_group()
     return model
 
