@@ -44,7 +44,7 @@ class SailEngine:
     _hold_comm, _held = False, ()
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
-    _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding, capture_nccl = False, False, None, False, False     # (the Transformer engines do not fork leaf work)
+    _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding, capture_nccl, post_stream = False, False, None, False, False, None     # (the Transformer engines do not fork leaf work)
     max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
     keep = None                      # tests: a dict that receives references to the GRU stack's internal tensors
 
@@ -86,6 +86,10 @@ class SailEngine:
         # stream, concurrently with the dependent chain (dY -> GRU backward -> dX -> scatter -> encoder backward): they fill
         # the SMs the latency-bound chain kernels leave idle (and each other's partial last waves)
         self.leaf_stream = torch.cuda.Stream(device=dev)
+        # data parallel: the side stream carries ONLY the NCCL calls, back to back; what follows a collective (Adam on the
+        # reduced slice, the global dW GEMM on gathered factors) runs on a third stream so that the HBM-bound update of
+        # bucket i overlaps the NVLink-bound all-reduce of bucket i+1
+        self.post_stream = torch.cuda.Stream(device=dev) if self.world > 1 else self.comm_stream
         self.use_leaf_stream = os.environ.get("ARK_LEAF_STREAM", "1") != "0"
         self.leaf_embedding = os.environ.get("ARK_LEAF_EMB", "0") != "0"
         # data parallel + CUDA graphs: capture the NCCL collectives INTO the step graph (one replay per step) instead of
@@ -637,6 +641,22 @@ class SailEngine:
             torch.cuda.current_stream().wait_stream(self.leaf_stream)
             self._leaf_used = False
 
+    def _join_side(self):
+        """The current stream waits for the side stream(s): collectives and the updates chained behind them."""
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.comm_stream)
+        if self.post_stream is not None and self.post_stream is not self.comm_stream:
+            cur.wait_stream(self.post_stream)
+
+    def _post(self):
+        """Stream context for work that follows a collective (ordered after everything queued on the side stream)."""
+        post = self.post_stream if self.post_stream is not None else self.comm_stream
+        if post is not self.comm_stream:
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+            post.wait_event(ev)
+        return torch.cuda.stream(post)
+
     def _comm_waits_for_leaf(self):
         """Buckets may contain gradients written on the leaf stream: the side stream waits for it too."""
         if self._leaf_used:
@@ -729,14 +749,17 @@ class SailEngine:
             with torch.cuda.stream(self.comm_stream):
                 with self._timed("nccl_all_gather", nbytes=float(dp_all_k.numel() * 2)):
                     torch.distributed.all_gather_into_tensor(dp_all_k, dp_b, group=self.group)
-                d3 = dp_all_k.shape[1]
-                f = self.flat
+            d3 = dp_all_k.shape[1]
+            f = self.flat
+            with self._post():
                 self._gemm(dp_all_k, MN, x_all_k, MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, dp_all_k.shape[0],
                            tag="enc_mlp_dW_global")
                 ops.colsum(dp_all_k, dp_all_k.shape[0], d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks agree bitwise
-                self._bucket_async([f.span(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")], upd, allreduce=False)
+                if upd is not None:
+                    s_, e_ = f.span(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
+                    self._adam_slice(s_, e_, upd)
         elif kind == "join":        # the main stream needs what the side stream produced
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self._join_side()
         else:
             raise ValueError(kind)
 
@@ -749,24 +772,30 @@ class SailEngine:
         self.comm_stream.wait_event(ev)
         self._comm_waits_for_leaf()
         f = self.flat
-        with torch.cuda.stream(self.comm_stream):
-            for (s, e) in spans:
-                if self.world > 1 and allreduce:
+        if self.world > 1 and allreduce:
+            with torch.cuda.stream(self.comm_stream):
+                for (s, e) in spans:
                     with self._timed("nccl_all_reduce", nbytes=4.0 * (e - s)):
                         torch.distributed.all_reduce(f.grad[s:e], group=self.group)
-                if upd is not None:
-                    with self._timed("adam_flat", nbytes=30.0 * (e - s)):
-                        if upd[0] == "dyn":     # graph replay: lr / bias corrections live in device memory
-                            ops.adam_flat_dyn(f.param[s:e], f.grad[s:e], f.exp_avg[s:e], f.exp_avg_sq[s:e], f.shadow[s:e],
-                                              self.dyn_f, self.betas[0], self.betas[1], self.eps)
-                        else:
-                            ops.adam_flat(f.param[s:e], f.grad[s:e], f.exp_avg[s:e], f.exp_avg_sq[s:e], f.shadow[s:e],
-                                          upd[1], self.betas[0], self.betas[1], self.eps, self.step_count)
+        if upd is not None:
+            with self._post():
+                for (s, e) in spans:
+                    self._adam_slice(s, e, upd)
+
+    def _adam_slice(self, s, e, upd):
+        f = self.flat
+        with self._timed("adam_flat", nbytes=30.0 * (e - s)):
+            if upd[0] == "dyn":     # graph replay: lr / bias corrections live in device memory
+                ops.adam_flat_dyn(f.param[s:e], f.grad[s:e], f.exp_avg[s:e], f.exp_avg_sq[s:e], f.shadow[s:e],
+                                  self.dyn_f, self.betas[0], self.betas[1], self.eps)
+            else:
+                ops.adam_flat(f.param[s:e], f.grad[s:e], f.exp_avg[s:e], f.exp_avg_sq[s:e], f.shadow[s:e],
+                              upd[1], self.betas[0], self.betas[1], self.eps, self.step_count)
 
     def _sync_grads(self):
         self._leaf_join()
         self._flush_bucket()
-        torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._join_side()
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, lr=None):
@@ -854,13 +883,13 @@ class SailEngine:
                                                 batch_global, train=True)
                     self._flush_bucket()              # the last gradient slices (world > 1: cuts a segment)
                     if self.world == 1 or self.capture_nccl:
-                        torch.cuda.current_stream().wait_stream(self.comm_stream)    # join the Adam (+ NCCL) branch
+                        self._join_side()    # join the Adam (+ NCCL) branches
                     self.stats[0:2] += out
                     self.stats[2] += 1
                     cur["g"].capture_end()
                     segs.append((cur["g"], []))
             finally:
-                self._capturing, self._upd = False, None
+                self._capturing, self._upd, self._segment_break = False, None, None     # (brk's closure pins the last graph)
             torch.cuda.current_stream().wait_stream(cap)
             st["out"], st["segs"] = out, segs
             st["philox_per_step"] = self._drop_calls * ((lay.n_tok * self.d + 3) // 4)
@@ -882,7 +911,7 @@ class SailEngine:
             for a in actions:
                 self._run_action(a, ("dyn", None))
         if self.world > 1:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)     # the next forward needs every updated weight
+            self._join_side()     # the next forward needs every updated weight
         self.launches_replayed += ent["n_launch"]
         self.philox_offset += ent["philox_per_step"]
         self.last_graph = ent
@@ -894,6 +923,9 @@ class SailEngine:
         torch.cuda.synchronize()
         self._graphs.clear()
         self.last_graph = None
+        self._segment_break = None
+        import gc
+        gc.collect()
 
     def eval_step(self, triples, seq, lay, eps, beta):
         """Forward only (validation loss, ablation_study.py:92-187 without the generation part)."""
