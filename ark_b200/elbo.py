@@ -45,6 +45,7 @@ class SailEngine:
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
     _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding, capture_nccl, post_stream = False, False, None, False, False, None     # (the Transformer engines do not fork leaf work)
+    logits_chunk_rows = 16384        # packed rows per logits workspace chunk (see forward_backward)
     max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
     keep = None                      # tests: a dict that receives references to the GRU stack's internal tensors
 
@@ -398,40 +399,70 @@ class SailEngine:
             saved.append((u_b, hp_f, hp_b, gates, mask))
             u_b = y_b
             del gi
-        logits = new(N, ldv, dtype=bf)
         w_out = self._w("dec.tok_emb.weight") if self.tied else self._w("dec.out.weight")
-        self._gemm(u_b, K, w_out, K, logits, N, V, d, tag="vocab_fwd", bias=f.p("dec.out.bias"))
-        # CE forward+backward in place (ablation_study.py:64-69): logits -> (softmax-onehot)/N_tok
-        ext = None
-        if autograd:
-            # hand the logits out; the caller turns the buffer into d(loss)/d(logits) in place and resumes us
-            ext = yield {"logits": logits, "heads": heads if self.has_enc else None}
-            ext = ext or {}
-            beta = 0.0                       # the KL term (if any) arrives through dmu / dlogv
-        else:
-            with self._timed("softmax_ce", nbytes=2.0 * N * V * 2 + 12.0 * N):
-                ops.softmax_ce(logits, V, tgt, 1.0 / n_tok_g, True, out[0:1], None)
-        if not train:
-            return out
-
-        # ---------------- decoder backward
-        # Order of the backward pass: the CHAIN first (dY -> GRU backward -> dX -> embedding scatter -> encoder), the
-        # LEAVES (weight-gradient GEMMs nothing in this pass consumes) after it, so that the two large late buckets
-        # (token / entity embedding tables: all-reduce + dense Adam on the side stream) overlap the leaf GEMMs.
+        g_wout = f.g("dec.tok_emb.weight") if self.tied else f.g("dec.out.weight")
+        # Token-chunked logits: beyond `logits_chunk_rows` packed rows the [N, V] bf16 logits never exist as
+        # a whole — a fixed workspace of <= chunk rows is projected, turned into its gradient by the fused softmax-CE and
+        # consumed by dY and dW (accumulated over chunks) before the next chunk overwrites it.  wd-articles at 256 graphs
+        # per GPU: 81 k rows x 60 944 columns = 9.9 GB of logits become a 2.0 GB workspace.
+        chunk = int(self.logits_chunk_rows)
+        chunked = (not autograd) and N > chunk
         deferred, keep_alive = [], []
         dx0_src, stack_weight_grads = None, None
-        dy = new(N, d)
-        self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")                         # dY = dLogits . W
+        ext = None
+        if chunked:
+            ws = new(chunk, ldv, dtype=bf)
+            dy = new(N, d) if train else None
+            if train and self.tied:
+                g_wout.zero_()        # the vocabulary dW accumulates here chunk by chunk; the embedding scatter adds on top
+            for ci, r0 in enumerate(range(0, N, chunk)):
+                rows = min(chunk, N - r0)
+                lg = ws[:rows]
+                self._gemm(u_b[r0:r0 + rows], K, w_out, K, lg, rows, V, d, tag="vocab_fwd", bias=f.p("dec.out.bias"))
+                with self._timed("softmax_ce", nbytes=2.0 * rows * V * 2 + 12.0 * rows):
+                    ops.softmax_ce(lg, V, tgt[r0:r0 + rows], 1.0 / n_tok_g, True, out[0:1], None)
+                if train:
+                    self._gemm(lg, K, w_out, MN, dy[r0:r0 + rows], rows, d, V, tag="vocab_dY")
+                    self._gemm(lg, MN, u_b[r0:r0 + rows], MN, g_wout, V, d, rows, tag="vocab_dW",
+                               accumulate=(ci > 0 or self.tied))
+                    ops.colsum(lg, rows, V, f.g("dec.out.bias"), accumulate=ci > 0)
+            if not train:
+                return out
 
-        def vocab_weight_grads(logits=logits):
-            g_wout = f.g("dec.tok_emb.weight") if self.tied else f.g("dec.out.weight")
-            # dW = dLogits^T . Y; tied weights: on top of the embedding scatter already in the slot
-            self._gemm(logits, MN, u_b, MN, g_wout, V, d, N, tag="vocab_dW", accumulate=self.tied)
-            ops.colsum(logits, N, V, f.g("dec.out.bias"))
-            self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
-            if self.tied:
-                self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
-        del logits
+            def vocab_weight_grads():
+                self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
+                if self.tied:
+                    self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+        else:
+            logits = new(N, ldv, dtype=bf)
+            self._gemm(u_b, K, w_out, K, logits, N, V, d, tag="vocab_fwd", bias=f.p("dec.out.bias"))
+            # CE forward+backward in place (ablation_study.py:64-69): logits -> (softmax-onehot)/N_tok
+            if autograd:
+                # hand the logits out; the caller turns the buffer into d(loss)/d(logits) in place and resumes us
+                ext = yield {"logits": logits, "heads": heads if self.has_enc else None}
+                ext = ext or {}
+                beta = 0.0                       # the KL term (if any) arrives through dmu / dlogv
+            else:
+                with self._timed("softmax_ce", nbytes=2.0 * N * V * 2 + 12.0 * N):
+                    ops.softmax_ce(logits, V, tgt, 1.0 / n_tok_g, True, out[0:1], None)
+            if not train:
+                return out
+
+            # ---------------- decoder backward
+            # Order of the backward pass: the CHAIN first (dY -> GRU backward -> dX -> embedding scatter -> encoder), the
+            # LEAVES (weight-gradient GEMMs nothing in this pass consumes) on the leaf stream, so that the two large late
+            # buckets (token / entity embedding tables: all-reduce + dense Adam on the side stream) overlap them.
+            dy = new(N, d)
+            self._gemm(logits, K, w_out, MN, dy, N, d, V, tag="vocab_dY")                         # dY = dLogits . W
+
+            def vocab_weight_grads(logits=logits):
+                # dW = dLogits^T . Y; tied weights: on top of the embedding scatter already in the slot
+                self._gemm(logits, MN, u_b, MN, g_wout, V, d, N, tag="vocab_dW", accumulate=self.tied)
+                ops.colsum(logits, N, V, f.g("dec.out.bias"))
+                self._grad_ready("dec.out.bias", "dec.out.weight" if not self.tied else "dec.out.bias")
+                if self.tied:
+                    self._grad_ready("dec.tok_emb.weight", "dec.tok_emb.weight")
+            del logits
         dh0 = new(b0, d)
         if wave:
             w_t = new(2 * nl, d, d3, dtype=bf)
@@ -514,7 +545,8 @@ class SailEngine:
             # stream with dh0 only)
             if dx0_src is not None:
                 self._gemm(dx0_src, K, self._w("dec.gru.weight_ih_l0"), MN, dy, N, d, d3, tag="gru_dX")
-            f.g("dec.tok_emb.weight").zero_()
+            if not (chunked and self.tied):       # (chunked + tied: the slot already holds the accumulated vocabulary dW)
+                f.g("dec.tok_emb.weight").zero_()
             with self._timed("tok_scatter_add", nbytes=N * d * 12.0):
                 ops.tok_scatter_add(dy, tok, f.g("dec.tok_emb.weight"))
             if not self.tied:             # (tied: final once the vocabulary dW has been added on top of the scatter)

@@ -821,3 +821,31 @@ def test_ark_posterior_bits_and_sampled_generation_match_reference():
     torch.manual_seed(5)
     b = model.generate(cfg["seq_len"], cfg["special_tokens"], batch_size=4, sample=True, top_p=0.9)
     assert torch.equal(a, b) and a.shape == (4, cfg["seq_len"]) and int(a.max()) < cfg["vocab_size"]
+
+
+@pytest.mark.parametrize("tied", [True, False])
+def test_token_chunked_logits_workspace_matches_unchunked(tied):
+    """beyond `logits_chunk_rows` packed rows the logits live in a bounded workspace that is projected,
+    CE'd and consumed (dY, dW accumulated, bias column sums) chunk by chunk — same loss and gradients as the
+    whole-tensor path (fp32 accumulation order of dW aside)."""
+    cfg, tri, seq, rng = _random_case(41, nE=700, nR=6, lo=1, hi=14, pad=True, d=64, dz=16, nl=2, B=96)
+    cfg["tie_weights"] = tied
+    eps = torch.from_numpy(rng.standard_normal((96, 16)).astype(np.float32)).to(DEV)
+    seq_t = torch.from_numpy(seq)
+    lay = pack_layout(seq_t).to(DEV)
+    tri_d, seq_d = torch.from_numpy(tri).to(DEV), seq_t.to(DEV)
+    res = []
+    for chunk in (1 << 20, 500):
+        torch.manual_seed(8)
+        eng = SAIL(dict(cfg)).to(DEV).engine()
+        eng.logits_chunk_rows = chunk
+        out = eng.forward_backward(tri_d, seq_d, lay, eps, 0.5).clone()
+        ev = eng.eval_step(tri_d, seq_d, lay, eps, 0.5).clone()
+        res.append((out, eng.flat.grad.clone(), ev, eng))
+    assert lay.n_tok > 1500          # at least four chunks of 500 rows
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(res[0][2], res[1][2], rtol=1e-4, atol=1e-6)
+    for name in res[0][3].flat.order:
+        a, b = res[0][3].flat.g(name), res[1][3].flat.g(name)
+        if a.norm() > 0:
+            assert ((a - b).norm() / a.norm()).item() < 2e-3, name
