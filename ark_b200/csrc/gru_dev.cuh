@@ -14,14 +14,22 @@ __device__ __forceinline__ int ld_acquire(const int32_t* p) {
 __device__ __forceinline__ void red_release_add(int32_t* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ int ld_relaxed(const int32_t* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Poll with RELAXED loads and order once at the end (one acquire fence): an acquire load per poll costs a fence per
+// round trip on the recurrent chain.
 __device__ __forceinline__ void wait_counter(const int32_t* p, int target) {
-  for (ptx::SpinGuard g; ld_acquire(p) < target;) {
+  for (ptx::SpinGuard g; ld_relaxed(p) < target;) {
     if (g.expired()) {
       printf("arkb200: gru_persist tile counter timed out (block %d,%d want %d have %d)\n", blockIdx.x, blockIdx.y,
              target, ld_acquire(p));
       __trap();
     }
   }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 

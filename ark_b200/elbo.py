@@ -45,6 +45,7 @@ class SailEngine:
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
     _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding, capture_nccl, post_stream = False, False, None, False, False, None     # (the Transformer engines do not fork leaf work)
+    nvtx = os.environ.get("ARK_NVTX", "0") != "0"   # NVTX range per kernel family (same tags as bench.py's `kernels` list)
     logits_chunk_rows = 16384        # packed rows per logits workspace chunk (see forward_backward)
     max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
     keep = None                      # tests: a dict that receives references to the GRU stack's internal tensors
@@ -162,6 +163,8 @@ class SailEngine:
             self.eng, self.tag, self.flops, self.nbytes = eng, tag, flops, nbytes
 
         def __enter__(self):
+            if SailEngine.nvtx:
+                torch.cuda.nvtx.range_push(self.tag)
             if self.eng.prof is not None:
                 # inside a stream capture the events become EXTERNAL event-record nodes of the graph: every replay
                 # re-records them, so elapsed_time() after a replay is the kernel's time inside the replayed graph
@@ -175,6 +178,8 @@ class SailEngine:
             if self.eng.prof is not None:
                 self.e1.record()
                 self.eng.prof.append((self.tag, self.e0, self.e1, self.flops, self.nbytes))
+            if SailEngine.nvtx:
+                torch.cuda.nvtx.range_pop()
 
     def _timed(self, tag, flops=0.0, nbytes=0.0):
         """CUDA events around one op on the launching stream when `self.prof` is a list (bench.py's roofline

@@ -433,12 +433,14 @@ def main():
     w.close()
 
     # ---------------- the other BASELINE workloads, same invocation (N = 1 only: keeps the multi-rank runs short)
+    # N > 1: every rank runs the wd-articles large-batch configuration too (BASELINE.json's last config: the >= 7x at
+    # 8 GPUs target is quoted on it), so that the driver's scaling runs carry it at every N.
     also = []
-    if rank == 0 and world == 1 and not args.no_also and args.model == "SAIL" and not args.dense and not args.batch:
-        extra = [(x, 0) for x in WORKLOADS if x != args.workload] + [("wd-articles", 256)]
+    if not args.no_also and args.model == "SAIL" and not args.dense and not args.batch and args.scaling == "weak":
+        extra = ([(x, 0) for x in WORKLOADS if x != args.workload] + [("wd-articles", 256)]) if world == 1 else [("wd-articles", 256)]
         for wl, b_ in extra:
             try:
-                o = Workload(args, wl, "SAIL", b_, False, dev, None, 1, 0, use_graph)
+                o = Workload(args, wl, "SAIL", b_, False, dev, group, world, rank, use_graph)
                 med, ts = o.measure(args.steps, args.warmup, 3)
                 ag, npf, md = o.kernel_profile(4)
                 rws = kernel_table(ag, npf, med / args.steps, pk, wl if not b_ else "-")
@@ -447,7 +449,7 @@ def main():
                        "tokens_per_step": o.dbs[0].layout.n_tok, "roofline": roofline_from(rws, pk, md),
                        "kernels": [{k: r.get(k) for k in ("name", "ms_per_step", "launches_per_step", "bound", "achieved", "unit", "frac")}
                                    for r in rws[:8]]}
-                if o.cfg.get("use_padding"):
+                if o.cfg.get("use_padding") and world == 1:
                     ent["note"] = ("ragged workload: the timed steps replay CUDA graphs captured for 4 fixed batch layouts; "
                                    "`eager_fresh` draws a NEW ragged batch every step (no graph)")
                     from ark_b200.synthetic import DeviceBatch, synth_batch
@@ -463,9 +465,12 @@ def main():
                     fms = statistics.median([o.window(args.steps, fstep) for _ in range(3)])
                     ent["eager_fresh"] = {"value": sum(n for _, _, n in fresh) / (fms / 1e3), "ms_per_step": fms / args.steps}
                     del fdb, feps
+                ent["n_gpus"], ent["global_batch"] = world, o.bg
                 also.append(ent)
                 o.close()
             except Exception as e:     # an extra workload must never take the headline line down
+                if world > 1:
+                    raise
                 also.append({"workload": f"autoreg_{wl} SAIL", "graphs_per_gpu": b_, "error": f"{type(e).__name__}: {e}"[:300]})
 
     if rank == 0:

@@ -93,8 +93,9 @@ class AutoRegEncoderMLP(nn.Module):
         return z, mu, logv
 
 
-def _gru_stack_f32(gru, x, h0, B, Lp):
-    """fp32 multi-layer GRU over time-major rows (t, b) on the library's kernels (eval semantics)."""
+def _gru_stack_f32(gru, x, h0, B, Lp, return_states=False):
+    """fp32 multi-layer GRU over time-major rows (t, b) on the library's kernels (eval semantics).
+    `h0`: one [B, d] tensor shared by every layer (reference models.py:140) or a list with one per layer."""
     dev = x.device
     d = x.shape[1]
     N = B * Lp
@@ -102,17 +103,19 @@ def _gru_stack_f32(gru, x, h0, B, Lp):
     off = (np.arange(Lp + 1, dtype=np.int32) * B).astype(np.int32)
     gh_ws = torch.empty(B, 3 * d, device=dev)
     u = x
+    finals = []
     for k in range(gru.num_layers):
         w_ih, w_hh = getattr(gru, f"weight_ih_l{k}").detach(), getattr(gru, f"weight_hh_l{k}").detach()
         b_ih, b_hh = getattr(gru, f"bias_ih_l{k}").detach(), getattr(gru, f"bias_hh_l{k}").detach()
         gi = torch.empty(N, 3 * d, device=dev)
         ops.gemm(u, K, w_ih, K, gi, N, 3 * d, d, bias=b_ih, backend="simt")
         hp = torch.empty(N, d, device=dev)
-        hp[:B].copy_(h0)
+        hp[:B].copy_(h0[k] if isinstance(h0, (list, tuple)) else h0)
         y = torch.empty(N, d, device=dev)
         ops.gru_layer_fwd(None, hp, w_hh, gi, b_hh, bt, off, Lp, d, y, None, None, gh_ws, 0)
         u = y
-    return u
+        finals.append(y[N - B:])
+    return (u, finals) if return_states else u
 
 
 class AutoRegDecoderGRU(nn.Module):
@@ -144,6 +147,24 @@ class AutoRegDecoderGRU(nn.Module):
         u = _gru_stack_f32(self.gru, x, h0, B, Lp)
         logits = _linear_f32(u, self.out)
         return logits.view(Lp, B, -1).transpose(0, 1).contiguous()
+
+    # ---- incremental decoding: one GRU step per generated token instead of re-decoding the prefix
+    @torch.no_grad()
+    def init_state(self, z):
+        """Per-layer hidden state before any token: h0 = tanh(z_proj z) for every layer (models.py:139-140)."""
+        h0 = _linear_f32(z.to(torch.float32).contiguous(), self.z_proj, ops.EPI_TANH)
+        return [h0] * self.gru.num_layers
+
+    @torch.no_grad()
+    def step(self, tok, state, pos=None):
+        """(logits [B, V] of the NEXT token, new state) after consuming `tok` [B] — bit-identical to
+        `self(z, prefix)[:, -1]` with `state` = the state after prefix[:, :-1] (same kernels, same operation order)."""
+        B = tok.shape[0]
+        d = self.tok_emb.weight.shape[1]
+        x = torch.empty(B, d, device=tok.device)
+        ops.tok_gather_fwd(self.tok_emb.weight.detach(), tok.to(torch.int32).contiguous(), x, None)
+        u, new_state = _gru_stack_f32(self.gru, x, state, B, 1, return_states=True)
+        return _linear_f32(u, self.out), new_state
 
 
 class AutoRegEncoder(nn.Module):
@@ -436,19 +457,27 @@ class SAIL(_EngineMixin, nn.Module):
 
     @torch.no_grad()
     def beam_generate(self, seq_len, special_tokens, seq_to_triples, z, ent_base, rel_base, beam=4):
-        """Batch-shared beam search ranked by the batch-MEAN log-probability — the reference's exact
-        procedure (models.py:283-300), including re-decoding the whole prefix at every step."""
+        """Batch-shared beam search ranked by the batch-MEAN log-probability — the reference's exact procedure
+        (models.py:283-300).  The reference re-decodes the whole prefix for every candidate and step (O(L^2) decoder
+        work); here every beam carries its GRU hidden states and a step consumes ONE token (same kernels, same
+        arithmetic, so the integer outputs are unchanged — tests/test_elbo_gpu.py)."""
         dev, B = z.device, z.size(0)
         eos = special_tokens["EOS"]
-        beams = [(torch.full((B, 1), special_tokens["BOS"], dtype=torch.long, device=dev), torch.zeros(B, device=dev))]
+        incremental = hasattr(self.dec, "step")      # GRU decoder: hidden-state cache (one step per token, not O(L^2))
+        state0 = self.dec.init_state(z) if incremental else None
+        beams = [(torch.full((B, 1), special_tokens["BOS"], dtype=torch.long, device=dev), torch.zeros(B, device=dev), state0)]
         for _ in range(seq_len - 1):
             grown = []
-            for prefix, score in beams:
-                logp = F.log_softmax(self.dec(z, prefix)[:, -1], dim=-1)
+            for prefix, score, state in beams:
+                if incremental:      # `state` = the decoder state after prefix[:, :-1]
+                    logits, nstate = self.dec.step(prefix[:, -1], state)
+                else:
+                    logits, nstate = self.dec(z, prefix)[:, -1], None
+                logp = F.log_softmax(logits, dim=-1)
                 best, idx = logp.topk(beam, dim=-1)
-                grown += [(torch.cat([prefix, idx[:, j:j + 1]], 1), score + best[:, j]) for j in range(beam)]
+                grown += [(torch.cat([prefix, idx[:, j:j + 1]], 1), score + best[:, j], nstate) for j in range(beam)]
             beams = sorted(grown, key=lambda c: c[1].mean().item(), reverse=True)[:beam]
-            if all(bool((p[:, -1] == eos).all()) for p, _ in beams):
+            if all(bool((p[:, -1] == eos).all()) for p, _, _ in beams):
                 break
         return [seq_to_triples(row, special_tokens, ent_base, rel_base) for row in beams[0][0].cpu()]
 
@@ -492,6 +521,23 @@ class DecoderOnlyGRU(nn.Module):
         u = _gru_stack_f32(self.gru, x, torch.zeros(B, d, device=seq_in.device), B, Lp)
         logits = _linear_f32(u, self.out)
         return logits.view(Lp, B, -1).transpose(0, 1).contiguous()
+
+    @torch.no_grad()
+    def init_state(self, B, device):
+        d = self.tok_emb.weight.shape[1]
+        return [torch.zeros(B, d, device=device) for _ in range(self.gru.num_layers)]
+
+    @torch.no_grad()
+    def step(self, tok, state, pos):
+        """(next-token logits [B, V], new state) after consuming `tok` [B] at position `pos` — bit-identical to
+        `self(prefix)[:, -1]` (incremental decoding)."""
+        B = tok.shape[0]
+        d = self.tok_emb.weight.shape[1]
+        x = torch.empty(B, d, device=tok.device)
+        ops.tok_gather_fwd(self.tok_emb.weight.detach(), tok.to(torch.int32).contiguous(), x, None)
+        x = (x + self.pos_emb.weight.detach()[pos][None, :]).contiguous()
+        u, new_state = _gru_stack_f32(self.gru, x, state, B, 1, return_states=True)
+        return _linear_f32(u, self.out), new_state
 
 
 class DecoderOnlyTransformer(nn.Module):
@@ -573,12 +619,19 @@ class ARK(_EngineMixin, nn.Module):
     @torch.no_grad()
     def generate(self, seq_len, special_tokens, device=None, batch_size=1, beam=1, sample=False, temperature=1.0,
                  top_p=0.0, top_k=0):
-        """Greedy or sampled generation, full prefix re-decoded per step (reference: models.py:408-471)."""
+        """Greedy or sampled generation (reference: models.py:408-471; its temperature / top-k / top-p filtering verbatim as
+        torch ops on the GPU).  The GRU model decodes incrementally from cached hidden states instead of re-decoding
+        the prefix at every step."""
         device = device or next(self.parameters()).device
         eos = special_tokens["EOS"]
         seq = torch.full((batch_size, 1), special_tokens["BOS"], dtype=torch.long, device=device)
-        for _ in range(seq_len - 1):
-            logits = self.dec(seq)[:, -1]
+        incremental = hasattr(self.dec, "step")      # GRU decoder: hidden-state cache, one step per token
+        state = self.dec.init_state(batch_size, device) if incremental else None
+        for t in range(seq_len - 1):
+            if incremental:
+                logits, state = self.dec.step(seq[:, -1], state, t)
+            else:
+                logits = self.dec(seq)[:, -1]
             if not sample:
                 nxt = logits.argmax(dim=-1, keepdim=True)
             else:

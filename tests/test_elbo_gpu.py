@@ -849,3 +849,24 @@ def test_token_chunked_logits_workspace_matches_unchunked(tied):
         a, b = res[0][3].flat.g(name), res[1][3].flat.g(name)
         if a.norm() > 0:
             assert ((a - b).norm() / a.norm()).item() < 2e-3, name
+
+
+def test_incremental_decoding_equals_prefix_redecoding():
+    """generation carries the GRU hidden states and consumes ONE token per step; the logits must be
+    bit-identical to the reference's procedure of re-decoding the whole prefix (models.py:291, 430)."""
+    arr, meta, params, _ = load_sail_golden("wd")
+    cfg = meta["cfg"]
+    model = _model_from(params, cfg).eval()
+    z = torch.from_numpy(arr["beam_z"]).to(DEV)
+    seq = torch.from_numpy(arr["seq"][:z.shape[0]]).to(DEV)
+    state = model.dec.init_state(z)
+    for t in range(seq.shape[1] - 1):
+        logits, state = model.dec.step(seq[:, t], state)
+        assert torch.equal(logits, model.dec(z, seq[:, :t + 1])[:, -1]), t
+    arr2, meta2, _, _ = load_ark_golden("wd")
+    ark = _ark_from({k[len("adam_param::"):]: v for k, v in arr2.items() if k.startswith("adam_param::")}, meta2["cfg"]).eval()
+    seq2 = torch.from_numpy(arr2["seq"][:3]).to(DEV)
+    st = ark.dec.init_state(3, DEV)
+    for t in range(seq2.shape[1] - 1):
+        logits, st = ark.dec.step(seq2[:, t], st, t)
+        assert torch.equal(logits, ark.dec(seq2[:, :t + 1])[:, -1]), t
