@@ -66,8 +66,14 @@ def pack_layout(seq_cpu: torch.Tensor) -> PackedLayout:
     if seq_cpu.is_cuda:
         raise ValueError("pack_layout works on the host copy of the batch (lengths are host metadata)")
     s = seq_cpu.numpy()
-    B, seq_len = s.shape
-    lens = (s[:, 1:] != PAD).sum(1).astype(np.int32)          # targets that are not PAD
+    return pack_layout_from_lens((s[:, 1:] != PAD).sum(1).astype(np.int32))          # targets that are not PAD
+
+
+def pack_layout_from_lens(lens: np.ndarray) -> PackedLayout:
+    """Layout from the live decoder positions per graph (3 n_b + 1) alone — what a loader that keeps the tensorised
+    split on the GPU knows on the host without reading any token back."""
+    lens = np.asarray(lens, dtype=np.int32)
+    B = len(lens)
     if B and lens[0] > 0 and (lens == lens[0]).all():
         return _uniform_layout(B, int(lens[0]))
     perm = np.argsort(-lens, kind="stable").astype(np.int32)

@@ -48,6 +48,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.engine.betas, self.engine.eps = tuple(g["betas"]), float(g["eps"])
         for st in self.state.values():
             st["step"] = torch.tensor(float(self.engine.step_count))
+        self._opt_called = True      # (LR schedulers check that the optimiser stepped before they do)
 
     def load_state_dict(self, state_dict):
         f = self.engine.flat

@@ -114,7 +114,7 @@ class BatchLoader:
     """
 
     def __init__(self, graphs, vocab, batch_size, rank=0, world=1, shuffle=False, drop_last=True, permute=False,
-                 seed=0, triple_order="keep", i2e=None, i2r=None):
+                 seed=0, triple_order="keep", i2e=None, i2r=None, device=None):
         if triple_order != "keep":       # reference: GraphSeqDataset canonicalises every graph (utils.py:96-99,115)
             graphs = [canonicalize(g, i2e, i2r, triple_order) for g in graphs]
         self.graphs = graphs             # (posterior_bits iterates a GraphSeqDataset over the same canonical graphs)
@@ -140,6 +140,12 @@ class BatchLoader:
         if pin:
             self.tri, self.seq = self.tri.pin_memory(), self.seq.pin_memory()
             self.tri_e, self.seq_e = self.tri_e.pin_memory(), self.seq_e.pin_memory()
+        # ON-DEVICE batch assembly: the tensorised split lives in HBM (wd-articles: ~10 KB per graph); an
+        # epoch's order / triple permutation is applied there and a batch is a slice of device memory — no per-step
+        # host->device copy of tokens at all.  The packed layout needs only the per-graph lengths, which the host has.
+        self.device = torch.device(device) if device is not None else None
+        if self.device is not None:
+            self.tri_d, self.seq_d = self.tri.to(self.device), self.seq.to(self.device)
 
     def __len__(self):
         per = self.B * self.world
@@ -148,20 +154,32 @@ class BatchLoader:
     def __iter__(self):
         self.epoch += 1
         tri, seq, lens = self.tri, self.seq, self.lens
+        tri_d, seq_d = (self.tri_d, self.seq_d) if self.device is not None else (None, None)
         if self.shuffle or (self.permute and not self.v["use_padding"]):
-            if torch.cuda.is_available():
-                torch.cuda.synchronize()     # last epoch's async H2D copies read tri_e / seq_e: finish them before rewriting
             rng = np.random.default_rng(self.seed + self.epoch)
             order = torch.from_numpy(rng.permutation(self.G) if self.shuffle else np.arange(self.G))
-            torch.index_select(self.tri, 0, order, out=self.tri_e)
-            torch.index_select(self.seq, 0, order, out=self.seq_e)
-            tri, seq, lens = self.tri_e, self.seq_e, self.lens[order.numpy()]
-            if self.permute and not self.v["use_padding"] and tri.shape[1] > 1:     # reference: utils.py:133-134
-                T = tri.shape[1]
-                p = torch.from_numpy(np.argsort(rng.random((self.G, T)), axis=1))     # a random order per graph
-                tri.copy_(torch.gather(tri, 1, p[:, :, None].expand(-1, -1, 3)))
-                tok = seq[:, 1:1 + 3 * T].reshape(self.G, T, 3)
-                seq[:, 1:1 + 3 * T] = torch.gather(tok, 1, p[:, :, None].expand(-1, -1, 3)).reshape(self.G, 3 * T)
+            lens = self.lens[order.numpy()]
+            T = tri.shape[1]
+            perm_tri = self.permute and not self.v["use_padding"] and T > 1                 # reference: utils.py:133-134
+            p = torch.from_numpy(np.argsort(rng.random((self.G, T)), axis=1)) if perm_tri else None   # a random order per graph
+            if self.device is None:
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()     # last epoch's async H2D copies read tri_e / seq_e: finish them before rewriting
+                torch.index_select(self.tri, 0, order, out=self.tri_e)
+                torch.index_select(self.seq, 0, order, out=self.seq_e)
+                tri, seq = self.tri_e, self.seq_e
+                if perm_tri:
+                    tri.copy_(torch.gather(tri, 1, p[:, :, None].expand(-1, -1, 3)))
+                    tok = seq[:, 1:1 + 3 * T].reshape(self.G, T, 3)
+                    seq[:, 1:1 + 3 * T] = torch.gather(tok, 1, p[:, :, None].expand(-1, -1, 3)).reshape(self.G, 3 * T)
+            else:                                # the same order / permutation, applied to the device-resident copy
+                order_d = order.to(self.device)
+                tri_d, seq_d = self.tri_d.index_select(0, order_d), self.seq_d.index_select(0, order_d)
+                if perm_tri:
+                    p_d = p.to(self.device)[:, :, None].expand(-1, -1, 3)
+                    tri_d = torch.gather(tri_d, 1, p_d)
+                    tok_d = seq_d[:, 1:1 + 3 * T].reshape(self.G, T, 3)
+                    seq_d[:, 1:1 + 3 * T] = torch.gather(tok_d, 1, p_d).reshape(self.G, 3 * T)
         per = self.B * self.world
         for g in range(len(self)):
             lo = g * per
@@ -169,7 +187,12 @@ class BatchLoader:
             a, b = lo + self.rank * self.B, min(lo + (self.rank + 1) * self.B, hi)
             if b <= a:
                 continue
-            yield tri[a:b], seq[a:b], int(lens[lo:hi].sum()), hi - lo
+            if self.device is not None:
+                from ark_b200.layout import pack_layout_from_lens
+                yield (tri_d[a:b], seq_d[a:b], int(lens[lo:hi].sum()), hi - lo,
+                       pack_layout_from_lens(lens[a:b]).to(self.device))
+            else:
+                yield tri[a:b], seq[a:b], int(lens[lo:hi].sum()), hi - lo
 
 
 # --------------------------------------------------------------------------------------------- loops
@@ -189,13 +212,14 @@ def train_epoch(model, dataloader, optimizer, config, device, b=1.0, eps_fn=None
         triples, seq = batch[0], batch[1]
         ntg = batch[2] if len(batch) > 2 else None
         bg = batch[3] if len(batch) > 3 else None
+        lay = batch[4] if len(batch) > 4 else None          # device-resident loader: layout from host-side lengths
         eps = None if eps_fn is None else eps_fn(i)
         if fused:
             lr = float(optimizer.param_groups[0]["lr"])
             if mt in ("ARK", "t-ARK"):       # decoder-only: loss = CE, KL = 0 (reference train.py:42-58)
-                model.ce_step(seq, lr=lr, n_tok_global=ntg)
+                model.ce_step(seq, layout=lay, lr=lr, n_tok_global=ntg)
             else:
-                model.elbo_step(triples, seq, b, eps=eps, lr=lr, n_tok_global=ntg, batch_global=bg, graph=replay)
+                model.elbo_step(triples, seq, b, eps=eps, layout=lay, lr=lr, n_tok_global=ntg, batch_global=bg, graph=replay)
             continue
         optimizer.zero_grad()
         if mt in ("ARK", "t-ARK"):
@@ -300,7 +324,8 @@ def main(argv=None):
     B = config["batch_size"]
     order = config.get("triple_order", "keep")
     train_loader = BatchLoader(train_g, vocab, B, rank, world, shuffle=config["shuffle_train"], drop_last=True,
-                               permute=config.get("permute_triples", False), triple_order=order, i2e=i2e, i2r=i2r)
+                               permute=config.get("permute_triples", False), triple_order=order, i2e=i2e, i2r=i2r,
+                               device=device if config.get("device_resident_data", True) else None)
     val_loader = BatchLoader(val_g, vocab, B, 0, 1, drop_last=False, triple_order=order, i2e=i2e, i2r=i2r)
     test_loader = BatchLoader(test_g, vocab, B, 0, 1, drop_last=False, triple_order=order, i2e=i2e, i2r=i2r)
 

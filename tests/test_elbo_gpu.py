@@ -870,3 +870,26 @@ def test_incremental_decoding_equals_prefix_redecoding():
     for t in range(seq2.shape[1] - 1):
         logits, st = ark.dec.step(seq2[:, t], st, t)
         assert torch.equal(logits, ark.dec(seq2[:, :t + 1])[:, -1]), t
+
+
+def test_device_resident_loader_yields_the_same_batches_as_the_host_loader():
+    """on-device batch assembly — the tensorised split lives in HBM, an epoch's shuffle / per-graph triple
+    permutation is applied there and a batch is a slice of device memory; integers identical to the host loader's."""
+    from kgvae.experiments.train import BatchLoader
+    rng = np.random.default_rng(3)
+    for pad in (True, False):
+        lay = O.vocab_layout(40, 4, 5, pad)
+        graphs = [[(int(rng.integers(40)), int(rng.integers(4)), int(rng.integers(40)))
+                   for _ in range(int(rng.integers(1, 6)) if pad else 5)] for _ in range(37)]
+        v = {"ENT_BASE": lay["ENT_BASE"], "REL_BASE": lay["REL_BASE"], "seq_len": lay["seq_len"], "max_edges": 5,
+             "use_padding": pad, "pad_eid": lay["pad_eid"], "pad_rid": lay["pad_rid"]}
+        kw = dict(shuffle=True, permute=True, seed=5)
+        host = BatchLoader(graphs, v, 8, **kw)
+        dev = BatchLoader(graphs, v, 8, device=DEV, **kw)
+        for _ in range(2):      # two epochs: different orders
+            hb, db = list(host), list(dev)
+            assert len(hb) == len(db) == 4
+            for (t, s, ntg, bg), (td, sd, ntg2, bg2, layd) in zip(hb, db):
+                assert td.is_cuda and torch.equal(td.cpu(), t) and torch.equal(sd.cpu(), s) and (ntg, bg) == (ntg2, bg2)
+                ref = pack_layout(s)
+                assert layd.n_tok == ref.n_tok and np.array_equal(layd.bt, ref.bt) and np.array_equal(layd.perm, ref.perm)

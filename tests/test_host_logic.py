@@ -260,3 +260,24 @@ def test_bf16_partial_sum_reduce_scatter_error_is_operand_rounding_sized():
     op_rel = (np.linalg.norm(bf16(g32).astype(np.float64) @ bf16(W32).astype(np.float64) - g32.astype(np.float64) @ W32)
               / np.linalg.norm(g32.astype(np.float64) @ W32))
     assert rel < 4e-3 and rel < 2.0 * op_rel, (rel, op_rel)
+
+
+def test_bench_kernel_table_and_roofline_selection():
+    """bench.py picks the single kernel with the largest in-graph time as `roofline` (never an aggregate of families),
+    computes achieved / peak from the algorithmic work and attaches the ncu DRAM traffic of that kernel."""
+    import bench
+    pk = {"hbm_gbs": 6552.0, "bf16_tflops": 1641.5, "bf16_tflops_sustained": 1386.4, "src": "measured"}
+    agg = {"gru_persist_bwd": {"ms": 0.9, "calls": 9, "flops": 9 * 16.1e9, "bytes": 0.0},
+           "gemm_tc:gru_gi": {"ms": 0.27, "calls": 9, "flops": 9 * 16.1e9, "bytes": 0.0},
+           "softmax_ce": {"ms": 0.05, "calls": 3, "flops": 0.0, "bytes": 3 * 1.2e6},
+           "nccl_all_reduce": {"ms": 1.2, "calls": 15, "flops": 0.0, "bytes": 15 * 4e7}}
+    rows = bench.kernel_table(agg, 3, 1.25, pk, "syn-types")
+    assert [r["name"] for r in rows] == ["nccl_all_reduce", "gru_persist_bwd", "gemm_tc:gru_gi", "softmax_ce"]
+    roof = bench.roofline_from(rows, pk, "graph-replay event nodes")
+    assert roof["kernel"] == "gru_persist_bwd" and roof["bound"] == "tensor"          # NCCL is never "our top kernel"
+    assert abs(roof["achieved"] - 16.1e9 / (0.1e-3) / 1e12) < 1e-6 and abs(roof["frac"] - roof["achieved"] / 1386.4) < 1e-9
+    assert roof["launches_per_step"] == 3.0 and abs(roof["share_of_step"] - 0.3 / 1.25) < 1e-9
+    ce = [r for r in rows if r["name"] == "softmax_ce"][0]
+    assert ce["bound"] == "hbm" and abs(ce["achieved"] - 1.2e6 / (0.05e-3 / 3) / 1e9) < 1e-3
+    if ("syn-types", "gru_persist_bwd") in bench.NCU_TRAFFIC:
+        assert roof["traffic"] == bench.NCU_TRAFFIC[("syn-types", "gru_persist_bwd")][0]
