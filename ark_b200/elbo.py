@@ -113,7 +113,7 @@ class SailEngine:
         self.dyn_beta = self._dyn_raw[16:20].view(torch.float32)     # beta of the ELBO (changes every epoch: NOT a graph key)
         self.launches_replayed = 0       # kernels of libarkb200 executed through graph replays
         self.force_unfused_gru = False   # tests: compare the persistent GRU kernel with the per-step path
-        self.gru_mode = "auto"           # "auto": cluster stack kernel (long chains of short batch tiles), else the
+        self.gru_mode = os.environ.get("ARK_GRU_MODE", "auto")   # "auto": cluster stack kernel (long chains of short batch tiles), else the
                                          # wavefront stack kernel when it fits, else per-layer persistent;
                                          # "wave": never the cluster kernel; "layer": neither (tests / A-B timing)
         self._gru_cluster_ws = None      # scratch of the cluster GRU kernels (gi^T / dx^T slices), grown on demand
@@ -248,6 +248,12 @@ class SailEngine:
         cl_nb = (self._use_gru_cluster(d, b0, nl, L)
                  if (use_tc and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru) else 0)
         wave_ok = use_tc and not self.force_unfused_gru and ops.gru_wave_supported(d, b0, nl) > 0
+        # A wavefront grid larger than the GPU (d = 512 with two batch tiles: 32 x 2 x 3 = 192 CTAs) runs its tile groups
+        # back to back; there the per-layer kernels (half-tile forward, K-split backward) are faster although they take
+        # nl * L dependent steps (measured on syn-paths: 0.82 vs 0.89 ms per training step)
+        if (wave_ok and self.gru_mode == "auto" and (d // 16) * ((b0 + 127) // 128) * nl > 148
+                and ops.gru_persist_bwd_ksplit(d, b0) and b0 > 64):
+            wave_ok = False
         cluster = cl_nb > 0
         # the two stack kernels share every tensor of their contract, so the direction can be chosen separately: with
         # 64-row batch tiles the cluster backward (16 work items per epilogue thread) is no faster than the wavefront's
