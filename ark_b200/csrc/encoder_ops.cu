@@ -92,9 +92,10 @@ __global__ void __launch_bounds__(GP_MAX_THREADS) gather_pool_fwd_kernel(
 // grid (B, 3, Z): every valid triple of graph perm[b] receives the SAME slice dg[b, slot]/cnt_b, so the value is
 // loaded once into registers and pushed with one 16-byte L2 reduction per (triple, float4); the Z CTAs of a
 // (graph, slot) split the triples.
+constexpr int kRelHist = 64;    // relation tables up to this many rows are accumulated through a per-CTA histogram
 __global__ void __launch_bounds__(256) gather_pool_bwd_kernel(
     const float* __restrict__ dg, const int64_t* __restrict__ triples, const int32_t* __restrict__ perm,
-    const float* __restrict__ inv_cnt, int T, int d, long long pad_rid, long long pad_eid,
+    const float* __restrict__ inv_cnt, int T, int d, long long pad_rid, long long pad_eid, int n_rel,
     float* __restrict__ dE, float* __restrict__ dR) {
   const int b = blockIdx.x, slot = blockIdx.y;
   const int src = perm ? perm[b] : b;
@@ -102,6 +103,28 @@ __global__ void __launch_bounds__(256) gather_pool_bwd_kernel(
   float* table = (slot == 1) ? dR : dE;
   const int d4 = d >> 2;
   const float inv = inv_cnt[b];
+  if (slot == 1 && n_rel > 0 && n_rel <= kRelHist) {
+    // the relation table has a handful of rows (3..7 in the IntelliGraphs sets) and every triple of the graph adds the
+    // SAME vector: count the graph's triples per relation in shared memory and push count * vector ONCE per relation
+    // present — n_rel reductions per (graph, column chunk) instead of one per triple, all of them onto the same few L2 lines
+    __shared__ int cnt[kRelHist];
+    for (int r = threadIdx.x; r < n_rel; r += blockDim.x) cnt[r] = 0;
+    __syncthreads();
+    for (int t = blockIdx.z * blockDim.x + threadIdx.x; t < T; t += gridDim.z * blockDim.x) {
+      const int64_t rel = tri[t * 3 + 1];
+      if (rel >= 0 && rel < n_rel && !(pad_rid >= 0 && rel == pad_rid)) atomicAdd(&cnt[(int)rel], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d4; c += blockDim.x) {
+      float4 v = *reinterpret_cast<const float4*>(dg + (int64_t)b * 3 * d + (int64_t)d + c * 4);
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      for (int r = 0; r < n_rel; ++r) {
+        const float k = (float)cnt[r];
+        if (k != 0.f) red_add_v4(dR + (int64_t)r * d + c * 4, make_float4(v.x * k, v.y * k, v.z * k, v.w * k));
+      }
+    }
+    return;
+  }
   for (int c = threadIdx.x; c < d4; c += blockDim.x) {
     float4 v = *reinterpret_cast<const float4*>(dg + (int64_t)b * 3 * d + (int64_t)slot * d + c * 4);
     v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
@@ -163,39 +186,61 @@ __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(
   if (threadIdx.x == 0 && kl_acc) atomicAdd(kl_acc, s * kl_scale);
 }
 
+// W = 4: four consecutive latent units per thread with 128-bit accesses (dz, strides % 4 == 0); W = 1: any shape
+template <int W>
 __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(
     const float* __restrict__ heads, int ld_heads, const float* __restrict__ eps, const int32_t* __restrict__ perm,
     const float* __restrict__ dz_in, int B, int dz, int clamp_logv, float bk, const float* __restrict__ beta_dev,
     const float* __restrict__ dmu_ext, const float* __restrict__ dlogv_ext, float* __restrict__ dheads,
     uint16_t* __restrict__ dheads_bf16, int ld_dh) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * dz) return;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * W;
+  if (i >= (int64_t)B * dz) return;
   if (beta_dev) bk *= *beta_dev;      // replayed CUDA graphs: beta lives in device memory (changes every epoch)
-  const int b = i / dz, j = i - b * dz;
-  const float mu = heads[(int64_t)b * ld_heads + j];
-  const float raw = heads[(int64_t)b * ld_heads + dz + j];
-  float lv = raw;
-  bool pass = true;
-  if (clamp_logv) {
-    lv = fminf(fmaxf(raw, -10.f), 10.f);
-    pass = (raw >= -10.f) && (raw <= 10.f);  // torch.clamp passes the gradient on the closed interval
-  }
+  const int b = (int)(i / dz), j = (int)(i - (int64_t)b * dz);
   const int64_t src = (int64_t)(perm ? perm[b] : b) * dz + j;
-  const float e = eps[src];
-  const float dzv = dz_in[i];
-  float dmu = fmaf(bk, mu, dzv);
-  float dlv = 0.5f * dzv * e * expf(0.5f * lv) + 0.5f * bk * (expf(lv) - 1.f);
-  if (dmu_ext) dmu += dmu_ext[src];          // upstream gradients of the returned (mu, logv) (autograd forward())
-  if (dlogv_ext) dlv += dlogv_ext[src];
-  if (!pass) dlv = 0.f;
-  const int64_t o = (int64_t)b * ld_dh;
-  if (dheads) {
-    dheads[o + j] = dmu;
-    dheads[o + dz + j] = dlv;
+  float mu[W], raw[W], e[W], dzv[W], xm[W], xl[W];
+  const float* hp = heads + (int64_t)b * ld_heads + j;
+  if constexpr (W == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(hp), c = *reinterpret_cast<const float4*>(hp + dz);
+    const float4 r = *reinterpret_cast<const float4*>(eps + src), g = *reinterpret_cast<const float4*>(dz_in + i);
+    mu[0] = a.x; mu[W - 3] = a.y; mu[W - 2] = a.z; mu[W - 1] = a.w;
+    raw[0] = c.x; raw[W - 3] = c.y; raw[W - 2] = c.z; raw[W - 1] = c.w;
+    e[0] = r.x; e[W - 3] = r.y; e[W - 2] = r.z; e[W - 1] = r.w;
+    dzv[0] = g.x; dzv[W - 3] = g.y; dzv[W - 2] = g.z; dzv[W - 1] = g.w;
+  } else {
+    mu[0] = hp[0]; raw[0] = hp[dz]; e[0] = eps[src]; dzv[0] = dz_in[i];
   }
-  if (dheads_bf16) {
-    dheads_bf16[o + j] = f32_to_bf16_bits(dmu);
-    dheads_bf16[o + dz + j] = f32_to_bf16_bits(dlv);
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    xm[k] = dmu_ext ? dmu_ext[src + k] : 0.f;      // upstream gradients of the returned (mu, logv) (autograd forward())
+    xl[k] = dlogv_ext ? dlogv_ext[src + k] : 0.f;
+  }
+  float dmu[W], dlv[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    float lv = raw[k];
+    bool pass = true;
+    if (clamp_logv) {
+      lv = fminf(fmaxf(raw[k], -10.f), 10.f);
+      pass = (raw[k] >= -10.f) && (raw[k] <= 10.f);  // torch.clamp passes the gradient on the closed interval
+    }
+    dmu[k] = fmaf(bk, mu[k], dzv[k]) + xm[k];
+    dlv[k] = 0.5f * dzv[k] * e[k] * expf(0.5f * lv) + 0.5f * bk * (expf(lv) - 1.f) + xl[k];
+    if (!pass) dlv[k] = 0.f;
+  }
+  const int64_t o = (int64_t)b * ld_dh + j;
+  if constexpr (W == 4) {
+    if (dheads) {
+      *reinterpret_cast<float4*>(dheads + o) = make_float4(dmu[0], dmu[W - 3], dmu[W - 2], dmu[W - 1]);
+      *reinterpret_cast<float4*>(dheads + o + dz) = make_float4(dlv[0], dlv[W - 3], dlv[W - 2], dlv[W - 1]);
+    }
+    if (dheads_bf16) {
+      *reinterpret_cast<uint2*>(dheads_bf16 + o) = make_uint2(pack_bf16x2(dmu[0], dmu[W - 3]), pack_bf16x2(dmu[W - 2], dmu[W - 1]));
+      *reinterpret_cast<uint2*>(dheads_bf16 + o + dz) = make_uint2(pack_bf16x2(dlv[0], dlv[W - 3]), pack_bf16x2(dlv[W - 2], dlv[W - 1]));
+    }
+  } else {
+    if (dheads) { dheads[o] = dmu[0]; dheads[o + dz] = dlv[0]; }
+    if (dheads_bf16) { dheads_bf16[o] = f32_to_bf16_bits(dmu[0]); dheads_bf16[o + dz] = f32_to_bf16_bits(dlv[0]); }
   }
 }
 
@@ -225,7 +270,7 @@ extern "C" int ark_gather_pool_fwd(const int64_t* triples, const int32_t* perm, 
 
 extern "C" int ark_gather_pool_bwd(const float* dg, const int64_t* triples, const int32_t* perm,
                                    const float* inv_cnt, int64_t B, int64_t T, int64_t d, int64_t pad_rid,
-                                   int64_t pad_eid, float* dE, float* dR, void* stream) {
+                                   int64_t pad_eid, int64_t n_rel, float* dE, float* dR, void* stream) {
   ARK_REQUIRE(dg && triples && inv_cnt && dE && dR, ARK_E_BADARG, "gather_pool_bwd: null pointer");
   ARK_REQUIRE(B > 0 && T > 0 && d > 0, ARK_E_BADARG, "gather_pool_bwd: B,T,d must be positive");
   ARK_REQUIRE(d % 4 == 0, ARK_E_SHAPE, "gather_pool_bwd: d must be a multiple of 4");
@@ -238,7 +283,8 @@ extern "C" int ark_gather_pool_bwd(const float* dg, const int64_t* triples, cons
   if (z < 1) z = 1;
   dim3 grid((unsigned)B, 3, (unsigned)z);
   gather_pool_bwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(dg, triples, perm, inv_cnt, (int)T, (int)d,
-                                                                    (long long)pad_rid, (long long)pad_eid, dE, dR);
+                                                                     (long long)pad_rid, (long long)pad_eid, (int)n_rel,
+                                                                     dE, dR);
   return launched("gather_pool_bwd");
 }
 
@@ -268,9 +314,17 @@ extern "C" int ark_reparam_kl_bwd(const float* heads, int64_t ld_heads, const fl
                                   float* dheads, uint16_t* dheads_bf16, int64_t ld_dh, void* stream) {
   ARK_REQUIRE(heads && eps && dz_in && (dheads || dheads_bf16), ARK_E_BADARG, "reparam_kl_bwd: null pointer");
   ARK_REQUIRE(B > 0 && dz > 0 && ld_heads >= 2 * dz && ld_dh >= 2 * dz, ARK_E_BADARG, "reparam_kl_bwd: bad sizes");
-  const int n = (int)(B * dz);
-  reparam_kl_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      heads, (int)ld_heads, eps, perm, dz_in, (int)B, (int)dz, clamp_logv, beta_kl_scale, beta_dev, dmu_ext, dlogv_ext,
-      dheads, dheads_bf16, (int)ld_dh);
+  const int64_t n = B * dz;
+  const bool vec = dz % 4 == 0 && ld_heads % 4 == 0 && ld_dh % 4 == 0 && aligned16(heads) && aligned16(eps) && aligned16(dz_in) &&
+                   (!dheads || aligned16(dheads)) && (!dheads_bf16 || (reinterpret_cast<uintptr_t>(dheads_bf16) & 7) == 0) &&
+                   (!dmu_ext || aligned16(dmu_ext)) && (!dlogv_ext || aligned16(dlogv_ext));
+  if (vec)
+    reparam_kl_bwd_kernel<4><<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        heads, (int)ld_heads, eps, perm, dz_in, (int)B, (int)dz, clamp_logv, beta_kl_scale, beta_dev, dmu_ext, dlogv_ext,
+        dheads, dheads_bf16, (int)ld_dh);
+  else
+    reparam_kl_bwd_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        heads, (int)ld_heads, eps, perm, dz_in, (int)B, (int)dz, clamp_logv, beta_kl_scale, beta_dev, dmu_ext, dlogv_ext,
+        dheads, dheads_bf16, (int)ld_dh);
   return launched("reparam_kl_bwd");
 }

@@ -8,10 +8,11 @@
 // 128 registers/thread — removes the L2 re-read but also the overlap between a row's load and its neighbour's
 // compute/store: 3.65-3.84 TB/s stand-alone against 4.26-4.53 TB/s for this two-pass kernel at V = 60943.)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ark {
 
-constexpr int kCeThreads = 512;
+constexpr int kCeThreadsDefault = 512;
 
 constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ float ex2(float x) {   // 2^x on the MUFU pipe; ex2(-inf) = 0
@@ -73,8 +74,8 @@ __device__ __forceinline__ void st1(float* p, float x) { *p = x; }
 // one CTA per row (grid-stride over rows).  Requires ldv % 8 == 0 and a 16B-aligned base so that every
 // row starts on a 16-byte boundary: all accesses inside [0, V8) are 128-bit.
 // U = independent 16-byte loads per thread in flight (4 for long rows, 2 for short ones)
-template <typename T, int U>
-__global__ void __launch_bounds__(kCeThreads, U == 4 ? 2 : 4) softmax_ce_kernel(
+template <typename T, int U, int kCeThreads = kCeThreadsDefault, int kMinCtas = (U == 4 ? 2 : 4)>
+__global__ void __launch_bounds__(kCeThreads, kMinCtas) softmax_ce_kernel(
     T* __restrict__ logits, int64_t N, int V, int64_t ldv, const int32_t* __restrict__ tgt, float grad_scale,
     int write_grad, float* __restrict__ loss_acc, float* __restrict__ lse_out) {
   __shared__ float red[33];
@@ -172,10 +173,44 @@ extern "C" int ark_softmax_ce(void* logits, int dtype, int64_t N, int64_t V, int
   if (N == 0) return 0;
   // 2 CTAs of 512 threads per SM keep one row loading while another computes/stores
   const bool deep = V >= 40000;   // long rows: 4 loads in flight per thread, 2 CTAs/SM; short rows: 2 loads, 4 CTAs/SM
+  cudaStream_t s = (cudaStream_t)stream;
+  // tuning knob (tools/bench_ce.py): ARK_CE_VARIANT = threads*100 + U*10 + CTAs/SM, e.g. 25643 = 256 threads, U 4, 3/SM
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("ARK_CE_VARIANT"); variant = e ? atoi(e) : 0; }
+#define ARK_CE_V(TT, UU, TH, PS)                                                                                        \
+  {                                                                                                                     \
+    const unsigned g_ = (unsigned)(N < (int64_t)(PS) * kNumSMs ? N : (int64_t)(PS) * kNumSMs);                          \
+    softmax_ce_kernel<TT, UU, TH, PS><<<g_, TH, 0, s>>>((TT*)logits, N, (int)V, ldv, tgt, grad_scale, write_grad, loss_acc, lse); \
+    return launched("softmax_ce");                                                                                      \
+  }
+  if (variant && dtype == ARK_BF16) {
+    switch (variant) {
+      case 51242: ARK_CE_V(uint16_t, 4, 512, 2)
+      case 51243: ARK_CE_V(uint16_t, 4, 512, 3)
+      case 51224: ARK_CE_V(uint16_t, 2, 512, 4)
+      case 25644: ARK_CE_V(uint16_t, 4, 256, 4)
+      case 25646: ARK_CE_V(uint16_t, 4, 256, 6)
+      case 25628: ARK_CE_V(uint16_t, 2, 256, 8)
+      case 25626: ARK_CE_V(uint16_t, 2, 256, 6)
+      case 102441: ARK_CE_V(uint16_t, 4, 1024, 1)
+      case 102422: ARK_CE_V(uint16_t, 2, 1024, 2)
+      default: break;
+    }
+  }
+  // measured stand-alone on B200 (tools/bench_ce.py, bf16, GB/s of algorithmic bytes; 70 % of the 6552 GB/s copy peak = 4586):
+  //   V 60943, N 4966 : 512 thr U4 2/SM 4435 | 512 thr U2 4/SM 4767 | 1024 thr U2 2/SM 4636
+  //   V 60943, N 20000: 512 thr U4 2/SM 4583 | 512 thr U2 4/SM 4808 | 1024 thr U2 2/SM 5050
+  //   V 24101, N 10333: 512 thr U2 4/SM 4928 | 256 thr U2 8/SM 5042
+  // -> more resident rows per SM beat more loads in flight per thread: a row's block reductions and pass switch are
+  //    covered by its neighbours
+  if (dtype == ARK_BF16 && !variant) {
+    if (!deep) ARK_CE_V(uint16_t, 2, 256, 8)
+    if (N >= 16384) ARK_CE_V(uint16_t, 2, 1024, 2)
+    ARK_CE_V(uint16_t, 2, 512, 4)
+  }
   const int per_sm = deep ? 2 : 4;
   const unsigned grid = (unsigned)(N < per_sm * kNumSMs ? N : per_sm * kNumSMs);
-  cudaStream_t s = (cudaStream_t)stream;
-#define ARK_CE_GO(TT, UU) softmax_ce_kernel<TT, UU><<<grid, kCeThreads, 0, s>>>((TT*)logits, N, (int)V, ldv, tgt, grad_scale, write_grad, loss_acc, lse)
+#define ARK_CE_GO(TT, UU) softmax_ce_kernel<TT, UU><<<grid, kCeThreadsDefault, 0, s>>>((TT*)logits, N, (int)V, ldv, tgt, grad_scale, write_grad, loss_acc, lse)
   if (dtype == ARK_BF16) {
     if (deep) ARK_CE_GO(uint16_t, 4); else ARK_CE_GO(uint16_t, 2);
   } else if (dtype == ARK_F32) {
@@ -184,5 +219,6 @@ extern "C" int ark_softmax_ce(void* logits, int dtype, int64_t N, int64_t V, int
     return fail(ARK_E_BADARG, "softmax_ce: unknown dtype %d", dtype);
   }
 #undef ARK_CE_GO
+#undef ARK_CE_V
   return launched("softmax_ce");
 }

@@ -59,7 +59,8 @@ def gather_pool_bwd(dg, triples, perm, inv_cnt, pad_rid, pad_eid, dE, dR):
     _contig(dg, triples, perm, inv_cnt, dE, dR)
     _C.lib().call("ark_gather_pool_bwd", _ptr(dg, torch.float32), _ptr(triples, torch.int64), _ptr(perm, torch.int32),
                   _ptr(inv_cnt, torch.float32), B, T, d, -1 if pad_rid is None else int(pad_rid),
-                  -1 if pad_eid is None else int(pad_eid), _ptr(dE, torch.float32), _ptr(dR, torch.float32), _stream())
+                  -1 if pad_eid is None else int(pad_eid), dR.shape[0], _ptr(dE, torch.float32), _ptr(dR, torch.float32),
+                  _stream())
 
 
 def pack_tokens(seq, perm, bt, off, L, tok_in, tgt, row_t=None):

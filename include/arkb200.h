@@ -61,9 +61,11 @@ int ark_gather_pool_fwd(const int64_t* triples, const int32_t* perm, const float
                         int64_t B, int64_t T, int64_t d, int64_t pad_rid,
                         float* g, uint16_t* g_bf16, float* inv_cnt, void* stream);
 /* dE[nE,d] / dR[nR,d] += dg[b, slot*d:(slot+1)*d] * inv_cnt[b] for every valid triple; caller zeroes
- * dE/dR first.  Rows pad_eid / pad_rid are never touched (nn.Embedding padding_idx semantics). */
+ * dE/dR first.  Rows pad_eid / pad_rid are never touched (nn.Embedding padding_idx semantics).  n_rel = rows of dR
+ * (<= 64: the relation slot is accumulated through a per-CTA histogram, one reduction per relation present; 0 = one
+ * reduction per triple as for the entity slots). */
 int ark_gather_pool_bwd(const float* dg, const int64_t* triples, const int32_t* perm, const float* inv_cnt,
-                        int64_t B, int64_t T, int64_t d, int64_t pad_rid, int64_t pad_eid,
+                        int64_t B, int64_t T, int64_t d, int64_t pad_rid, int64_t pad_eid, int64_t n_rel,
                         float* dE, float* dR, void* stream);
 
 /* ---- a1: packed token ids (utils.py:102-108 layout; PAD-skip) ----
