@@ -410,6 +410,19 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiPa
     splits = (int)((tiles * 2 <= kNumSMs ? kNumSMs : 2 * kNumSMs) / tiles);
     if (splits > num_kb / 4) splits = num_kb / 4;
     if (splits < 1) splits = 1;
+  } else if (!PERSIST && !ep.c_bf16 && ep.epilogue == ARK_EPI_NONE && !ep.aux && num_kb >= 128 && L::TOTAL * 2 <= 227 * 1024) {
+    // WAVE QUANTISATION: a grid a little larger than the GPU (vocabulary dY on wd-articles: 156 tiles, K = 60 943) runs a
+    // nearly empty second round — 53 % of the SMs' time.  Split K so that the work units fill whole rounds of the 2 x 148
+    // co-resident CTA slots: pick the split count with the best units / (rounds x slots), at least 8 k-blocks per unit
+    // (measured 417 -> 315 us, 743 -> 983 TFLOP/s).  Only for a long K (>= 8192): on the 25 us GRU dX / dW GEMMs of
+    // syn-types (K = 2560..3072) the zero-fill + red.add epilogue cost more than the idle half round (24 -> 31 us).
+    const int64_t slots = 2 * kNumSMs;
+    double best = (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
+    for (int sp = 2; sp <= 16 && num_kb / sp >= 8; ++sp) {
+      const int64_t units = tiles * sp;
+      const double eff = (double)units / (double)(((units + slots - 1) / slots) * slots);
+      if (eff > best + 0.04) { best = eff; splits = sp; }
+    }
   }
   ep2.kb_per_split = (num_kb + splits - 1) / splits;
   splits = (num_kb + ep2.kb_per_split - 1) / ep2.kb_per_split;

@@ -250,8 +250,9 @@ class SailEngine:
         wave_ok = use_tc and not self.force_unfused_gru and ops.gru_wave_supported(d, b0, nl) > 0
         # A wavefront grid larger than the GPU (d = 512 with two batch tiles: 32 x 2 x 3 = 192 CTAs) runs its tile groups
         # back to back; there the per-layer kernels (half-tile forward, K-split backward) are faster although they take
-        # nl * L dependent steps (measured on syn-paths: 0.82 vs 0.89 ms per training step)
-        if (wave_ok and self.gru_mode == "auto" and (d // 16) * ((b0 + 127) // 128) * nl > 148
+        # nl * L dependent steps (measured on syn-paths, L = 10: 0.82 vs 0.89 ms per training step; NOT for long chains:
+        # wd-articles at 256 graphs per GPU, L = 637: 47.9 vs 42.2 ms)
+        if (wave_ok and self.gru_mode == "auto" and (d // 16) * ((b0 + 127) // 128) * nl > 148 and L <= 32
                 and ops.gru_persist_bwd_ksplit(d, b0) and b0 > 64):
             wave_ok = False
         cluster = cl_nb > 0
