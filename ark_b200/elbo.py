@@ -305,13 +305,15 @@ class SailEngine:
                       and self.world * B * triples.shape[1] <= nE_rows)
             if fg:
                 x_all = [new(self.world * B, d3, dtype=bf) for _ in range(self.n_mlp)]
-                gathers = [(x_all[k], acts[k]) for k in range(self.n_mlp)]
+                gathers = []          # (the X factors travel with the dY factors, layer by layer, in the backward pass:
+                                      #  gathered here they competed for SMs with the cooperative GRU forward kernels)
                 if fg_emb:
                     tri_p = triples.index_select(0, lay.perm_dev.long()).contiguous()      # rows in packed order
                     tri_all = torch.empty((self.world * B,) + tuple(triples.shape[1:]), device=dev, dtype=triples.dtype)
                     inv_all = new(self.world * B)
                     gathers += [(tri_all, tri_p), (inv_all, inv_cnt)]
-                self._comm_action(("gathers", gathers))
+                if gathers:
+                    self._comm_action(("gathers", gathers))
             w_heads = f.fused(f.shadow, "enc.mu.weight", "enc.logv.weight", (2 * dz, d3))
             b_heads = f.fused(f.param, "enc.mu.bias", "enc.logv.bias", (2 * dz,))
             heads = new(B, 2 * dz)
@@ -620,19 +622,20 @@ class SailEngine:
 
         # ---------------- encoder MLP + pooled gather backward
         wb = self.world * B
+        mlp_items = []
         for k in range(self.n_mlp - 1, -1, -1):
             dp_b = new(B, d3, dtype=bf)
             ops.gelu_bwd(da, pres[k], None, dp_b)
             if fg:
-                # data parallel: this layer's dY factor is gathered, the GLOBAL dW_k = dY_all^T X_all formed and Adam
-                # applied, all on the side stream (in order behind the X-factor gather issued after the encoder
-                # forward) while the chain below continues: nothing on this stream waits for it before the step ends
+                # data parallel: the layers' dY / X factors are gathered (one grouped call after the chain below), the
+                # GLOBAL dW_k = dY_all^T X_all formed and Adam applied, all on the side streams: nothing on this stream
+                # waits for it before the step ends
                 dp_all_k = new(wb, d3, dtype=bf)
                 keep_alive.append((dp_b, dp_all_k))
             da = new(B, d3)
             self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3, tag="enc_mlp_dX")
-            if fg:      # AFTER the dX GEMM is queued: the side stream's Adam rewrites W_k, which that GEMM still reads
-                self._comm_action(("mlp_dw", k, dp_all_k, dp_b, x_all[k]))
+            if fg:
+                mlp_items.append((k, dp_all_k, dp_b, x_all[k], acts[k]))
             if not fg:
                 def mlp_weight_grads(k=k, dp_b=dp_b):
                     self._gemm(dp_b, MN, acts[k], MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, B, tag="enc_mlp_dW")
@@ -640,6 +643,9 @@ class SailEngine:
                     self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
                 keep_alive.append(dp_b)
                 self._leaf(mlp_weight_grads)
+        if fg:      # AFTER the last dX GEMM is queued (the side streams' Adam rewrites W_k, which those GEMMs read): ONE
+            self._comm_action(("mlp_dw", mlp_items))      # grouped all-gather of every layer's two factors (2 nl small
+                                                          # messages are launch-latency bound: ~0.1 ms per NCCL call)
         gE, gR = f.g("enc.e_emb.weight"), f.g("enc.r_emb.weight")
         if fg and fg_emb:       # (opt-in) the embedding scatter over the GLOBAL batch from gathered factors
             da_all = new(wb, d3)
@@ -785,23 +791,27 @@ class SailEngine:
                         with torch.distributed._coalescing_manager(group=self.group, device=self.device, async_ops=False):
                             for o, i in pairs:
                                 torch.distributed.all_gather_into_tensor(o, i, group=self.group)
-        elif kind == "mlp_dw":      # (k, dY_all, dY_local, X_all): gather -> global dW_k GEMM -> bias -> Adam, side stream
-            _, k, dp_all_k, dp_b, x_all_k = action
+        elif kind == "mlp_dw":      # [(k, dY_all, dY_local, X_all, X_local)]: gathers -> global dW_k GEMMs -> bias -> Adam
+            items = action[1]
             ev = torch.cuda.Event()
             ev.record()
             self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
-                with self._timed("nccl_all_gather", nbytes=float(dp_all_k.numel() * 2)):
-                    torch.distributed.all_gather_into_tensor(dp_all_k, dp_b, group=self.group)
-            d3 = dp_all_k.shape[1]
+                with self._timed("nccl_all_gather", nbytes=float(sum(it[1].numel() * 4 for it in items))):
+                    with torch.distributed._coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                        for _, dp_all_k, dp_b, x_all_k, x_k in items:
+                            torch.distributed.all_gather_into_tensor(dp_all_k, dp_b, group=self.group)     # dY factor
+                            torch.distributed.all_gather_into_tensor(x_all_k, x_k, group=self.group)       # X factor
             f = self.flat
             with self._post():
-                self._gemm(dp_all_k, MN, x_all_k, MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, dp_all_k.shape[0],
-                           tag="enc_mlp_dW_global")
-                ops.colsum(dp_all_k, dp_all_k.shape[0], d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks agree bitwise
-                if upd is not None:
-                    s_, e_ = f.span(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
-                    self._adam_slice(s_, e_, upd)
+                for k, dp_all_k, _, x_all_k, _ in items:
+                    d3 = dp_all_k.shape[1]
+                    self._gemm(dp_all_k, MN, x_all_k, MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, dp_all_k.shape[0],
+                               tag="enc_mlp_dW_global")
+                    ops.colsum(dp_all_k, dp_all_k.shape[0], d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks agree bitwise
+                    if upd is not None:
+                        s_, e_ = f.span(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
+                        self._adam_slice(s_, e_, upd)
         elif kind == "join":        # the main stream needs what the side stream produced
             self._join_side()
         else:
@@ -818,9 +828,13 @@ class SailEngine:
         f = self.flat
         if self.world > 1 and allreduce:
             with torch.cuda.stream(self.comm_stream):
-                for (s, e) in spans:
-                    with self._timed("nccl_all_reduce", nbytes=4.0 * (e - s)):
-                        torch.distributed.all_reduce(f.grad[s:e], group=self.group)
+                with self._timed("nccl_all_reduce", nbytes=4.0 * sum(e - s for s, e in spans)):
+                    if len(spans) == 1:
+                        torch.distributed.all_reduce(f.grad[spans[0][0]:spans[0][1]], group=self.group)
+                    else:   # the slices of one bucket leave in ONE grouped NCCL launch (they are launch-latency bound)
+                        with torch.distributed._coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                            for (s, e) in spans:
+                                torch.distributed.all_reduce(f.grad[s:e], group=self.group)
         if upd is not None:
             with self._post():
                 for (s, e) in spans:
