@@ -56,6 +56,9 @@ class SailEngine:
         if cfg["model_type"] not in ("SAIL", "ARK"):
             raise NotImplementedError("SailEngine accelerates model_type 'SAIL' (MLP encoder + GRU decoder) and its "
                                       "decoder-only sibling 'ARK'")
+        if str(cfg.get("precision", "bf16")).lower() != "bf16":
+            raise NotImplementedError(f"precision {cfg.get('precision')!r}: the fused step is built for bf16 GEMM operands with "
+                                      "fp32 accumulation / masters / state only (a tcgen05 kind::tf32 path does not exist)")
         self.has_enc = cfg["model_type"] == "SAIL"
         dev = next(model.parameters()).device
         if dev.type != "cuda":

@@ -156,8 +156,15 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": 1 + W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        # (same keys as the CUDA arm's `config`, so that the two lines can be compared field by field)
         "config": {"workload": f"autoreg_{args.workload} SAIL", "graphs_per_gpu": batch, "global_batch": batch,
-                   "dense": bool(args.dense),
+                   "d_model": cfg["d_model"], "d_latent": cfg["d_latent"], "n_layers": cfg["n_layers"],
+                   "vocab_size": cfg["vocab_size"], "seq_len": cfg["seq_len"],
+                   "params": sum(p.numel() for p in model.parameters()),
+                   "triples_per_step": tri / K, "tokens_per_step_rank0": int((hb[0][1][:, 1:] != 0).sum()),
+                   "dense": bool(args.dense), "parallelism": "cpu", "l2": "n/a (host)", "gemm_backend": "MKL/oneDNN (torch CPU)",
+                   "cuda_graph": False, "precision": "fp32",
+                   "timing": f"wall clock over {K} full train steps",
                    "note": "reference CPU path = torch-CPU port of the reference step (same ATen/MKL calls), all host "
                            "threads; steps/warm-up capped so the run ends within minutes"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
