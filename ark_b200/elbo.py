@@ -45,6 +45,7 @@ class SailEngine:
     dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
     _gru_cluster_ws = None
     _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding, capture_nccl, post_stream = False, False, None, False, False, None     # (the Transformer engines do not fork leaf work)
+    prof_stream = {}                 # tag -> "main" | "leaf" | "side": the stream a timed op was launched on (bench.py)
     nvtx = os.environ.get("ARK_NVTX", "0") != "0"   # NVTX range per kernel family (same tags as bench.py's `kernels` list)
     logits_chunk_rows = 16384        # packed rows per logits workspace chunk (see forward_backward)
     max_graphs = 8                   # captured step graphs kept per engine (oldest evicted first)
@@ -180,7 +181,10 @@ class SailEngine:
         def __exit__(self, *exc):
             if self.eng.prof is not None:
                 self.e1.record()
-                self.eng.prof.append((self.tag, self.e0, self.e1, self.flops, self.nbytes))
+                eng, cur = self.eng, torch.cuda.current_stream()
+                where = ("side" if cur in (eng.comm_stream, eng.post_stream) else "leaf" if cur == eng.leaf_stream else "main")
+                eng.prof_stream[self.tag] = where
+                eng.prof.append((self.tag, self.e0, self.e1, self.flops, self.nbytes))
             if SailEngine.nvtx:
                 torch.cuda.nvtx.range_pop()
 

@@ -271,10 +271,11 @@ def test_bench_kernel_table_and_roofline_selection():
            "gemm_tc:gru_gi": {"ms": 0.27, "calls": 9, "flops": 9 * 16.1e9, "bytes": 0.0},
            "softmax_ce": {"ms": 0.05, "calls": 3, "flops": 0.0, "bytes": 3 * 1.2e6},
            "nccl_all_reduce": {"ms": 1.2, "calls": 15, "flops": 0.0, "bytes": 15 * 4e7}}
-    rows = bench.kernel_table(agg, 3, 1.25, pk, "syn-types")
-    assert [r["name"] for r in rows] == ["nccl_all_reduce", "gru_persist_bwd", "gemm_tc:gru_gi", "softmax_ce"]
+    agg["adam_flat"] = {"ms": 1.0, "calls": 24, "flops": 0.0, "bytes": 24 * 1.8e8}
+    rows = bench.kernel_table(agg, 3, 1.25, pk, "syn-types", {"adam_flat": "side", "nccl_all_reduce": "side"})
+    assert [r["name"] for r in rows] == ["nccl_all_reduce", "adam_flat", "gru_persist_bwd", "gemm_tc:gru_gi", "softmax_ce"]
     roof = bench.roofline_from(rows, pk, "graph-replay event nodes")
-    assert roof["kernel"] == "gru_persist_bwd" and roof["bound"] == "tensor"          # NCCL is never "our top kernel"
+    assert roof["kernel"] == "gru_persist_bwd" and roof["bound"] == "tensor"   # side-stream Adam / NCCL overlap the chain
     assert abs(roof["achieved"] - 16.1e9 / (0.1e-3) / 1e12) < 1e-6 and abs(roof["frac"] - roof["achieved"] / 1386.4) < 1e-9
     assert roof["launches_per_step"] == 3.0 and abs(roof["share_of_step"] - 0.3 / 1.25) < 1e-9
     ce = [r for r in rows if r["name"] == "softmax_ce"][0]
