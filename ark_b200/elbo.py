@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import math
 import os
+import sys
 
 import numpy as np
 import torch
@@ -42,7 +43,8 @@ class SailEngine:
     # defaults of the data-parallel / GRU-driver switches, also for subclasses with their own __init__
     # (ark_b200.tsail: the Transformer engines reuse the bucket machinery below)
     _hold_comm, _held = False, ()
-    dp_hold_comm, dp_factor_gather, dp_emb_min_bytes = False, True, None
+    mm, _mm_spans, dp_mm_ctas, _factor_wss = None, frozenset(), 32, {}     # multicast gradient exchange (csrc/dp_reduce.cu): SailEngine only
+    dp_hold_comm, dp_factor_gather, dp_emb_min_bytes, dp_mlp_pipe = False, True, None, True
     _gru_cluster_ws = None
     _leaf_used, use_leaf_stream, leaf_stream, leaf_embedding, capture_nccl, post_stream = False, False, None, False, False, None     # (the Transformer engines do not fork leaf work)
     prof_stream = {}                 # tag -> "main" | "leaf" | "side": the stream a timed op was launched on (bench.py)
@@ -73,14 +75,38 @@ class SailEngine:
         self.p_drop = float(cfg.get("dec_dropout", 0.1)) if self.nl > 1 else 0.0
         if self.d % 8:
             raise ValueError("d_model must be a multiple of 8")
-        self.flat = FlatParams(sail_param_order(model) if self.has_enc else ark_param_order(model), dev)
+        self.group = dist_group
+        self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
+        # data parallel on an NVSwitch node: the flat buffers live in symmetric multicast memory and the gradient
+        # buckets are reduced IN THE SWITCH by a kernel that also applies Adam to the slice this rank owns and
+        # multicasts the new parameters (csrc/dp_reduce.cu).  ARK_DP_MULTIMEM=0: NCCL all-reduce + replicated Adam;
+        # =1: fail instead of falling back to NCCL when the allocation has no multicast mapping
+        self.mm, self._mm_spans, self._factor_wss = None, set(), {}
+        mm_mode = os.environ.get("ARK_DP_MULTIMEM", "auto")
+        if (self.world >= 4 and mm_mode != "0") or (self.world > 1 and mm_mode == "1"):
+            try:
+                from .symm import SymmFlat
+                self.mm = SymmFlat.__new__(SymmFlat)
+                def alloc(numel, mm=self.mm):
+                    mm.__init__(numel, dev, dist_group)
+                    return mm.buffers()
+                self.flat = FlatParams(sail_param_order(model) if self.has_enc else ark_param_order(model), dev, alloc)
+            except Exception as exc:      # no multicast (PCIe box, MIG, old driver): the NCCL path is the same math
+                if mm_mode == "1":
+                    raise
+                print(f"[ark_b200] multicast gradient exchange unavailable ({type(exc).__name__}: {exc}); using NCCL",
+                      file=sys.stderr, flush=True)
+                self.mm = None
+        if self.mm is None:
+            self.flat = FlatParams(sail_param_order(model) if self.has_enc else ark_param_order(model), dev)
+        # CTAs of the exchange kernels: at 8 ranks 16 already saturate the switch (profiles/r02_dp_multicast.md) and
+        # 128 + 16 <= 148 lets them run NEXT TO the one-CTA-per-SM GRU kernels
+        self.dp_mm_ctas = int(os.environ.get("ARK_DP_MM_CTAS", "16" if self.world >= 8 else "32"))
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.step_count = 0
         self.backend = gemm_backend
         self.seed, self.philox_offset = int(seed), 0
         self.ldv = _up8(self.V)
-        self.group = dist_group
-        self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
         if self.world > 1 and bucket_mb == 16.0:
             bucket_mb = 48.0        # with NVSwitch a few large all-reduces beat many launch-latency-bound small ones
         bucket_mb = float(os.environ.get("ARK_BUCKET_MB", bucket_mb))
@@ -121,9 +147,10 @@ class SailEngine:
                                          # wavefront stack kernel when it fits, else per-layer persistent;
                                          # "wave": never the cluster kernel; "layer": neither (tests / A-B timing)
         self._gru_cluster_ws = None      # scratch of the cluster GRU kernels (gi^T / dx^T slices), grown on demand
-        self.dp_factor_gather = True     # data parallel: all-gather the [B, 3d] FACTORS of the encoder-MLP weight
+        self.dp_factor_gather = os.environ.get("ARK_DP_FACTOR_GATHER", "1") != "0"   # data parallel: all-gather the [B, 3d] FACTORS of the encoder-MLP weight
                                          # gradients (dW = dY^T X, rank <= global batch) instead of all-reducing dW
         self.dp_hold_comm = os.environ.get("ARK_DP_HOLD_COMM", "0") != "0"   # opt-in: see _release_comm
+        self.dp_mlp_pipe = os.environ.get("ARK_DP_MLP_PIPE", "1") != "0"     # encoder-MLP factor exchange, layer by layer
         self.dp_emb_min_bytes = None     # ... and (opt-in: a byte threshold) of the entity-embedding gradient of a large
                                          # table.  Off by default: the scatter's atomics make the ranks' results differ
                                          # in the last bits, so replicas would drift apart without a periodic re-sync
@@ -311,9 +338,15 @@ class SailEngine:
             fg_emb = (fg and self.dp_emb_min_bytes is not None and nE_rows * d * 4 >= self.dp_emb_min_bytes
                       and self.world * B * triples.shape[1] <= nE_rows)
             if fg:
-                x_all = [new(self.world * B, d3, dtype=bf) for _ in range(self.n_mlp)]
-                gathers = []          # (the X factors travel with the dY factors, layer by layer, in the backward pass:
-                                      #  gathered here they competed for SMs with the cooperative GRU forward kernels)
+                if self.mm is not None:     # gathered by multicast stores into symmetric memory (csrc/dp_reduce.cu)
+                    x_all, dy_all = self._factor_views(self._factor_ws(self.world * B, d3), self.world * B, d3)
+                else:
+                    x_all, dy_all = [new(self.world * B, d3, dtype=bf) for _ in range(self.n_mlp)], None
+                # pipelined exchange (default): the X factors leave NOW (hidden behind the whole decoder), each dY_k as
+                # soon as the backward chain has produced it.  Legacy (ARK_DP_MLP_PIPE=0, or NCCL outside the graph):
+                # one grouped call for all 2 nl factors after the chain
+                pipe = self.dp_mlp_pipe and self.mm is None and not (self._capturing and not self.capture_nccl)
+                gathers = [(x_all[k], acts[k]) for k in range(self.n_mlp)] if pipe else []
                 if fg_emb:
                     tri_p = triples.index_select(0, lay.perm_dev.long()).contiguous()      # rows in packed order
                     tri_all = torch.empty((self.world * B,) + tuple(triples.shape[1:]), device=dev, dtype=triples.dtype)
@@ -623,6 +656,8 @@ class SailEngine:
             self._gemm(dheads_b[:, :2 * dz], MN, acts[-1], MN, g_wh, 2 * dz, d3, B, tag="enc_heads_bwd")
             ops.colsum(dheads, B, 2 * dz, g_bh)
             self._grad_ready("dec.z_proj.weight", "enc.logv.bias")
+            if self.mm is not None:      # every decoder gradient is final: exchange them NOW, behind the encoder-MLP chain,
+                self._flush_bucket()     # instead of at the end of the step together with the embedding rows
         da = new(B, d3)
         self._gemm(dheads_b[:, :2 * dz], K, w_heads, MN, da, B, d3, 2 * dz, tag="enc_heads_bwd")
         self._leaf(heads_weight_grads)
@@ -637,11 +672,15 @@ class SailEngine:
                 # data parallel: the layers' dY / X factors are gathered (one grouped call after the chain below), the
                 # GLOBAL dW_k = dY_all^T X_all formed and Adam applied, all on the side streams: nothing on this stream
                 # waits for it before the step ends
-                dp_all_k = new(wb, d3, dtype=bf)
+                dp_all_k = dy_all[k] if dy_all is not None else new(wb, d3, dtype=bf)
                 keep_alive.append((dp_b, dp_all_k))
+                if pipe:        # dY_k leaves now; the global dW_k GEMM follows it on the side streams
+                    self._comm_action(("mlp_dw_gather", k, dp_all_k, dp_b, x_all[k]))
             da = new(B, d3)
             self._gemm(dp_b, K, self._w(f"enc.mlp.{2 * k}.weight"), MN, da, B, d3, d3, tag="enc_mlp_dX")
-            if fg:
+            if fg and pipe:     # W_k has been read for the last time: Adam may rewrite it
+                self._comm_action(("mlp_dw_adam", k))
+            elif fg:
                 mlp_items.append((k, dp_all_k, dp_b, x_all[k], acts[k]))
             if not fg:
                 def mlp_weight_grads(k=k, dp_b=dp_b):
@@ -650,7 +689,7 @@ class SailEngine:
                     self._grad_ready(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
                 keep_alive.append(dp_b)
                 self._leaf(mlp_weight_grads)
-        if fg:      # AFTER the last dX GEMM is queued (the side streams' Adam rewrites W_k, which those GEMMs read): ONE
+        if fg and not pipe:      # AFTER the last dX GEMM is queued (the side streams' Adam rewrites W_k, which those GEMMs read): ONE
             self._comm_action(("mlp_dw", mlp_items))      # grouped all-gather of every layer's two factors (2 nl small
                                                           # messages are launch-latency bound: ~0.1 ms per NCCL call)
         gE, gR = f.g("enc.e_emb.weight"), f.g("enc.r_emb.weight")
@@ -703,6 +742,8 @@ class SailEngine:
         cur = torch.cuda.current_stream()
         cur.wait_stream(self.comm_stream)
         if self.post_stream is not None and self.post_stream is not self.comm_stream:
+            if self._capturing:      # a step that queued nothing on the post stream: bring it into the capture first
+                self.post_stream.wait_stream(self.comm_stream)
             cur.wait_stream(self.post_stream)
 
     def _post(self):
@@ -804,21 +845,69 @@ class SailEngine:
             ev.record()
             self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
-                with self._timed("nccl_all_gather", nbytes=float(sum(it[1].numel() * 4 for it in items))):
-                    with torch.distributed._coalescing_manager(group=self.group, device=self.device, async_ops=False):
-                        for _, dp_all_k, dp_b, x_all_k, x_k in items:
-                            torch.distributed.all_gather_into_tensor(dp_all_k, dp_b, group=self.group)     # dY factor
-                            torch.distributed.all_gather_into_tensor(x_all_k, x_k, group=self.group)       # X factor
+                if self.mm is not None:     # every rank multicasts its rows into its slot of all ranks' gathered matrices
+                    wb, d3 = items[0][1].shape
+                    ws, B_ = self._factor_ws(wb, d3), wb // self.world
+                    slot = lambda t: t.data_ptr() - ws.buf.data_ptr() + self.mm.rank * B_ * d3 * 2
+                    pairs = [p for _, dp_all_k, dp_b, x_all_k, x_k in items for p in ((dp_b, slot(dp_all_k)), (x_k, slot(x_all_k)))]
+                    for i in range(0, len(pairs), 8):
+                        with self._timed("dp_allgather_mc", nbytes=float(sum(t.numel() * 2 for t, _ in pairs[i:i + 8]) * self.world)):
+                            ops.dp_allgather_mc(self.mm, ws, pairs[i:i + 8], ctas=self.dp_mm_ctas)
+                else:
+                    with self._timed("nccl_all_gather", nbytes=float(sum(it[1].numel() * 4 for it in items))):
+                        with torch.distributed._coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                            for _, dp_all_k, dp_b, x_all_k, x_k in items:
+                                torch.distributed.all_gather_into_tensor(dp_all_k, dp_b, group=self.group)     # dY factor
+                                torch.distributed.all_gather_into_tensor(x_all_k, x_k, group=self.group)       # X factor
             f = self.flat
-            with self._post():
-                for k, dp_all_k, _, x_all_k, _ in items:
-                    d3 = dp_all_k.shape[1]
+            # the global dW_k GEMMs (tensor-bound) on the leaf stream, each layer's Adam (HBM-bound) on the post stream
+            # behind its GEMM: GEMM k+1 overlaps Adam k
+            split = self.use_leaf_stream and self.post_stream is not self.comm_stream and not (self.prof is not None and not self._capturing)
+            gstream = self.leaf_stream if split else (self.post_stream if self.post_stream is not None else self.comm_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+            gstream.wait_event(ev)
+            if split:
+                self.post_stream.wait_event(ev)
+                self._leaf_used = True
+            for k, dp_all_k, _, x_all_k, _ in items:
+                d3 = dp_all_k.shape[1]
+                with torch.cuda.stream(gstream):
                     self._gemm(dp_all_k, MN, x_all_k, MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, dp_all_k.shape[0],
                                tag="enc_mlp_dW_global")
                     ops.colsum(dp_all_k, dp_all_k.shape[0], d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks agree bitwise
-                    if upd is not None:
+                    if split:
+                        evk = torch.cuda.Event()
+                        evk.record(gstream)
+                if upd is not None:
+                    if split:
+                        self.post_stream.wait_event(evk)
+                    with torch.cuda.stream(self.post_stream if split else gstream):
                         s_, e_ = f.span(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
                         self._adam_slice(s_, e_, upd)
+        elif kind == "mlp_dw_gather":   # (k, dY_all, dY_local, X_all): dY_k -> all ranks; global dW_k + bias on the post stream
+            _, k, dp_all_k, dp_b, x_all_k = action
+            ev = torch.cuda.Event()
+            ev.record()
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                with self._timed("nccl_all_gather", nbytes=float(dp_all_k.numel() * 2)):
+                    torch.distributed.all_gather_into_tensor(dp_all_k, dp_b, group=self.group)
+            f, d3 = self.flat, dp_all_k.shape[1]
+            with self._post():
+                self._gemm(dp_all_k, MN, x_all_k, MN, f.g(f"enc.mlp.{2 * k}.weight"), d3, d3, dp_all_k.shape[0],
+                           tag="enc_mlp_dW_global")
+                ops.colsum(dp_all_k, dp_all_k.shape[0], d3, f.g(f"enc.mlp.{2 * k}.bias"), deterministic=True)   # ranks agree bitwise
+        elif kind == "mlp_dw_adam":     # (k,): everything queued on the current stream (the dX GEMM that reads W_k) first
+            if upd is not None:
+                k, f = action[1], self.flat
+                post = self.post_stream if self.post_stream is not None else self.comm_stream
+                ev = torch.cuda.Event()
+                ev.record()
+                post.wait_event(ev)
+                with torch.cuda.stream(post):
+                    s_, e_ = f.span(f"enc.mlp.{2 * k}.weight", f"enc.mlp.{2 * k}.bias")
+                    self._adam_slice(s_, e_, upd)
         elif kind == "join":        # the main stream needs what the side stream produced
             self._join_side()
         else:
@@ -833,6 +922,25 @@ class SailEngine:
         self.comm_stream.wait_event(ev)
         self._comm_waits_for_leaf()
         f = self.flat
+        if self.world > 1 and allreduce and self.mm is not None:
+            # switch-reduced gradients -> Adam on the owned slice -> multicast parameters, ONE kernel (K11); without an
+            # update in flight (gradients only) the same kernel multicasts the sum back into the gradient buffer
+            spans4 = [(s, min(f.numel, (e + 3) // 4 * 4)) for s, e in spans]
+            with torch.cuda.stream(self.comm_stream):
+                for i in range(0, len(spans4), 16):
+                    part = spans4[i:i + 16]
+                    with self._timed("dp_reduce_adam", nbytes=4.0 * sum(e - s for s, e in part)):
+                        if upd is None:
+                            ops.dp_reduce_adam(self.mm, part, f.exp_avg, f.exp_avg_sq, 0, ctas=self.dp_mm_ctas)
+                        elif upd[0] == "dyn":
+                            ops.dp_reduce_adam(self.mm, part, f.exp_avg, f.exp_avg_sq, 1, 0.0, self.betas[0], self.betas[1],
+                                               self.eps, hyper=self.dyn_f, ctas=self.dp_mm_ctas)
+                        else:
+                            ops.dp_reduce_adam(self.mm, part, f.exp_avg, f.exp_avg_sq, 1, upd[1], self.betas[0], self.betas[1],
+                                               self.eps, step=self.step_count, ctas=self.dp_mm_ctas)
+                    if upd is not None:
+                        self._mm_spans.update(part)
+            return
         if self.world > 1 and allreduce:
             with torch.cuda.stream(self.comm_stream):
                 with self._timed("nccl_all_reduce", nbytes=4.0 * sum(e - s for s, e in spans)):
@@ -857,6 +965,39 @@ class SailEngine:
                 ops.adam_flat(f.param[s:e], f.grad[s:e], f.exp_avg[s:e], f.exp_avg_sq[s:e], f.shadow[s:e],
                               upd[1], self.betas[0], self.betas[1], self.eps, self.step_count)
 
+    def _factor_ws(self, wb, d3):
+        """Symmetric multicast home of the gathered encoder-MLP factors: [2 n_mlp, world * B, 3d] bf16 (X_all_k, dY_all_k).
+        Creating it is a COLLECTIVE host-side rendezvous: before any capture, in the same order on every rank."""
+        ws = self._factor_wss.get((wb, d3))
+        if ws is None:
+            if self._capturing:
+                raise RuntimeError("the symmetric factor workspace must exist before the step is captured")
+            from .symm import SymmBuf
+            ws = self._factor_wss[(wb, d3)] = SymmBuf(2 * self.n_mlp * wb * d3 * 2, self.device, self.group)
+        return ws
+
+    def _factor_views(self, ws, wb, d3):
+        nb = wb * d3 * 2
+        mats = [ws.buf[i * nb:(i + 1) * nb].view(torch.bfloat16).view(wb, d3) for i in range(2 * self.n_mlp)]
+        return mats[0::2], mats[1::2]          # X_all_k, dY_all_k
+
+    def gather_adam_state(self):
+        """COLLECTIVE (every rank).  With the multicast exchange a rank maintains exp_avg / exp_avg_sq only for the
+        slices it owns; before the optimiser state is read as a whole (checkpoint on rank 0, a switch to another
+        exchange) every owner broadcasts its slices."""
+        if self.mm is None or not self._mm_spans:
+            return
+        self._sync_grads()
+        torch.cuda.synchronize(self.device)
+        f, dist = self.flat, torch.distributed
+        for s, e in sorted(self._mm_spans):
+            for r, (lo, hi) in enumerate(self.mm.owned(s, e)):
+                if hi > lo:
+                    src = dist.get_global_rank(self.group, r)
+                    dist.broadcast(f.exp_avg[lo:hi], src, group=self.group)
+                    dist.broadcast(f.exp_avg_sq[lo:hi], src, group=self.group)
+        torch.cuda.synchronize(self.device)
+
     def _sync_grads(self):
         self._leaf_join()
         self._flush_bucket()
@@ -867,6 +1008,9 @@ class SailEngine:
         """Dense Adam over the whole flat buffer (torch.optim.Adam defaults, ablation_study.py:571) — the separate
         optimizer.step() of the reference's loop.  train_step() instead updates bucket by bucket during backward."""
         self._sync_grads()
+        if self._mm_spans:       # earlier fused steps kept a sharded Adam state: make it whole before the dense update
+            self.gather_adam_state()
+            self._mm_spans.clear()
         self.step_count += 1
         f = self.flat
         with self._timed("adam_flat", nbytes=30.0 * f.numel):
@@ -936,6 +1080,9 @@ class SailEngine:
             if (self.backend == "tc" and self.gru_mode in ("auto", "cluster") and not self.force_unfused_gru
                     and self._use_gru_cluster(self.d, b0, self.nl, lay.L)):
                 self._cluster_ws(lay.L, b0, self.d, self.nl)      # scratch must exist before capture
+            if (self.mm is not None and self.has_enc and self.dp_factor_gather and triples is not None
+                    and (batch_global is None or batch_global == self.world * triples.shape[0])):
+                self._factor_ws(self.world * triples.shape[0], 3 * self.d)      # (a collective rendezvous)
             torch.cuda.synchronize()
             n0 = _C.lib().launch_count()
             cap = torch.cuda.Stream(device=dev)

@@ -75,7 +75,9 @@ def merge_span(pending, s, e, gap=64):
 
 
 class FlatParams:
-    def __init__(self, groups, device):
+    def __init__(self, groups, device, alloc=None):
+        """alloc(numel) -> (param f32, grad f32, shadow bf16) zero-filled flat buffers: data parallelism places them in
+        symmetric multicast memory (ark_b200.symm.SymmFlat)."""
         self.slots = {}  # name -> (offset, numel, shape)
         off = 0
         for g in groups:
@@ -85,11 +87,14 @@ class FlatParams:
                 off += p.numel()
         self.numel = (off + ALIGN - 1) // ALIGN * ALIGN
         self.device = device
-        self.param = torch.zeros(self.numel, device=device, dtype=torch.float32)
-        self.grad = torch.zeros(self.numel, device=device, dtype=torch.float32)
+        if alloc is not None:
+            self.param, self.grad, shadow = alloc(self.numel)
+        else:
+            self.param = torch.zeros(self.numel, device=device, dtype=torch.float32)
+            self.grad = torch.zeros(self.numel, device=device, dtype=torch.float32)
         self.exp_avg = torch.zeros(self.numel, device=device, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(self.numel, device=device, dtype=torch.float32)
-        self.shadow = torch.zeros(self.numel, device=device, dtype=torch.bfloat16)
+        self.shadow = shadow if alloc is not None else torch.zeros(self.numel, device=device, dtype=torch.bfloat16)
         self.order = [n for g in groups for n, _ in g]
         with torch.no_grad():
             for g in groups:

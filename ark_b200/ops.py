@@ -274,6 +274,35 @@ def adam_flat_dyn(p, g, m, v, shadow, hyper, beta1, beta2, eps, grad_scale=1.0):
                   float(beta1), float(beta2), float(eps), float(grad_scale), _stream())
 
 
+def dp_reduce_adam(sym, spans, m, v, mode, lr=0.0, beta1=0.9, beta2=0.999, eps=1e-8, step=1, hyper=None, ctas=0):
+    """K11 (csrc/dp_reduce.cu): switch-reduced gradients -> Adam on this rank's 1/world slice -> multicast parameters.
+    sym: ark_b200.symm.SymmFlat; spans: [(begin, end)] in elements (multiples of 4); mode 0 = gradient all-reduce only."""
+    import numpy as np
+    sb = np.ascontiguousarray([s_ for s_, _ in spans], dtype=np.int64)
+    se = np.ascontiguousarray([e_ for _, e_ in spans], dtype=np.int64)
+    flags = (ctypes.c_void_p * sym.world)(*sym.peer_flags)
+    _contig(m, v, hyper)
+    _C.lib().call("ark_dp_reduce_adam", ctypes.c_void_p(sym.mc_grad), ctypes.c_void_p(sym.mc_param),
+                  ctypes.c_void_p(sym.mc_shadow), _ptr(sym.param, torch.float32), _ptr(m, torch.float32),
+                  _ptr(v, torch.float32), flags, sym.rank, sym.world, sb.ctypes.data_as(ctypes.c_void_p),
+                  se.ctypes.data_as(ctypes.c_void_p), len(spans), int(mode), float(lr), float(beta1), float(beta2),
+                  float(eps), int(step), _ptr(hyper, torch.float32), int(ctas), _stream())
+
+
+def dp_allgather_mc(sym, ws, items, ctas=0):
+    """All-gather by multicast store (csrc/dp_reduce.cu).  ws: ark_b200.symm.SymmBuf holding the gathered buffers;
+    items: [(src tensor, byte offset of THIS rank's slot in ws)]."""
+    import numpy as np
+    n = len(items)
+    src = (ctypes.c_void_p * n)(*[t.data_ptr() for t, _ in items])
+    dst = (ctypes.c_void_p * n)(*[ws.mc + int(o) for _, o in items])
+    nb = np.ascontiguousarray([t.numel() * t.element_size() for t, _ in items], dtype=np.int64)
+    _contig(*[t for t, _ in items])
+    flags = (ctypes.c_void_p * sym.world)(*sym.peer_flags)
+    _C.lib().call("ark_dp_allgather_mc", src, dst, nb.ctypes.data_as(ctypes.c_void_p), n, flags, sym.rank, sym.world,
+                  int(ctas), _stream())
+
+
 def gru_wave_supported(d, bt0, nl) -> int:
     return int(_C.lib().raw("ark_gru_wave_supported")(int(d), int(bt0), int(nl)))
 

@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE workloads (`also` array)")
     ap.add_argument("--no-kernel-profile", action="store_true", help="skip the per-kernel timing pass (ncu runs)")
+    ap.add_argument("--timeline", default=None, help="PREFIX: dump the in-graph [tag, stream, start_ms, end_ms] of one replay per rank")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: YAML batch_size per GPU; strong: YAML batch_size split over the GPUs")
@@ -297,7 +298,7 @@ class Workload:
                 "api": "kgvae.model.models.ARK.ce_step(seq_cpu)" if dec_only else
                        "kgvae.model.models.SAIL.elbo_step(triples_cpu, seq_cpu, beta)"}
 
-    def kernel_profile(self, n_replays=6):
+    def kernel_profile(self, n_replays=6, timeline_path=None):
         """Per-kernel time inside the REPLAYED graph: a second capture of the same step with external event-record
         nodes around every op (SailEngine._timed), read back after each replay.  Falls back to eager per-op events
         (which include host launch gaps) for engines without a graphed step."""
@@ -315,6 +316,13 @@ class Workload:
                     self.step(i, graph=True)
                     eng.profile_summary(prof=eng.last_graph["prof"], agg=agg)
                     n += 1
+                if timeline_path:                       # [tag, stream, start_ms, end_ms] of the LAST replay, per rank
+                    pr = eng.last_graph["prof"]
+                    first = min(pr, key=lambda r: -r[1].elapsed_time(pr[0][1]))[1]
+                    rows = sorted(([t, eng.prof_stream.get(t, "main"), round(first.elapsed_time(a), 4), round(first.elapsed_time(b), 4)]
+                                   for t, a, b, _, _ in pr), key=lambda r: r[2])
+                    with open(f"{timeline_path}.rank{self.rank}.json", "w") as fh:
+                        json.dump(rows, fh)
                 if eng.prof:                            # eager side-stream work between graph segments (NCCL under DP)
                     eng.profile_summary(agg=agg)
             else:
@@ -417,7 +425,7 @@ def main():
 
     e2e = None if args.no_e2e else w.measure_e2e(args.steps, min(args.windows, 3))
 
-    agg, n_prof, mode = ({}, 1, "skipped") if args.no_kernel_profile else w.kernel_profile()
+    agg, n_prof, mode = ({}, 1, "skipped") if args.no_kernel_profile else w.kernel_profile(timeline_path=args.timeline)
     step_ms = total_ms / args.steps
     rows = kernel_table(agg, n_prof, step_ms, pk, args.workload if (args.model == "SAIL" and not args.dense and not args.batch) else "-",
                         dict(getattr(w.eng, "prof_stream", {})))

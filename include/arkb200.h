@@ -334,6 +334,30 @@ int ark_adam_flat(float* p, const float* g, float* m, float* v, uint16_t* shadow
 int ark_adam_flat_dyn(float* p, const float* g, float* m, float* v, uint16_t* shadow, int64_t n,
                       const float* hyper, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- K11: data-parallel gradient reduce-scatter + SHARDED Adam + parameter broadcast, one kernel over NVSwitch multicast ----
+ * Replaces, under data parallelism, `all-reduce(grad); optimizer.step()` (the reference has no multi-GPU path; the
+ * single-GPU statement is ablation_study.py:596-600).  The flat buffers of every rank live in one symmetric allocation that is
+ * also mapped as a multicast object: grad_mc / param_mc / shadow_mc are MULTICAST addresses of the f32 gradient, f32
+ * parameter and bf16 shadow buffers; param / m / v are this rank's own (unicast) buffers.  For each span [begin, end)
+ * (elements, multiples of 4; host arrays) rank r owns the r-th 1/world of it: it reads the SUM of all ranks' gradients
+ * with multimem.ld_reduce, applies Adam there (m, v are only maintained for owned slices) and multicasts the new
+ * parameters + bf16 copies to every rank.  mode 0: gradient all-reduce only (the sum is multicast back into grad).
+ * peer_flags: host array [world] of every rank's 512-byte zero-initialised flag block (peer-mapped addresses); the
+ * kernel exchanges "ready"/"done" epochs through them, so every rank must issue the same sequence of calls.
+ * hyper != NULL: step-dependent scalars in device memory as in ark_adam_flat_dyn.  ctas <= 0: default (32). */
+int ark_dp_reduce_adam(float* grad_mc, float* param_mc, uint16_t* shadow_mc, const float* param, float* m, float* v,
+                       uint32_t* const* peer_flags, int rank, int world, const int64_t* span_begin,
+                       const int64_t* span_end, int n_spans, int mode, float lr, float beta1, float beta2, float eps,
+                       int64_t step, const float* hyper, int ctas, void* stream);
+
+/* All-gather by multicast store (same symmetric-memory protocol and flag blocks as ark_dp_reduce_adam; the calls of both
+ * kinds must be issued in the same order on every rank, on one stream): item i = nbytes[i] bytes at src[i] (this rank's
+ * rows) written to dst_mc[i] = the MULTICAST address of this rank's slot in the gathered buffer, i.e. into every rank's
+ * copy.  Used for the [B, 3d] factors of the encoder-MLP weight gradients (dW = dY_all^T X_all).  src / dst_mc / nbytes:
+ * host arrays [n_items], n_items <= 8; 16-byte granularity.  ctas <= 0: default (16). */
+int ark_dp_allgather_mc(const void* const* src, void* const* dst_mc, const int64_t* nbytes, int n_items,
+                        uint32_t* const* peer_flags, int rank, int world, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -374,6 +374,8 @@ def main(argv=None):
                      "step_ms": 1e3 * dt / max(len(train_loader), 1)})
         if scheduler is not None:
             scheduler.step()
+        if world > 1:       # every rank: owners broadcast their slices of the (sharded) Adam state before rank 0 reads it
+            model.engine().gather_adam_state()
         if rank == 0:
             ckpt = {"epoch": epoch + 1, "model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
                     "optimizer_state_dict": optimizer.state_dict(),

@@ -78,6 +78,13 @@ def main():
             outs.append(fn(tri, seq, lay, eps, beta, n_tok_global=n_tok_g, batch_global=B * world).clone())
         torch.cuda.synchronize()
         res.append((torch.stack(outs), e.flat.param.clone()))
+        if e.mm is not None:        # multicast exchange: the Adam state is sharded until the owners broadcast it
+            e.gather_adam_state()
+            for buf in (e.flat.exp_avg, e.flat.exp_avg_sq):
+                ref = buf.clone()
+                dist.broadcast(ref, 0)
+                assert torch.equal(ref, buf), "Adam state differs between ranks after gather_adam_state()"
+            assert e.flat.exp_avg.abs().sum() > 0
         if graphed:
             nseg = len(next(iter(e._graphs.values()))["segs"])
             if e.capture_nccl:
@@ -93,7 +100,7 @@ def main():
     dist.broadcast(p, 0)
     if "DP_EMB_MIN_BYTES" not in os.environ:     # (the embedding gather's atomics are not bitwise reproducible)
         assert torch.equal(p, res[1][1]), "ranks diverged"
-    print(f"DP_CHECK ok rank {rank}/{world}: grad rel {rel:.2e}, segments {nseg}, graphed-vs-eager mismatches {bad:.4f}",
+    print(f"DP_CHECK ok rank {rank}/{world} ({'multicast' if e.mm is not None else 'NCCL'} exchange): grad rel {rel:.2e}, segments {nseg}, graphed-vs-eager mismatches {bad:.4f}",
           flush=True)
     dist.barrier()
     dist.destroy_process_group()
