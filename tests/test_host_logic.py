@@ -282,3 +282,19 @@ def test_bench_kernel_table_and_roofline_selection():
     assert ce["bound"] == "hbm" and abs(ce["achieved"] - 1.2e6 / (0.05e-3 / 3) / 1e9) < 1e-3
     if ("syn-types", "gru_persist_bwd") in bench.NCU_TRAFFIC:
         assert roof["traffic"] == bench.NCU_TRAFFIC[("syn-types", "gru_persist_bwd")][0]
+
+
+def test_multicast_exchange_slices_partition_every_span():
+    """ark_b200.symm.SymmFlat.owned mirrors the slice rule of csrc/dp_reduce.cu (rank r owns the r-th ceil(n4/world) vec4 block
+    of a span): the slices are disjoint, cover the span, stay 16-byte aligned — for ragged sizes and more ranks than vec4s."""
+    from ark_b200.symm import SymmFlat
+    for world in (2, 3, 4, 8, 16):
+        sym = SymmFlat.__new__(SymmFlat)
+        sym.world = world
+        for s, e in ((0, 4), (64, 64 + 4 * 7), (128, 128 + 4 * 1000003), (4096, 4096)):
+            sl = sym.owned(s, e)
+            assert len(sl) == world and sl[0][0] == s and sl[-1][1] == e
+            for (a, b), (c, _) in zip(sl, sl[1:] + [(e, e)]):
+                assert a <= b == c and a % 4 == 0 and b % 4 == 0
+            per = ((e - s) // 4 + world - 1) // world
+            assert all(b - a <= 4 * per for a, b in sl)
