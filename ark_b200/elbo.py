@@ -132,7 +132,7 @@ class SailEngine:
         self._upd = None                 # (mode, lr) while a train step is in flight: buckets are updated as they finish
         self._pending = []
         self._hold_comm, self._held = False, []   # see _comm_action: no NCCL next to the 128-CTA cooperative GRU kernels
-        self.prof = None
+        self.prof, self.prof_stream = None, {}
         self._capturing = False
         self._segment_break = None
         self._graphs = {}
