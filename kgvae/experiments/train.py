@@ -389,6 +389,8 @@ def main(argv=None):
             if (epoch + 1) % int(config.get("save_every", 10)) == 0:
                 torch.save(ckpt, os.path.join(run_dir, f"{tag}_checkpoint_epoch_{epoch + 1}.pt"),
                            _use_new_zipfile_serialization=False)
+        if world > 1:       # rank 0 alone validated / logged / saved: the others wait HERE, on the host, not inside the
+            torch.distributed.barrier()     # next step's exchange kernel (its cross-rank spin is bounded: csrc/dp_reduce.cu)
     if rank == 0:     # final evaluation (reference final_validation, ablation_study.py:190-346, minus the intelligraphs parts)
         final = {}
         splits = [("final_val", val_loader)] + ([("final_test", test_loader)] if config.get("use_test_for_final_eval") else [])
